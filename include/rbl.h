@@ -1,0 +1,157 @@
+/*
+ * rbl.h -- C ABI of the B200-native hot path of Rigid_Body_Light (librbl.so).
+ *
+ * The reference has no C ABI: its boundary is the nanobind class
+ * c_rigid.CManyBodies (/root/reference/src/c_rigid_obj.cpp:997-1027) consumed by
+ * /root/reference/src/Rigid.py.  This header is what a host class in ANY language
+ * binds instead of that C++ class; each entry point cites the reference member it
+ * replaces.  rigid_body_light_b200/csrc/c_rigid.cpp (pybind11) is the host class
+ * shipped here; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *  - `real` arrays are in the context's precision (RBL_F32 -> float, RBL_F64 -> double);
+ *  - host-pointer calls are synchronous: results are in the output buffer on return;
+ *  - rbl_dev_* calls take DEVICE pointers, enqueue on the context stream and return
+ *    immediately; rbl_sync() waits and reports deferred errors (blob below the wall);
+ *  - every call returns an rbl_status; rbl_last_error(ctx) holds the message;
+ *  - a context is bound to one CUDA device and is not thread-safe;
+ *  - there is no CPU fallback: without a CUDA device rbl_create fails.
+ */
+#ifndef RBL_H
+#define RBL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbl_ctx rbl_ctx;
+
+typedef enum {
+  RBL_OK = 0,
+  RBL_ERR_INVALID = 1,    /* bad argument / size */
+  RBL_ERR_CUDA = 2,       /* CUDA runtime error (message has the cudaError string) */
+  RBL_ERR_BELOW_WALL = 3, /* a blob centre has z < 0 with the wall on (c_rigid_obj.cpp:95-97) */
+  RBL_ERR_SINGULAR = 4,   /* K^T K singular (:313-316) or a PC block not SPD */
+  RBL_ERR_STATE = 5,      /* parameters / configuration not set yet */
+  RBL_ERR_NOMEM = 6
+} rbl_status;
+
+enum { RBL_F32 = 4, RBL_F64 = 8 };
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* precision: RBL_F32 or RBL_F64 (the reference picks it at compile time,
+ * eigen_defines.h:5-37); device: CUDA ordinal, or -1 for the current device. */
+int rbl_create(int precision, int device, rbl_ctx** out);
+void rbl_destroy(rbl_ctx* ctx);
+const char* rbl_last_error(const rbl_ctx* ctx); /* ctx may be NULL: last create error */
+int rbl_precision(const rbl_ctx* ctx);
+int rbl_sm_count(const rbl_ctx* ctx);
+const char* rbl_version(void);
+
+/* ---- state: CManyBodies setters/getters (host pointers) --------------------------- */
+/* setParameters (:183-195): stores a, dt, kBT, eta and the MEAN-REMOVED ref config
+ * (n_blb x 3, row-major). */
+int rbl_set_parameters(rbl_ctx* ctx, double a, double dt, double kBT, double eta,
+                       const void* ref_cfg, int n_blb);
+/* setBlkPC / setWallPC (:197-199).  `wall` gates the wall correction of BOTH the
+ * preconditioner and apply_M, like PC_wall in the reference. */
+int rbl_set_flags(rbl_ctx* ctx, int block_pc, int wall);
+/* setConfig (:201-233): X 3*n_bod, Q 4*n_bod as [w,x,y,z]; quaternions are normalised.
+ * Like the reference it does NOT invalidate an already built preconditioner. */
+int rbl_set_config(rbl_ctx* ctx, const void* X, const void* Q, int n_bod);
+/* getConfig (:235-255) */
+int rbl_get_config(rbl_ctx* ctx, void* X, void* Q);
+/* set_K_mats (:395-402): refreshes the cached blob positions / lever arms K is made of */
+int rbl_set_K_mats(rbl_ctx* ctx);
+int rbl_n_bodies(const rbl_ctx* ctx);
+int rbl_blobs_per_body(const rbl_ctx* ctx);
+
+/* ---- operators (host pointers) ---------------------------------------------------- */
+/* multi_body_pos (:295-300): out 3*N, blob-major xyz */
+int rbl_blob_positions(rbl_ctx* ctx, void* out);
+/* K_x_U (:404): U 6*n_bod -> out 3*N */
+int rbl_K_dot(rbl_ctx* ctx, const void* U, void* out);
+/* KT_x_Lam (:410): lambda 3*N -> out 6*n_bod */
+int rbl_KT_dot(rbl_ctx* ctx, const void* lambda, void* out);
+/* Kinv_x_V (:406) and KTinv_x_F (:408) */
+int rbl_Kinv_dot(rbl_ctx* ctx, const void* V, void* out);
+int rbl_KTinv_dot(rbl_ctx* ctx, const void* F, void* out);
+/* apply_M (:641-659): U = M F, or B M B F with the wall; n_blobs is free (it need not
+ * equal n_bod*n_blb, tests/test_interface.py:171-177). F, r, out: 3*n_blobs */
+int rbl_apply_M(rbl_ctx* ctx, const void* F, const void* r, int n_blobs, void* out);
+/* apply_PC (:589-616): in/out 3*N + 6*n_bod, exact inverse of [Mt -K; -K^T 0] */
+int rbl_apply_PC(rbl_ctx* ctx, const void* in, void* out);
+/* RigidBody.apply_saddle (Rigid.py:73-80): out = [M lam - K U ; K^T lam], fused on device */
+int rbl_apply_saddle(rbl_ctx* ctx, const void* x, void* out);
+/* evolve_X_Q (:865-878): U 6*n_bod (velocities; multiplied by dt inside), rebuilds K,
+ * invalidates the preconditioner */
+int rbl_evolve(rbl_ctx* ctx, const void* U);
+/* get_K / get_Kinv (:978-992) as CSC arrays.  K is 3N x 6n_bod with 9 stored entries per
+ * blob (indptr 6*n_bod+1, indices/data 9*N); Kinv is 6n_bod x 3N with 4 stored entries
+ * per column (indptr 3*N+1, indices/data 12*N; a computed entry that happens to be
+ * exactly zero is kept, the reference's .pruned() would drop it). */
+int rbl_export_K_csc(rbl_ctx* ctx, int64_t* indptr, int32_t* indices, void* data);
+int rbl_export_Kinv_csc(rbl_ctx* ctx, int64_t* indptr, int32_t* indices, void* data);
+
+/* ---- Krylov drivers (absent from the reference) --------------------- */
+/* Right-preconditioned restarted GMRES on the saddle system  A x = rhs  with
+ * A = apply_saddle and preconditioner P^-1 = apply_PC composed with the sign flip that
+ * maps the reference's two conventions onto each other.
+ * rhs/x: 3N+6n_bod.  Returns iterations in *iters and ||r||/||rhs|| in *relres. */
+int rbl_gmres(rbl_ctx* ctx, const void* rhs, void* x, double tol, int restart, int max_iter,
+              int* iters, double* relres);
+/* out = (B M B)^{1/2} W by Lanczos (replaces the dense Cholesky of M_half_W, :661-675).
+ * W, out: 3*N.  tol is the relative change of the iterate. */
+int rbl_lanczos_sqrt(rbl_ctx* ctx, const void* W, void* out, double tol, int max_iter,
+                     int* iters);
+
+/* ---- device-resident API (device pointers, asynchronous on the context stream) ---- */
+/* Targets [tgt_first, tgt_first+n_tgt) of the n_blobs sources: out has 3*n_tgt reals.
+ * This is the entry a multi-GPU host shards by body range. */
+int rbl_dev_apply_M(rbl_ctx* ctx, const void* dF, const void* dr, int n_blobs, int tgt_first,
+                    int n_tgt, void* dout);
+int rbl_dev_blob_positions(rbl_ctx* ctx, void* dout);
+int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout);
+int rbl_dev_KT_dot(rbl_ctx* ctx, const void* dlambda, void* dout);
+int rbl_dev_apply_PC(rbl_ctx* ctx, const void* din, void* dout);
+int rbl_dev_apply_saddle(rbl_ctx* ctx, const void* dx, void* dout);
+int rbl_sync(rbl_ctx* ctx);
+/* the context's cudaStream_t (as void*); set_stream lets a host share its own stream */
+void* rbl_stream(rbl_ctx* ctx);
+int rbl_set_stream(rbl_ctx* ctx, void* cuda_stream);
+
+/* ---- memory + timing helpers (so a C/C++ host needs nothing but this header) ------- */
+int rbl_dev_alloc(rbl_ctx* ctx, size_t bytes, void** dptr);
+int rbl_dev_free(rbl_ctx* ctx, void* dptr);
+int rbl_pinned_alloc(rbl_ctx* ctx, size_t bytes, void** hptr);
+int rbl_pinned_free(rbl_ctx* ctx, void* hptr);
+int rbl_memcpy_h2d(rbl_ctx* ctx, void* dst, const void* src, size_t bytes);
+int rbl_memcpy_d2h(rbl_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* CUDA-event timer on the context stream */
+int rbl_timer_start(rbl_ctx* ctx);
+int rbl_timer_stop(rbl_ctx* ctx, double* elapsed_ms);
+/* writes more than L2 (126 MB) so the next timed call starts cold */
+int rbl_flush_l2(rbl_ctx* ctx);
+
+/* ---- tuning + measurement ------------------------------------------------------------ */
+int rbl_num_matvec_variants(const rbl_ctx* ctx);
+/* targets per thread and threads per CTA of variant idx */
+int rbl_matvec_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
+int rbl_set_matvec_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t rbl_launch_count(const rbl_ctx* ctx);
+/* average duration (ms, CUDA events around the kernel alone) of the matvec kernel over
+ * the launches since the last reset; enable/disable with rbl_profile_matvec */
+int rbl_profile_matvec(rbl_ctx* ctx, int enable);
+int rbl_matvec_profile(rbl_ctx* ctx, double* avg_ms, int64_t* launches, int reset);
+/* sustained FMA-pipe peak of this precision (TFLOP/s), the roofline denominator */
+int rbl_fma_peak(rbl_ctx* ctx, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBL_H */

@@ -1,0 +1,417 @@
+"""CPU oracle for the Rigid_Body_Light hot path -- TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``rigid_body_light_b200/`` or ``Rigid/`` may import this module.
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do, as the checker or the reported CPU
+baseline, never as the product path.
+
+What it restates (citations are into /root/reference/src/):
+
+* the O(N^2) pair arithmetic lives in ``rbl_oracle.c`` (c_rigid_obj.cpp:31-142,
+  413-459, 618-659) and is reached through ctypes;
+* everything O(N) around it is plain numpy float64 below, one function per
+  reference member function, each citing the lines it follows.
+
+Pinning status: the two pair kernels are pinned bit-for-bit against the
+reference's own source compiled into ``oracle/_ref`` (tests/test_oracle_vs_ref.py)
+and blob placement against scipy's ``Rotation`` exactly like the reference's
+tests/test_interface.py:55-73.  The reference holds no golden values for M.F, K,
+K^T or the preconditioner: for those, parity is "unpinned by
+the reference" and defended by the physics checks in tests/test_oracle_physics.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and oracle/_ref when /root/reference exists)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = [os.path.join(_HERE, f) for f in ("rbl_oracle.c", "oracle_impl.inc")]
+    stale = force or not os.path.exists(so) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in src
+    )
+    need_ref = os.path.exists("/root/reference/src/c_rigid_obj.cpp") and not os.path.exists(
+        os.path.join(_HERE, "_ref", "libref_pair.so")
+    )
+    if stale or need_ref:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        _LIB = ctypes.CDLL(os.path.join(_HERE, "liboracle.so"))
+        _declare(_LIB)
+    return _LIB
+
+
+def ref_pair_lib():
+    """The reference's own pair kernels (oracle/_ref/libref_pair.so) or None."""
+    global _REF
+    if _REF is None:
+        p = os.path.join(_HERE, "_ref", "libref_pair.so")
+        if not os.path.exists(p):
+            build()
+        if not os.path.exists(p):
+            return None
+        _REF = ctypes.CDLL(p)
+        for sfx, ct in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
+            f = getattr(_REF, f"ref_rpy_pair_{sfx}")
+            f.argtypes = [ct, ct, ct, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ct]
+            f.restype = None
+            g = getattr(_REF, f"ref_wall_pair_{sfx}")
+            g.argtypes = [ct, ct, ct, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ct]
+            g.restype = ctypes.c_int
+    return _REF
+
+
+_CT = {np.dtype(np.float64): ("f64", ctypes.c_double), np.dtype(np.float32): ("f32", ctypes.c_float)}
+
+
+def _declare(L):
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    for sfx, ct in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
+        getattr(L, f"orc_dense_mobility_{sfx}").argtypes = [vp, ci, ct, ct, ci, vp]
+        getattr(L, f"orc_apply_M_dense_{sfx}").argtypes = [vp, vp, ci, ct, ct, ci, vp]
+        getattr(L, f"orc_apply_M_rows_{sfx}").argtypes = [vp, vp, ci, ct, ct, ci, vp, ci, ci, vp]
+        getattr(L, f"orc_pair_block_{sfx}").argtypes = [vp, ci, ci, ct, ci, vp]
+        getattr(L, f"orc_damp_{sfx}").argtypes = [vp, ci, ct, vp]
+        getattr(L, f"orc_damp_{sfx}").restype = None
+    L.orc_num_threads.restype = ci
+
+
+class OracleError(RuntimeError):
+    """Raised where the reference throws (blob below the wall) or exit()s (overlap)."""
+
+
+def _check(err):
+    if err == 1:
+        raise OracleError("two blobs overlap (reference calls exit(), c_rigid_obj.cpp:53-58)")
+    if err == 2:
+        raise OracleError("A blob has its center below the wall (z<0) (c_rigid_obj.cpp:95-97)")
+    if err:
+        raise MemoryError("oracle: allocation failed")
+
+
+def _prep(x, dtype):
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype).reshape(-1))
+
+
+# --------------------------------------------------------------------------- #
+# O(N^2) mobility (ctypes into rbl_oracle.c)
+# --------------------------------------------------------------------------- #
+def dense_mobility(r, a, eta, wall, dtype=np.float64):
+    """rotne_prager_tensor (c_rigid_obj.cpp:413-459): dense 3N x 3N matrix."""
+    r = _prep(r, dtype)
+    n = r.size // 3
+    sfx, _ = _CT[np.dtype(dtype)]
+    M = np.empty((3 * n, 3 * n), dtype=dtype, order="F")
+    _check(getattr(lib(), f"orc_dense_mobility_{sfx}")(r.ctypes.data, n, a, eta, int(wall), M.ctypes.data))
+    return M
+
+
+def apply_M_dense(F, r, a, eta, wall, dtype=np.float64):
+    """apply_M exactly as the reference runs it (c_rigid_obj.cpp:641-659):
+    dense assembly + GEMV, single thread.  This is the timed CPU baseline."""
+    F = _prep(F, dtype)
+    r = _prep(r, dtype)
+    n = r.size // 3
+    sfx, _ = _CT[np.dtype(dtype)]
+    U = np.empty(3 * n, dtype=dtype)
+    _check(getattr(lib(), f"orc_apply_M_dense_{sfx}")(F.ctypes.data, r.ctypes.data, n, a, eta, int(wall), U.ctypes.data))
+    return U
+
+
+def apply_M(F, r, a, eta, wall, rows=None, dtype=np.float64):
+    """Matrix-free rows of the same matrix (long-double row sums for float64).
+    ``rows`` = None (all), an int array of target blob indices, or (row0, nrows)."""
+    F = _prep(F, dtype)
+    r = _prep(r, dtype)
+    n = r.size // 3
+    sfx, _ = _CT[np.dtype(dtype)]
+    fn = getattr(lib(), f"orc_apply_M_rows_{sfx}")
+    if rows is None:
+        rows = (0, n)
+    if isinstance(rows, tuple):
+        row0, nrows = rows
+        U = np.empty(3 * nrows, dtype=dtype)
+        _check(fn(F.ctypes.data, r.ctypes.data, n, a, eta, int(wall), None, row0, nrows, U.ctypes.data))
+    else:
+        idx = np.ascontiguousarray(rows, dtype=np.int32)
+        U = np.empty(3 * idx.size, dtype=dtype)
+        _check(fn(F.ctypes.data, r.ctypes.data, n, a, eta, int(wall), idx.ctypes.data, 0, idx.size, U.ctypes.data))
+    return U
+
+
+def pair_block(r, i, j, a, wall, dtype=np.float64):
+    """One upper-triangular block as rotne_prager_tensor's loop evaluates it (:432-447)."""
+    r = _prep(r, dtype)
+    sfx, _ = _CT[np.dtype(dtype)]
+    B = np.empty(9, dtype=dtype)
+    _check(getattr(lib(), f"orc_pair_block_{sfx}")(r.ctypes.data, i, j, a, int(wall), B.ctypes.data))
+    return B.reshape(3, 3)
+
+
+def damp_diag(r, a):
+    """make_damp_mat (c_rigid_obj.cpp:618-639): per-blob B_ii = min(1, z/a) (3N)."""
+    r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
+    d = np.where(r[:, 2] >= a, 1.0, r[:, 2] / a)
+    return np.repeat(d, 3)
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+# --------------------------------------------------------------------------- #
+# O(N) rigid-body pieces (numpy float64)
+# --------------------------------------------------------------------------- #
+def remove_mean(cfg):
+    """removeMean (c_rigid_obj.cpp:176-181)."""
+    cfg = np.asarray(cfg, dtype=np.float64).reshape(-1, 3)
+    return cfg - cfg.mean(axis=0)
+
+
+def normalize_quats(Q):
+    """setConfig normalises each quaternion (c_rigid_obj.cpp:212-216); layout [w,x,y,z]."""
+    Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+    return Q / np.linalg.norm(Q, axis=1, keepdims=True)
+
+
+def rotation_matrices(Q):
+    """Eigen Quaternion::toRotationMatrix for unit quaternions stored [w,x,y,z]
+    (used at c_rigid_obj.cpp:258,308)."""
+    Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+    w, x, y, z = Q[:, 0], Q[:, 1], Q[:, 2], Q[:, 3]
+    R = np.empty((Q.shape[0], 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - w * z)
+    R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y)
+    R[:, 2, 1] = 2 * (y * z + w * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def blob_positions(X, Q, ref_cfg):
+    """get_r_vecs ... multi_body_pos (c_rigid_obj.cpp:257-300):
+    r_{b,k} = R(q_b) ref_k + X_b, body-major.  ``ref_cfg`` already mean-removed,
+    ``Q`` already normalised.  Returns (N_bod*N_blb, 3)."""
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+    R = rotation_matrices(Q)
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    r = np.einsum("bij,kj->bki", R, ref) + X[:, None, :]
+    return r.reshape(-1, 3)
+
+
+def _rho(r, X, n_blb):
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+    return np.asarray(r, dtype=np.float64).reshape(X.shape[0], n_blb, 3) - X[:, None, :]
+
+
+def K_dot(U, r, X, n_blb):
+    """K_x_U (c_rigid_obj.cpp:404) with K's entries from :368-383:
+    (K U)_k = u_b + omega_b x (r_k - X_b)."""
+    U = np.asarray(U, dtype=np.float64).reshape(-1, 6)
+    rho = _rho(r, X, n_blb)
+    out = U[:, None, :3] + np.cross(U[:, None, 3:], rho)
+    return out.reshape(-1)
+
+
+def KT_dot(lam, r, X, n_blb):
+    """KT_x_Lam (c_rigid_obj.cpp:410): F_b = sum_k lam_k, T_b = sum_k rho_k x lam_k."""
+    rho = _rho(r, X, n_blb)
+    lam = np.asarray(lam, dtype=np.float64).reshape(rho.shape)
+    F = lam.sum(axis=1)
+    T = np.cross(rho, lam).sum(axis=1)
+    return np.concatenate([F, T], axis=1).reshape(-1)
+
+
+def K_dense(r, X, n_blb):
+    """Make_K_Kinv's K (c_rigid_obj.cpp:368-383) as a dense (3N, 6N_bod) array."""
+    rho = _rho(r, X, n_blb)
+    nb = rho.shape[0]
+    K = np.zeros((3 * nb * n_blb, 6 * nb))
+    for b in range(nb):
+        for k in range(n_blb):
+            row = 3 * (b * n_blb + k)
+            rx, ry, rz = rho[b, k]
+            K[row:row + 3, 6 * b:6 * b + 3] = np.eye(3)
+            K[row + 0, 6 * b + 4] = rz
+            K[row + 0, 6 * b + 5] = -ry
+            K[row + 1, 6 * b + 5] = rx
+            K[row + 1, 6 * b + 3] = -rz
+            K[row + 2, 6 * b + 3] = ry
+            K[row + 2, 6 * b + 4] = -rx
+    return K
+
+
+def KTK_inv_blocks(Q, ref_cfg):
+    """block_KTKinv (c_rigid_obj.cpp:302-326): per body diag(I/N_blb, S),
+    S = (sum|ref|^2 I - R (sum ref ref^T) R^T)^-1; off-diagonal blocks dropped."""
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    n_blb = ref.shape[0]
+    sumr2 = (ref * ref).sum()
+    moi = ref.T @ ref
+    R = rotation_matrices(Q)
+    out = np.zeros((R.shape[0], 6, 6))
+    for b in range(R.shape[0]):
+        D = sumr2 * np.eye(3) - R[b] @ moi @ R[b].T
+        if np.linalg.det(D) < 1e-13:
+            raise OracleError("K^T K is singular (reference exit()s, c_rigid_obj.cpp:313-316)")
+        out[b, :3, :3] = np.eye(3) / n_blb
+        out[b, 3:, 3:] = np.linalg.inv(D)
+    return out
+
+
+def Kinv_dense(r, X, Q, ref_cfg):
+    """Kinv = (K^T K)^-1 K^T (c_rigid_obj.cpp:388-390), dense (6N_bod, 3N)."""
+    ref = np.asarray(ref_cfg).reshape(-1, 3)
+    K = K_dense(r, X, ref.shape[0])
+    blk = KTK_inv_blocks(Q, ref)
+    nb = blk.shape[0]
+    G = np.zeros((6 * nb, 6 * nb))
+    for b in range(nb):
+        G[6 * b:6 * b + 6, 6 * b:6 * b + 6] = blk[b]
+    return G @ K.T
+
+
+def diag_invM(r, a, eta, wall):
+    """diag_invM (c_rigid_obj.cpp:489-543): per blob inverse of the 3x3
+    self-mobility (4/3 I + wall self term), times 8 pi eta a.  Returns (N,3,3)."""
+    r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
+    n = r.shape[0]
+    out = np.empty((n, 3, 3))
+    for i in range(n):
+        B = np.eye(3) * (4.0 / 3.0)
+        if wall:
+            h = r[i, 2] / a
+            if h < 0:
+                raise OracleError("A blob has its center below the wall (z<0)")
+            inv = 1.0 / h
+            i3 = inv ** 3
+            i5 = i3 * inv * inv
+            B[0, 0] += -(9 * inv - 2 * i3 + i5) / 12.0
+            B[1, 1] += -(9 * inv - 2 * i3 + i5) / 12.0
+            B[2, 2] += -(9 * inv - 4 * i3 + i5) / 6.0
+        out[i] = np.linalg.inv(B) * (8.0 * np.pi * eta * a)
+    return out
+
+
+def block_invM(X, Q, ref_cfg, a, eta, wall):
+    """Block_diag_invM (c_rigid_obj.cpp:461-487): per body, inverse of the dense
+    RPY(+wall) matrix of that body's blobs alone.  Returns (N_bod, 3N_blb, 3N_blb)."""
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+    Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+    nb = X.shape[0]
+    sz = 3 * ref.shape[0]
+    out = np.empty((nb, sz, sz))
+    for b in range(nb):
+        rb = blob_positions(X[b:b + 1], Q[b:b + 1], ref)
+        out[b] = np.linalg.inv(np.asarray(dense_mobility(rb, a, eta, wall)))
+    return out
+
+
+class PC:
+    """apply_PC (c_rigid_obj.cpp:589-616) with its lazily built state
+    (:591-596): invM (diag :489-543 or block :461-487), Ninv = K^T invM K per body
+    (:593) and its Cholesky solve (:554-567, :605-608).  M_scale = 1 (:194)."""
+
+    def __init__(self, X, Q, ref_cfg, a, eta, wall, block):
+        self.ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+        self.n_blb = self.ref.shape[0]
+        self.X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+        self.Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+        self.nb = self.X.shape[0]
+        self.r = blob_positions(self.X, self.Q, self.ref)
+        sz = 3 * self.n_blb
+        if block:
+            self.invM = block_invM(self.X, self.Q, self.ref, a, eta, wall)
+        else:
+            d = diag_invM(self.r, a, eta, wall)
+            self.invM = np.zeros((self.nb, sz, sz))
+            for b in range(self.nb):
+                for k in range(self.n_blb):
+                    self.invM[b, 3 * k:3 * k + 3, 3 * k:3 * k + 3] = d[b * self.n_blb + k]
+        Kd = K_dense(self.r, self.X, self.n_blb)
+        self.Kb = [Kd[sz * b:sz * (b + 1), 6 * b:6 * b + 6] for b in range(self.nb)]
+        self.Ninv = [self.Kb[b].T @ self.invM[b] @ self.Kb[b] for b in range(self.nb)]
+
+    def apply(self, IN):
+        IN = np.asarray(IN, dtype=np.float64).reshape(-1)
+        sz = 3 * self.n_blb
+        n3 = sz * self.nb
+        slip = IN[:n3]
+        F = IN[n3:]
+        lam = np.empty(n3)
+        U = np.empty(6 * self.nb)
+        for b in range(self.nb):
+            s = slip[sz * b:sz * (b + 1)]
+            rhs = -F[6 * b:6 * b + 6] - self.Kb[b].T @ (self.invM[b] @ s)  # :601
+            L = np.linalg.cholesky(self.Ninv[b])                            # :562
+            u = np.linalg.solve(L.T, np.linalg.solve(L, rhs))               # :607
+            U[6 * b:6 * b + 6] = u
+            lam[sz * b:sz * (b + 1)] = self.invM[b] @ (s + self.Kb[b] @ u)  # :610
+        return np.concatenate([lam, U])
+
+
+def apply_saddle(x, X, Q, ref_cfg, a, eta, wall):
+    """RigidBody.apply_saddle (Rigid.py:73-80): [M lam - K U ; K^T lam]."""
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    n_blb = ref.shape[0]
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+    r = blob_positions(X, Q, ref)
+    n3 = 3 * r.shape[0]
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    lam, U = x[:n3], x[n3:]
+    slip = apply_M(lam, r, a, eta, wall) - K_dot(U, r, X, n_blb)
+    return np.concatenate([slip, KT_dot(lam, r, X, n_blb)])
+
+
+def quat_mul(p, q):
+    """Hamilton product p*q for arrays stored [w,x,y,z] (Eigen operator*, :704)."""
+    pw, px, py, pz = p[..., 0], p[..., 1], p[..., 2], p[..., 3]
+    qw, qx, qy, qz = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    return np.stack([
+        pw * qw - px * qx - py * qy - pz * qz,
+        pw * qx + px * qw + py * qz - pz * qy,
+        pw * qy - px * qz + py * qw + pz * qx,
+        pw * qz + px * qy - py * qx + pz * qw,
+    ], axis=-1)
+
+
+def update_X_Q(X, Q, disp):
+    """update_X_Q + Q_from_Om (c_rigid_obj.cpp:679-710): ``disp`` already has
+    units of displacement ([u(3), omega(3)] * dt per body)."""
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+    Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+    d = np.asarray(disp, dtype=np.float64).reshape(-1, 6)
+    om = d[:, 3:]
+    th = np.linalg.norm(om, axis=1)
+    qrot = np.zeros_like(Q)
+    qrot[:, 0] = np.cos(th / 2)
+    big = th > 1e-10
+    qrot[big, 1:] = (np.sin(th[big] / 2) / th[big])[:, None] * om[big]
+    qrot /= np.linalg.norm(qrot, axis=1, keepdims=True)
+    Qn = quat_mul(qrot, Q)
+    Qn /= np.linalg.norm(Qn, axis=1, keepdims=True)
+    return X + d[:, :3], Qn
+
+
+def evolve(X, Q, U, dt):
+    """evolve_X_Q (c_rigid_obj.cpp:865-878): U *= dt, then update_X_Q."""
+    return update_X_Q(X, Q, np.asarray(U, dtype=np.float64) * dt)

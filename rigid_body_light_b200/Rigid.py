@@ -1,0 +1,152 @@
+"""``RigidBody`` -- the Python API of Rigid_Body_Light on the B200-native host class.
+
+Mirror of /root/reference/src/Rigid.py:5-135: same constructor signature, same method
+names, argument meaning, return shapes and ``RuntimeError`` conditions, so code and tests
+written against the reference run unchanged.  Differences, all additive:
+
+* ``precision=`` keyword (default: the module default, like the reference's compile-time
+  choice) selects the float or double host class per object;
+* ``apply_saddle`` calls the fused device operator instead of composing four host calls
+  (same result: [M lam - K U ; K^T lam], Rigid.py:73-80);
+* ``Kinv_dot`` / ``KTinv_dot`` / ``gmres`` / ``brownian_sqrt`` expose operators the
+  reference keeps unbound or leaves to the user.
+"""
+import numpy as np
+
+from . import c_rigid as crigid
+
+
+def _count(x):
+    return int(np.prod(np.shape(x)))
+
+
+class RigidBody:
+    X_shape = None
+    Q_shape = None
+
+    def __init__(self, rigid_config, X, Q, a, eta, dt, wall_PC=False, block_PC=False, precision=None):
+        rigid_config = np.asarray(rigid_config)
+        if rigid_config.size % 3 != 0:
+            raise RuntimeError(
+                f"Rigid config must have length 3N. Rigid config shape: {rigid_config.shape}"
+            )
+        self.cb = crigid.host_class(precision)()
+        self.precision = self.cb.precision
+        self.blobs_per_body = rigid_config.size // 3
+        kbt = 1.0  # the reference hard-wires kBT = 1 here too (Rigid.py:23)
+        self.cb.setParameters(a, dt, kbt, eta, rigid_config)
+        self.cb.setBlkPC(block_PC)
+        self.cb.setWallPC(wall_PC)
+        self.set_config(X, Q)
+
+    # -- configuration ---------------------------------------------------------------
+    def set_config(self, X, Q):
+        X = np.asarray(X)
+        Q = np.asarray(Q)
+        nx, rx = divmod(_count(X), 3)
+        nq, rq = divmod(_count(Q), 4)
+        if rx:
+            raise RuntimeError("X must have total length 3N")
+        if rq:
+            raise RuntimeError("Q must have total length 4N")
+        if nx != nq:
+            raise RuntimeError("X and Q must have the same number of bodies")
+        self.N_bodies = nx
+        self.X_shape = X.shape
+        self.Q_shape = Q.shape
+        self.cb.setConfig(X.reshape(-1), Q.reshape(-1))
+        self.cb.set_K_mats()
+        self.total_blobs = self.N_bodies * self.blobs_per_body
+
+    def get_config(self):
+        X, Q = self.cb.getConfig()
+        return X.reshape(self.X_shape), Q.reshape(self.Q_shape)
+
+    def _like_X(self, flat):
+        return np.asarray(flat).reshape((-1, 3) if len(self.X_shape) == 2 else (-1))
+
+    def get_blob_positions(self):
+        return self._like_X(self.cb.multi_body_pos())
+
+    # -- operators -------------------------------------------------------------------
+    def KT_dot(self, lambda_vec):
+        lambda_vec = np.asarray(lambda_vec)
+        self._need(lambda_vec, 3 * self.total_blobs, "lambda", "3*N_blobs")
+        return self._like_X(self.cb.KT_x_Lam(lambda_vec.reshape(-1)))
+
+    def K_dot(self, U):
+        U = np.asarray(U)
+        self._need(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        return self._like_X(self.cb.K_x_U(U.reshape(-1)))
+
+    def apply_PC(self, b):
+        b = np.asarray(b)
+        self._need_system(b)
+        return self.cb.apply_PC(b.reshape(-1))
+
+    def apply_saddle(self, x):
+        x = np.asarray(x)
+        self._need_system(x)
+        return self.cb.apply_saddle(x.reshape(-1))
+
+    def apply_M(self, forces, positions):
+        forces = np.asarray(forces)
+        positions = np.asarray(positions)
+        if np.size(positions) != np.size(forces):
+            raise RuntimeError("Positions and forces must be of the same size")
+        if np.size(positions) % 3 != 0:
+            raise RuntimeError(
+                "Positions and forces must have total length 3N, where N is the number of blobs"
+            )
+        return self.cb.apply_M(forces.reshape(-1), positions.reshape(-1))
+
+    def get_K(self):
+        return self.cb.get_K()
+
+    def get_Kinv(self):
+        return self.cb.get_Kinv()
+
+    def evolve_rigid_bodies(self, U):
+        U = np.asarray(U)
+        self._need(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        self.cb.evolve_X_Q(U.reshape(-1))
+
+    # -- extensions (not in the reference's Python API) ---------------------------------
+    def Kinv_dot(self, V):
+        V = np.asarray(V)
+        self._need(V, 3 * self.total_blobs, "V", "3*N_blobs")
+        return self._like_X(self.cb.Kinv_x_V(V.reshape(-1)))
+
+    def KTinv_dot(self, F):
+        F = np.asarray(F)
+        self._need(F, 6 * self.N_bodies, "F", "6*N_bodies")
+        return self._like_X(self.cb.KTinv_x_F(F.reshape(-1)))
+
+    def gmres(self, rhs, tol=1e-8, restart=60, max_iter=300):
+        """Solve apply_saddle(x) = rhs on the device, preconditioned with apply_PC.
+        Returns (x, iterations, relative residual)."""
+        rhs = np.asarray(rhs)
+        self._need_system(rhs)
+        return self.cb.gmres(rhs.reshape(-1), tol, restart, max_iter)
+
+    def brownian_sqrt(self, W, tol=1e-6, max_iter=100):
+        """(B M B)^{1/2} W by Lanczos over the device mobility product.
+        Returns (vector, iterations)."""
+        W = np.asarray(W)
+        self._need(W, 3 * self.total_blobs, "W", "3*N_blobs")
+        return self.cb.lanczos_sqrt(W.reshape(-1), tol, max_iter)
+
+    # -- size checks (RuntimeError like Rigid.py:117-135) -------------------------------
+    def _need(self, vec, n, name, what):
+        if vec.size != n:
+            raise RuntimeError(
+                f"{name} must have total size {what} = {n}. {name} shape: {vec.shape}"
+            )
+
+    def _need_system(self, vec):
+        n = 3 * self.total_blobs + 6 * self.N_bodies
+        if vec.size != n:
+            raise RuntimeError(
+                "Rigid system input vector must have total size 3*N_blobs + 6*N_bodies = "
+                f"{n}. system_input shape: {vec.shape}"
+            )

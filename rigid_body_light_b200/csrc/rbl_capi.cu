@@ -1,0 +1,1058 @@
+// rbl_capi.cu -- context object + the C ABI of include/rbl.h.
+//
+// The context owns what CManyBodies owns in the reference
+// (/root/reference/src/c_rigid_obj.cpp:144-168): parameters, reference configuration,
+// X_n/Q_n, the K data (here: cached blob positions) and the lazily built preconditioner
+// -- but resident in HBM.  Host-pointer entry points stage through device buffers and
+// call the same device path the rbl_dev_* entry points expose.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/rbl.h"
+#include "rbl_krylov.cuh"
+#include "rbl_matvec.cuh"
+#include "rbl_rigid.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  ~DevBuf() { release(); }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct rbl_ctx {
+  int precision = 0;
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+  virtual ~rbl_ctx() {}
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  // virtual interface (void* = real* of the context's precision)
+  virtual int set_parameters(double a, double dt, double kBT, double eta, const void* cfg, int n_blb) = 0;
+  virtual int set_flags(int block_pc, int wall) = 0;
+  virtual int set_config(const void* X, const void* Q, int n_bod) = 0;
+  virtual int get_config(void* X, void* Q) = 0;
+  virtual int set_K_mats() = 0;
+  virtual int n_bodies() const = 0;
+  virtual int blobs_per_body() const = 0;
+  virtual int blob_positions(void* out, bool dev) = 0;
+  virtual int K_dot(const void* U, void* out, bool dev) = 0;
+  virtual int KT_dot(const void* lam, void* out, bool dev) = 0;
+  virtual int Kinv_dot(const void* V, void* out) = 0;
+  virtual int KTinv_dot(const void* F, void* out) = 0;
+  virtual int apply_M(const void* F, const void* r, int n, void* out) = 0;
+  virtual int dev_apply_M(const void* F, const void* r, int n, int t0, int nt, void* out) = 0;
+  virtual int apply_PC(const void* in, void* out, bool dev) = 0;
+  virtual int apply_saddle(const void* x, void* out, bool dev) = 0;
+  virtual int evolve(const void* U) = 0;
+  virtual int export_K(int64_t* indptr, int32_t* indices, void* data) = 0;
+  virtual int export_Kinv(int64_t* indptr, int32_t* indices, void* data) = 0;
+  virtual int gmres(const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) = 0;
+  virtual int lanczos(const void* W, void* out, double tol, int max_iter, int* iters) = 0;
+  virtual int sync() = 0;
+  virtual int fma_peak(int iters, double* tflops) = 0;
+  virtual int num_variants() const = 0;
+  virtual int variant_info(int idx, int* T, int* threads) const = 0;
+
+  // shared plumbing
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  int64_t launches = 0;
+  int variant = -1;
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  DevBuf flush_buf;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return this->fail(e_ == cudaErrorMemoryAllocation ? RBL_ERR_NOMEM : RBL_ERR_CUDA,  \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+// a launcher that enqueued `n` kernels
+#define LAUNCH(n, call) \
+  do {                  \
+    CK(call);           \
+    this->launches += (n); \
+  } while (0)
+#define RET(call)                 \
+  do {                            \
+    int s_ = (call);              \
+    if (s_ != RBL_OK) return s_;  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+template <typename real>
+struct Ctx final : rbl_ctx {
+  // parameters (setParameters, c_rigid_obj.cpp:183-195)
+  double a = 0, dt = 0, kBT = 0, eta = 0;
+  bool params_set = false, cfg_set = false, wall = false, block_pc = false, pc_set = false;
+  bool r_valid = false;
+  int n_blb = 0, n_bod = 0;
+  int pc_n_bod = 0;
+  // device state
+  DevBuf d_ref, d_X, d_Q, d_r, d_S;
+  // matvec workspace
+  DevBuf d_rec, d_box_src, d_box_tgt, d_scratch, d_flags;
+  // staging for the host-pointer API
+  DevBuf d_in0, d_in1, d_out0;
+  // preconditioner
+  DevBuf d_dinv, d_Minv, d_Kc, d_Y, d_L, d_y;
+  bool pc_shared = false;
+  // krylov
+  DevBuf d_V, d_w, d_z, d_tmp, d_partial, d_coef, d_dots;
+
+  enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, N_FLAGS = 4 };
+
+  ~Ctx() override {
+    for (auto& pr : prof_events) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  long long N() const { return (long long)n_bod * n_blb; }
+  size_t sys_size() const { return (size_t)(3 * N() + 6 * (long long)n_bod); }
+
+  int init() {
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    CK(d_flags.ensure(N_FLAGS * sizeof(int)));
+    CK(cudaMemsetAsync(d_flags.p, 0, N_FLAGS * sizeof(int), stream));
+    return RBL_OK;
+  }
+
+  int h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return RBL_OK;
+  }
+  int d2h(void* dst, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    return RBL_OK;
+  }
+
+  // waits for the stream and turns device flags into status codes
+  int sync() override {
+    int flags[N_FLAGS] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (flags[0] || flags[1] || flags[2]) {
+      CK(cudaMemsetAsync(d_flags.p, 0, sizeof(flags), stream));
+      if (flags[FLAG_BELOW])
+        return fail(RBL_ERR_BELOW_WALL,
+                    "A blob has its center below the wall (z<0). Cannot compute mobility- check "
+                    "your configuration.");
+      if (flags[FLAG_SINGULAR])
+        return fail(RBL_ERR_SINGULAR, "K^T*K is singular (is your rigid body a dimer?)");
+      pc_set = false;
+      return fail(RBL_ERR_SINGULAR, "preconditioner block is not positive definite");
+    }
+    return RBL_OK;
+  }
+
+  // ---- state --------------------------------------------------------------------------
+  int set_parameters(double a_, double dt_, double kBT_, double eta_, const void* cfg,
+                     int n_blb_) override {
+    if (n_blb_ <= 0 || !cfg) return fail(RBL_ERR_INVALID, "setParameters: empty rigid configuration");
+    if (!(a_ > 0) || !(eta_ > 0)) return fail(RBL_ERR_INVALID, "setParameters: a and eta must be positive");
+    a = a_; dt = dt_; kBT = kBT_; eta = eta_;
+    n_blb = n_blb_;
+    // removeMean (c_rigid_obj.cpp:176-181), in `real` like the reference
+    const real* c = static_cast<const real*>(cfg);
+    std::vector<real> ref(c, c + 3 * (size_t)n_blb);
+    real mean[3] = {0, 0, 0};
+    for (int k = 0; k < n_blb; ++k)
+      for (int d = 0; d < 3; ++d) mean[d] += ref[3 * k + d];
+    for (int d = 0; d < 3; ++d) mean[d] /= (real)n_blb;
+    for (int k = 0; k < n_blb; ++k)
+      for (int d = 0; d < 3; ++d) ref[3 * k + d] -= mean[d];
+    CK(d_ref.ensure(ref.size() * sizeof(real)));
+    RET(h2d(d_ref.p, ref.data(), ref.size() * sizeof(real)));
+    CK(cudaStreamSynchronize(stream));
+    params_set = true;
+    r_valid = false;
+    pc_set = false;
+    return RBL_OK;
+  }
+
+  int set_flags(int block_pc_, int wall_) override {
+    if (block_pc_ >= 0 && (block_pc_ != 0) != block_pc) { block_pc = block_pc_ != 0; pc_set = false; }
+    if (wall_ >= 0 && (wall_ != 0) != wall) { wall = wall_ != 0; pc_set = false; }
+    return RBL_OK;
+  }
+
+  int set_config(const void* X, const void* Q, int n_bod_) override {
+    if (!params_set) return fail(RBL_ERR_STATE, "setConfig before setParameters");
+    if (n_bod_ <= 0 || !X || !Q) return fail(RBL_ERR_INVALID, "setConfig: empty configuration");
+    n_bod = n_bod_;
+    CK(d_X.ensure(3 * (size_t)n_bod * sizeof(real)));
+    CK(d_Q.ensure(4 * (size_t)n_bod * sizeof(real)));
+    RET(h2d(d_X.p, X, 3 * (size_t)n_bod * sizeof(real)));
+    RET(h2d(d_Q.p, Q, 4 * (size_t)n_bod * sizeof(real)));
+    LAUNCH(1, rbl::normalize_quats<real>(d_Q.as<real>(), n_bod, stream));  // :216
+    CK(cudaStreamSynchronize(stream));
+    cfg_set = true;
+    r_valid = false;
+    // the reference keeps a built PC across setConfig (only evolve_X_Q resets PC_mat_Set,
+    // :877); it cannot survive a change of the number of bodies, so rebuild in that case
+    if (pc_set && pc_n_bod != n_bod) pc_set = false;
+    return RBL_OK;
+  }
+
+  int get_config(void* X, void* Q) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    RET(d2h(X, d_X.p, 3 * (size_t)n_bod * sizeof(real)));
+    RET(d2h(Q, d_Q.p, 4 * (size_t)n_bod * sizeof(real)));
+    CK(cudaStreamSynchronize(stream));
+    return RBL_OK;
+  }
+
+  int set_K_mats() override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    CK(d_r.ensure(3 * (size_t)N() * sizeof(real)));
+    CK(d_S.ensure(9 * (size_t)n_bod * sizeof(real)));
+    LAUNCH(1, rbl::place_blobs<real>(d_X.as<real>(), d_Q.as<real>(), d_ref.as<real>(), n_bod, n_blb,
+                                     d_r.as<real>(), stream));
+    LAUNCH(1, rbl::ktk_inv_blocks<real>(d_Q.as<real>(), d_ref.as<real>(), n_bod, n_blb, d_S.as<real>(),
+                                        d_flags.as<int>() + FLAG_SINGULAR, stream));
+    r_valid = true;
+    return RBL_OK;
+  }
+  int need_K() {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!r_valid) RET(set_K_mats());
+    return RBL_OK;
+  }
+  int n_bodies() const override { return n_bod; }
+  int blobs_per_body() const override { return n_blb; }
+
+  // ---- O(N) operators -------------------------------------------------------------------
+  int blob_positions(void* out, bool dev) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    const size_t bytes = 3 * (size_t)N() * sizeof(real);
+    if (dev) {
+      LAUNCH(1, rbl::place_blobs<real>(d_X.as<real>(), d_Q.as<real>(), d_ref.as<real>(), n_bod, n_blb,
+                                       static_cast<real*>(out), stream));
+      return RBL_OK;
+    }
+    CK(d_out0.ensure(bytes));
+    LAUNCH(1, rbl::place_blobs<real>(d_X.as<real>(), d_Q.as<real>(), d_ref.as<real>(), n_bod, n_blb,
+                                     d_out0.as<real>(), stream));
+    RET(d2h(out, d_out0.p, bytes));
+    CK(cudaStreamSynchronize(stream));
+    return RBL_OK;
+  }
+
+  int K_dot(const void* U, void* out, bool dev) override {
+    RET(need_K());
+    const size_t nin = 6 * (size_t)n_bod * sizeof(real), nout = 3 * (size_t)N() * sizeof(real);
+    const real* dU = static_cast<const real*>(U);
+    real* dO = static_cast<real*>(out);
+    if (!dev) {
+      CK(d_in0.ensure(nin));
+      CK(d_out0.ensure(nout));
+      RET(h2d(d_in0.p, U, nin));
+      dU = d_in0.as<real>();
+      dO = d_out0.as<real>();
+    }
+    LAUNCH(1, rbl::k_dot<real>(dU, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)1, nullptr, dO, stream));
+    if (!dev) {
+      RET(d2h(out, dO, nout));
+      RET(sync());
+    }
+    return RBL_OK;
+  }
+
+  int KT_dot(const void* lam, void* out, bool dev) override {
+    RET(need_K());
+    const size_t nin = 3 * (size_t)N() * sizeof(real), nout = 6 * (size_t)n_bod * sizeof(real);
+    const real* dL = static_cast<const real*>(lam);
+    real* dO = static_cast<real*>(out);
+    if (!dev) {
+      CK(d_in0.ensure(nin));
+      CK(d_out0.ensure(nout));
+      RET(h2d(d_in0.p, lam, nin));
+      dL = d_in0.as<real>();
+      dO = d_out0.as<real>();
+    }
+    LAUNCH(1, rbl::kt_dot<real>(dL, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dO, stream));
+    if (!dev) {
+      RET(d2h(out, dO, nout));
+      RET(sync());
+    }
+    return RBL_OK;
+  }
+
+  int Kinv_dot(const void* V, void* out) override {  // (K^T K)^-1 K^T V  (:390,406)
+    RET(need_K());
+    const size_t nin = 3 * (size_t)N() * sizeof(real), nout = 6 * (size_t)n_bod * sizeof(real);
+    CK(d_in0.ensure(nin));
+    CK(d_out0.ensure(nout));
+    RET(h2d(d_in0.p, V, nin));
+    LAUNCH(1, rbl::kt_dot<real>(d_in0.as<real>(), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, d_out0.as<real>(), stream));
+    LAUNCH(1, rbl::ktk_inv_apply<real>(d_S.as<real>(), n_bod, n_blb, d_out0.as<real>(), stream));
+    RET(d2h(out, d_out0.p, nout));
+    return sync();
+  }
+  int KTinv_dot(const void* F, void* out) override {  // K (K^T K)^-1 F  (:408)
+    RET(need_K());
+    const size_t nin = 6 * (size_t)n_bod * sizeof(real), nout = 3 * (size_t)N() * sizeof(real);
+    CK(d_in0.ensure(nin));
+    CK(d_out0.ensure(nout));
+    RET(h2d(d_in0.p, F, nin));
+    LAUNCH(1, rbl::ktk_inv_apply<real>(d_S.as<real>(), n_bod, n_blb, d_in0.as<real>(), stream));
+    LAUNCH(1, rbl::k_dot<real>(d_in0.as<real>(), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)1, nullptr, d_out0.as<real>(), stream));
+    RET(d2h(out, d_out0.p, nout));
+    return sync();
+  }
+
+  // ---- the mobility product ---------------------------------------------------------------
+  int pick_variant(int n_tgt) const {
+    if (variant >= 0) return variant;
+    // big problems: the widest register tile; small ones: the smallest target tile so the
+    // stream-K unit grid still covers the SMs
+    return n_tgt >= 16384 ? 0 : rbl::matvec_num_variants<real>() - 1;
+  }
+
+  int dev_apply_M(const void* F, const void* r, int n, int t0, int nt, void* out) override {
+    if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
+    if (n < 0 || t0 < 0 || nt < 0 || t0 + nt > n) return fail(RBL_ERR_INVALID, "apply_M: bad target range");
+    if (n == 0 || nt == 0) return RBL_OK;
+    const int v = pick_variant(nt);
+    rbl::MatvecArgs<real> A;
+    CK(rbl::matvec_plan<real>(v, wall, n, t0, nt, sm_count, &A.plan));
+    const size_t n_pad = (size_t)A.plan.n_src_tiles * rbl::kSrcTile;
+    CK(d_rec.ensure(n_pad * rbl::kRecReals * sizeof(real)));
+    CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
+    CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
+    CK(d_scratch.ensure(2 * (size_t)A.plan.grid * 3 * A.plan.tgt_tile * sizeof(real)));
+    LAUNCH(1, rbl::pack_records<real>(static_cast<const real*>(r), static_cast<const real*>(F), n, (int)n_pad, wall,
+                                      (real)a, d_rec.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), t0, nt, A.plan.tgt_tile, d_box_tgt.as<float>(), stream));
+    A.rec = d_rec.as<real>();
+    A.box_src = d_box_src.as<float>();
+    A.box_tgt = d_box_tgt.as<float>();
+    A.out = static_cast<real*>(out);
+    A.scratch = d_scratch.as<real>();
+    A.C = rbl::make_pair_consts<real>(a, eta);
+    A.wall = wall ? 1 : 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      prof_events.emplace_back(e0, e1);
+    }
+    LAUNCH(2, rbl::matvec_launch<real>(v, A, stream, e0, e1));
+    return RBL_OK;
+  }
+
+  int apply_M(const void* F, const void* r, int n, void* out) override {
+    if (n < 0) return fail(RBL_ERR_INVALID, "apply_M: negative size");
+    if (n == 0) return RBL_OK;
+    const size_t bytes = 3 * (size_t)n * sizeof(real);
+    CK(d_in0.ensure(bytes));
+    CK(d_in1.ensure(bytes));
+    CK(d_out0.ensure(bytes));
+    RET(h2d(d_in0.p, F, bytes));
+    RET(h2d(d_in1.p, r, bytes));
+    RET(dev_apply_M(d_in0.p, d_in1.p, n, 0, n, d_out0.p));
+    RET(d2h(out, d_out0.p, bytes));
+    return sync();
+  }
+
+  int dev_saddle(const real* dx, real* dout) {
+    RET(need_K());
+    const int n = (int)N();
+    // slip = M lam - K U ; F = K^T lam   (Rigid.py:73-80)
+    RET(dev_apply_M(dx, d_r.p, n, 0, n, dout));
+    LAUNCH(1, rbl::k_dot<real>(dx + 3 * (size_t)n, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)-1, dout, dout, stream));
+    LAUNCH(1, rbl::kt_dot<real>(dx, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dout + 3 * (size_t)n, stream));
+    return RBL_OK;
+  }
+  int apply_saddle(const void* x, void* out, bool dev) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (dev) return dev_saddle(static_cast<const real*>(x), static_cast<real*>(out));
+    const size_t bytes = sys_size() * sizeof(real);
+    CK(d_in0.ensure(bytes));
+    CK(d_out0.ensure(bytes));
+    RET(h2d(d_in0.p, x, bytes));
+    RET(dev_saddle(d_in0.as<real>(), d_out0.as<real>()));
+    RET(d2h(out, d_out0.p, bytes));
+    return sync();
+  }
+
+  // ---- preconditioner -----------------------------------------------------------------------
+  int build_pc() {
+    RET(need_K());
+    const int sz = 3 * n_blb;
+    const size_t n3 = 3 * (size_t)N();
+    CK(d_Kc.ensure(6 * n3 * sizeof(real)));
+    CK(d_Y.ensure(6 * n3 * sizeof(real)));
+    CK(d_L.ensure(36 * (size_t)n_bod * sizeof(real)));
+    CK(d_y.ensure(n3 * sizeof(real)));
+    int* fl = d_flags.as<int>();
+    LAUNCH(1, rbl::pc_fill_kcols<real>(d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, d_Kc.as<real>(), stream));
+    if (!block_pc) {
+      CK(d_dinv.ensure(n3 * sizeof(real)));
+      LAUNCH(1, rbl::pc_diag_build<real>(d_r.as<real>(), (int)N(), (real)a, (real)eta, wall, d_dinv.as<real>(), fl + FLAG_BELOW, stream));
+      LAUNCH(1, rbl::pc_diag_mul<real>(d_dinv.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
+    } else if (!wall) {
+      // free space: one factorisation of the reference-shape body, rotated per body
+      pc_shared = true;
+      CK(d_Minv.ensure((size_t)sz * sz * sizeof(real)));
+      LAUNCH(1, rbl::pc_block_assemble<real>(d_ref.as<real>(), 1, n_blb, (real)a, (real)eta, false, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
+      LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), 1, sz, fl + FLAG_NOT_SPD, stream));
+      LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), 0, d_Q.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
+    } else {
+      pc_shared = false;
+      const size_t bytes = (size_t)n_bod * sz * sz * sizeof(real);
+      cudaError_t e = d_Minv.ensure(bytes);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        char msg[256];
+        snprintf(msg, sizeof(msg),
+                 "block preconditioner with wall needs %.1f GB for %d dense %dx%d body blocks; use the "
+                 "diagonal preconditioner (block_PC=False) at this size",
+                 bytes / 1e9, n_bod, sz, sz);
+        return fail(RBL_ERR_NOMEM, msg);
+      }
+      LAUNCH(1, rbl::pc_block_assemble<real>(d_r.as<real>(), n_bod, n_blb, (real)a, (real)eta, true, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
+      LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), n_bod, sz, fl + FLAG_NOT_SPD, stream));
+      LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), (size_t)sz * sz, nullptr, d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
+    }
+    LAUNCH(1, rbl::pc_ninv_chol<real>(d_Y.as<real>(), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, d_L.as<real>(), fl + FLAG_NOT_SPD, stream));
+    RET(sync());  // below-wall / not-SPD surface here, like the reference's lazy build (:591-596)
+    pc_set = true;
+    pc_n_bod = n_bod;
+    return RBL_OK;
+  }
+
+  int dev_pc(const real* din, real* dout) {
+    if (!pc_set) RET(build_pc());
+    const int sz = 3 * n_blb;
+    const size_t n3 = 3 * (size_t)N();
+    if (!block_pc)
+      LAUNCH(1, rbl::pc_diag_mul<real>(d_dinv.as<real>(), din, n_bod, n_blb, 1, d_y.as<real>(), stream));
+    else
+      LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), pc_shared ? 0 : (size_t)sz * sz, pc_shared ? d_Q.as<real>() : nullptr,
+                                        din, n_bod, n_blb, 1, d_y.as<real>(), stream));
+    LAUNCH(1, rbl::pc_finish<real>(d_y.as<real>(), din + n3, d_Y.as<real>(), d_L.as<real>(), d_r.as<real>(), d_X.as<real>(),
+                                   n_bod, n_blb, dout, stream));
+    return RBL_OK;
+  }
+  int apply_PC(const void* in, void* out, bool dev) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (dev) return dev_pc(static_cast<const real*>(in), static_cast<real*>(out));
+    const size_t bytes = sys_size() * sizeof(real);
+    CK(d_in0.ensure(bytes));
+    CK(d_out0.ensure(bytes));
+    RET(h2d(d_in0.p, in, bytes));
+    RET(dev_pc(d_in0.as<real>(), d_out0.as<real>()));
+    RET(d2h(out, d_out0.p, bytes));
+    return sync();
+  }
+
+  // ---- integrator ---------------------------------------------------------------------------
+  int evolve(const void* U) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    const size_t bytes = 6 * (size_t)n_bod * sizeof(real);
+    CK(d_in0.ensure(bytes));
+    RET(h2d(d_in0.p, U, bytes));
+    LAUNCH(1, rbl::integrate<real>(d_in0.as<real>(), (real)dt, n_bod, d_X.as<real>(), d_Q.as<real>(), d_X.as<real>(), d_Q.as<real>(), stream));
+    RET(set_K_mats());  // :876
+    pc_set = false;     // :877
+    return sync();
+  }
+
+  // ---- CSC export of K and Kinv (host side; :368-390, :978-992) -------------------------------
+  int fetch_geometry(std::vector<real>& r, std::vector<real>& X, std::vector<real>& S) {
+    RET(need_K());
+    r.resize(3 * (size_t)N());
+    X.resize(3 * (size_t)n_bod);
+    S.resize(9 * (size_t)n_bod);
+    RET(d2h(r.data(), d_r.p, r.size() * sizeof(real)));
+    RET(d2h(X.data(), d_X.p, X.size() * sizeof(real)));
+    RET(d2h(S.data(), d_S.p, S.size() * sizeof(real)));
+    return sync();
+  }
+  int export_K(int64_t* indptr, int32_t* indices, void* data_) override {
+    std::vector<real> r, X, S;
+    RET(fetch_geometry(r, X, S));
+    real* data = static_cast<real*>(data_);
+    int64_t nnz = 0;
+    for (int b = 0; b < n_bod; ++b) {
+      const size_t base = (size_t)b * n_blb;
+      for (int c = 0; c < 6; ++c) {
+        indptr[6 * b + c] = nnz;
+        for (int k = 0; k < n_blb; ++k) {
+          const size_t i = base + k;
+          const real px = r[3 * i] - X[3 * b], py = r[3 * i + 1] - X[3 * b + 1], pz = r[3 * i + 2] - X[3 * b + 2];
+          const int32_t row = (int32_t)(3 * i);
+          switch (c) {
+            case 0: case 1: case 2:
+              indices[nnz] = row + c; data[nnz++] = 1; break;
+            case 3:  // omega_x: rows y,z = (-pz, +py)   (:380-381)
+              indices[nnz] = row + 1; data[nnz++] = -pz;
+              indices[nnz] = row + 2; data[nnz++] = py; break;
+            case 4:  // omega_y: rows x,z = (+pz, -px)   (:376,382)
+              indices[nnz] = row + 0; data[nnz++] = pz;
+              indices[nnz] = row + 2; data[nnz++] = -px; break;
+            default: // omega_z: rows x,y = (-py, +px)   (:377-378)
+              indices[nnz] = row + 0; data[nnz++] = -py;
+              indices[nnz] = row + 1; data[nnz++] = px; break;
+          }
+        }
+      }
+    }
+    indptr[6 * (size_t)n_bod] = nnz;
+    return RBL_OK;
+  }
+  int export_Kinv(int64_t* indptr, int32_t* indices, void* data_) override {
+    std::vector<real> r, X, S;
+    RET(fetch_geometry(r, X, S));
+    real* data = static_cast<real*>(data_);
+    int64_t nnz = 0;
+    const real inv_n = (real)1 / (real)n_blb;
+    for (int b = 0; b < n_bod; ++b) {
+      const real* Sb = &S[9 * (size_t)b];
+      for (int k = 0; k < n_blb; ++k) {
+        const size_t i = (size_t)b * n_blb + k;
+        const real px = r[3 * i] - X[3 * b], py = r[3 * i + 1] - X[3 * b + 1], pz = r[3 * i + 2] - X[3 * b + 2];
+        // rows of -[rho]x : the rotational part of K's row p
+        const real kr[3][3] = {{0, pz, -py}, {-pz, 0, px}, {py, -px, 0}};
+        for (int p = 0; p < 3; ++p) {
+          indptr[3 * i + p] = nnz;
+          indices[nnz] = 6 * b + p; data[nnz++] = inv_n;
+          for (int q = 0; q < 3; ++q) {
+            indices[nnz] = 6 * b + 3 + q;
+            data[nnz++] = Sb[3 * q] * kr[p][0] + Sb[3 * q + 1] * kr[p][1] + Sb[3 * q + 2] * kr[p][2];
+          }
+        }
+      }
+    }
+    indptr[3 * (size_t)N()] = nnz;
+    return RBL_OK;
+  }
+
+  // ---- Krylov drivers -------------------------------------------------------------------------
+  int read_scalars(const real* d, int m, std::vector<double>& out) {
+    std::vector<real> h(m);
+    RET(d2h(h.data(), d, m * sizeof(real)));
+    CK(cudaStreamSynchronize(stream));
+    out.resize(m);
+    for (int i = 0; i < m; ++i) out[i] = (double)h[i];
+    return RBL_OK;
+  }
+  int dev_norm(const real* v, size_t n, double* out) {
+    LAUNCH(2, rbl::multi_dot<real>(v, n, 1, v, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+    std::vector<double> s;
+    RET(read_scalars(d_dots.as<real>(), 1, s));
+    *out = std::sqrt(std::max(s[0], 0.0));
+    return RBL_OK;
+  }
+
+  int gmres(const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (restart < 1 || max_iter < 1) return fail(RBL_ERR_INVALID, "gmres: restart and max_iter must be >= 1");
+    RET(need_K());
+    const size_t n = sys_size(), n_head = 3 * (size_t)N();
+    const int m = restart;
+    CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
+    CK(d_w.ensure(n * sizeof(real)));
+    CK(d_z.ensure(n * sizeof(real)));
+    CK(d_tmp.ensure(n * sizeof(real)));
+    CK(d_in1.ensure(n * sizeof(real)));   // rhs
+    CK(d_out0.ensure(n * sizeof(real)));  // x
+    CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
+    CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    real* V = d_V.as<real>();
+    real* w = d_w.as<real>();
+    real* z = d_z.as<real>();
+    real* tmp = d_tmp.as<real>();
+    real* b = d_in1.as<real>();
+    real* xs = d_out0.as<real>();
+    RET(h2d(b, rhs, n * sizeof(real)));
+    CK(cudaMemsetAsync(xs, 0, n * sizeof(real), stream));
+    double bnorm = 0;
+    RET(dev_norm(b, n, &bnorm));
+    int total = 0;
+    double res = bnorm;
+    if (bnorm == 0) {
+      RET(d2h(x, xs, n * sizeof(real)));
+      *iters = 0;
+      *relres = 0;
+      return sync();
+    }
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), hcol;
+    std::vector<real> coef(m + 1);
+    bool first = true;
+    while (total < max_iter) {
+      // r0 = b - A x  (x = 0 on the first cycle)
+      if (first) {
+        LAUNCH(1, rbl::scale_copy<real>(b, (real)1, w, n, false, stream));
+      } else {
+        RET(dev_saddle(xs, w));
+        LAUNCH(1, rbl::scale_copy<real>(w, (real)-1, w, n, false, stream));
+        LAUNCH(1, rbl::scale_copy<real>(b, (real)1, w, n, true, stream));
+      }
+      first = false;
+      double beta = 0;
+      RET(dev_norm(w, n, &beta));
+      res = beta;
+      if (beta / bnorm <= tol) break;
+      LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / beta), V, n, false, stream));
+      std::fill(g.begin(), g.end(), 0.0);
+      g[0] = beta;
+      int j = 0;
+      for (; j < m && total < max_iter; ++j, ++total) {
+        // z = P S v_j ; w = A z
+        LAUNCH(1, rbl::flip_tail<real>(V + (size_t)j * n, n_head, n, tmp, stream));
+        RET(dev_pc(tmp, z));
+        RET(dev_saddle(z, w));
+        // classical Gram-Schmidt, twice (one device->host read per pass)
+        std::fill(H.begin() + (size_t)j * (m + 1), H.begin() + (size_t)(j + 1) * (m + 1), 0.0);
+        for (int pass = 0; pass < 2; ++pass) {
+          LAUNCH(2, rbl::multi_dot<real>(V, n, j + 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+          LAUNCH(1, rbl::multi_axpy<real>(V, n, j + 1, d_dots.as<real>(), (real)-1, w, n, stream));
+          RET(read_scalars(d_dots.as<real>(), j + 1, hcol));
+          for (int i = 0; i <= j; ++i) H[(size_t)j * (m + 1) + i] += hcol[i];
+        }
+        double hn = 0;
+        RET(dev_norm(w, n, &hn));
+        H[(size_t)j * (m + 1) + j + 1] = hn;
+        if (hn > 0) LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / hn), V + (size_t)(j + 1) * n, n, false, stream));
+        // Givens
+        double* h = &H[(size_t)j * (m + 1)];
+        for (int i = 0; i < j; ++i) {
+          const double t = cs[i] * h[i] + sn[i] * h[i + 1];
+          h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
+          h[i] = t;
+        }
+        const double den = std::hypot(h[j], h[j + 1]);
+        cs[j] = den > 0 ? h[j] / den : 1.0;
+        sn[j] = den > 0 ? h[j + 1] / den : 0.0;
+        h[j] = den;
+        h[j + 1] = 0;
+        g[j + 1] = -sn[j] * g[j];
+        g[j] = cs[j] * g[j];
+        res = std::fabs(g[j + 1]);
+        if (res / bnorm <= tol || hn == 0) {
+          ++j;
+          ++total;
+          break;
+        }
+      }
+      // y = H^-1 g ; x += P S (V y)
+      std::vector<double> y(j);
+      for (int i = j - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int k = i + 1; k < j; ++k) s -= H[(size_t)k * (m + 1) + i] * y[k];
+        y[i] = s / H[(size_t)i * (m + 1) + i];
+      }
+      for (int i = 0; i < j; ++i) coef[i] = (real)y[i];
+      RET(h2d(d_coef.p, coef.data(), j * sizeof(real)));
+      CK(cudaMemsetAsync(w, 0, n * sizeof(real), stream));
+      LAUNCH(1, rbl::multi_axpy<real>(V, n, j, d_coef.as<real>(), (real)1, w, n, stream));
+      LAUNCH(1, rbl::flip_tail<real>(w, n_head, n, tmp, stream));
+      RET(dev_pc(tmp, z));
+      LAUNCH(1, rbl::scale_copy<real>(z, (real)1, xs, n, true, stream));
+      CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
+      if (res / bnorm <= tol) break;
+    }
+    RET(d2h(x, xs, n * sizeof(real)));
+    *iters = total;
+    *relres = res / bnorm;
+    return sync();
+  }
+
+  // symmetric tridiagonal eigen-decomposition by cyclic Jacobi on the dense k x k matrix
+  static void jacobi_eig(std::vector<double>& A, int k, std::vector<double>& evec) {
+    evec.assign((size_t)k * k, 0.0);
+    for (int i = 0; i < k; ++i) evec[(size_t)i * k + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      double off = 0;
+      for (int p = 0; p < k; ++p)
+        for (int q = p + 1; q < k; ++q) off += A[(size_t)p * k + q] * A[(size_t)p * k + q];
+      if (off < 1e-30) break;
+      for (int p = 0; p < k; ++p)
+        for (int q = p + 1; q < k; ++q) {
+          const double apq = A[(size_t)p * k + q];
+          if (std::fabs(apq) < 1e-300) continue;
+          const double th = (A[(size_t)q * k + q] - A[(size_t)p * k + p]) / (2 * apq);
+          const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
+          const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+          for (int i = 0; i < k; ++i) {
+            const double aip = A[(size_t)i * k + p], aiq = A[(size_t)i * k + q];
+            A[(size_t)i * k + p] = c * aip - s * aiq;
+            A[(size_t)i * k + q] = s * aip + c * aiq;
+          }
+          for (int i = 0; i < k; ++i) {
+            const double api = A[(size_t)p * k + i], aqi = A[(size_t)q * k + i];
+            A[(size_t)p * k + i] = c * api - s * aqi;
+            A[(size_t)q * k + i] = s * api + c * aqi;
+          }
+          for (int i = 0; i < k; ++i) {
+            const double vip = evec[(size_t)i * k + p], viq = evec[(size_t)i * k + q];
+            evec[(size_t)i * k + p] = c * vip - s * viq;
+            evec[(size_t)i * k + q] = s * vip + c * viq;
+          }
+        }
+    }
+  }
+
+  int lanczos(const void* W, void* out, double tol, int max_iter, int* iters) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
+    RET(need_K());
+    const size_t n = 3 * (size_t)N();
+    const int nb = (int)N();
+    const int m = max_iter;
+    CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
+    CK(d_w.ensure(n * sizeof(real)));
+    CK(d_out0.ensure(n * sizeof(real)));
+    CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
+    CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    real* V = d_V.as<real>();
+    real* w = d_w.as<real>();
+    RET(h2d(w, W, n * sizeof(real)));
+    double wnorm = 0;
+    RET(dev_norm(w, n, &wnorm));
+    if (wnorm == 0) {
+      CK(cudaMemsetAsync(d_out0.p, 0, n * sizeof(real), stream));
+      RET(d2h(out, d_out0.p, n * sizeof(real)));
+      *iters = 0;
+      return sync();
+    }
+    LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / wnorm), V, n, false, stream));
+    std::vector<double> alpha, beta, y_prev, y, s;
+    int k = 0;
+    for (; k < m;) {
+      // w = M v_k - beta_{k-1} v_{k-1}
+      RET(dev_apply_M(V + (size_t)k * n, d_r.p, nb, 0, nb, w));
+      if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-beta[k - 1]), w, n, true, stream));
+      LAUNCH(2, rbl::multi_dot<real>(V + (size_t)k * n, n, 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+      RET(read_scalars(d_dots.as<real>(), 1, s));
+      alpha.push_back(s[0]);
+      LAUNCH(1, rbl::scale_copy<real>(V + (size_t)k * n, (real)(-s[0]), w, n, true, stream));
+      // full reorthogonalisation (keeps the basis orthonormal in fp32 too)
+      LAUNCH(2, rbl::multi_dot<real>(V, n, k + 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+      LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>(), (real)-1, w, n, stream));
+      double bn = 0;
+      RET(dev_norm(w, n, &bn));
+      ++k;
+      // y = ||W|| T_k^{1/2} e_1
+      std::vector<double> T((size_t)k * k, 0.0), Z;
+      for (int i = 0; i < k; ++i) {
+        T[(size_t)i * k + i] = alpha[i];
+        if (i + 1 < k) T[(size_t)i * k + i + 1] = T[(size_t)(i + 1) * k + i] = beta[i];
+      }
+      jacobi_eig(T, k, Z);
+      y.assign(k, 0.0);
+      for (int e = 0; e < k; ++e) {
+        const double lam = std::max(T[(size_t)e * k + e], 0.0);
+        const double f = std::sqrt(lam) * Z[(size_t)0 * k + e] * wnorm;
+        for (int i = 0; i < k; ++i) y[i] += Z[(size_t)i * k + e] * f;
+      }
+      double diff = 0, nrm = 0;
+      for (int i = 0; i < k; ++i) {
+        const double d = y[i] - (i < (int)y_prev.size() ? y_prev[i] : 0.0);
+        diff += d * d;
+        nrm += y[i] * y[i];
+      }
+      y_prev = y;
+      const bool converged = k > 1 && std::sqrt(diff) <= tol * std::sqrt(nrm);
+      if (converged || bn <= 1e-14 * wnorm || k == m) break;
+      beta.push_back(bn);
+      LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / bn), V + (size_t)k * n, n, false, stream));
+    }
+    std::vector<real> coef(k);
+    for (int i = 0; i < k; ++i) coef[i] = (real)y[i];
+    RET(h2d(d_coef.p, coef.data(), k * sizeof(real)));
+    CK(cudaMemsetAsync(d_out0.p, 0, n * sizeof(real), stream));
+    LAUNCH(1, rbl::multi_axpy<real>(V, n, k, d_coef.as<real>(), (real)1, d_out0.as<real>(), n, stream));
+    RET(d2h(out, d_out0.p, n * sizeof(real)));
+    *iters = k;
+    return sync();
+  }
+
+  // ---- measurement ----------------------------------------------------------------------------
+  int fma_peak(int iters, double* tflops) override {
+    CK(d_out0.ensure(256));
+    double flops = 0;
+    // warm-up + timed
+    LAUNCH(1, rbl::fma_peak_launch<real>(sm_count, std::max(iters / 8, 1), d_out0.as<real>(), &flops, stream));
+    CK(cudaEventRecord(t0, stream));
+    LAUNCH(1, rbl::fma_peak_launch<real>(sm_count, iters, d_out0.as<real>(), &flops, stream));
+    CK(cudaEventRecord(t1, stream));
+    CK(cudaEventSynchronize(t1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return RBL_OK;
+  }
+  int num_variants() const override { return rbl::matvec_num_variants<real>(); }
+  int variant_info(int idx, int* T, int* threads) const override {
+    if (idx < 0 || idx >= rbl::matvec_num_variants<real>()) return RBL_ERR_INVALID;
+    const rbl::MatvecVariant v = rbl::matvec_variant<real>(idx);
+    *T = v.T;
+    *threads = v.threads;
+    return RBL_OK;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+#define CTX_OR_FAIL(ctx)          \
+  if (!(ctx)) return RBL_ERR_INVALID
+
+extern "C" {
+
+const char* rbl_version(void) { return "rigid_body_light_b200 0.1.0 (sm_100a)"; }
+
+int rbl_create(int precision, int device, rbl_ctx** out) {
+  if (!out) return RBL_ERR_INVALID;
+  *out = nullptr;
+  if (precision != RBL_F32 && precision != RBL_F64) {
+    g_create_error = "rbl_create: precision must be RBL_F32 (4) or RBL_F64 (8)";
+    return RBL_ERR_INVALID;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("rbl_create: no CUDA device (there is no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return RBL_ERR_CUDA;
+  }
+  if (device < 0) {
+    e = cudaGetDevice(&device);
+    if (e != cudaSuccess) {
+      g_create_error = std::string("cudaGetDevice: ") + cudaGetErrorString(e);
+      return RBL_ERR_CUDA;
+    }
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return RBL_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return RBL_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = std::string("rbl_create: kernels are built for sm_100a only; device is ") + prop.name;
+    return RBL_ERR_CUDA;
+  }
+  rbl_ctx* c = nullptr;
+  int st;
+  if (precision == RBL_F32) {
+    auto* p = new Ctx<float>();
+    p->precision = precision; p->device = device; p->sm_count = prop.multiProcessorCount;
+    st = p->init();
+    c = p;
+  } else {
+    auto* p = new Ctx<double>();
+    p->precision = precision; p->device = device; p->sm_count = prop.multiProcessorCount;
+    st = p->init();
+    c = p;
+  }
+  if (st != RBL_OK) {
+    g_create_error = c->err;
+    delete c;
+    return st;
+  }
+  *out = c;
+  return RBL_OK;
+}
+
+void rbl_destroy(rbl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  delete ctx;
+}
+
+const char* rbl_last_error(const rbl_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int rbl_precision(const rbl_ctx* ctx) { return ctx ? ctx->precision : 0; }
+int rbl_sm_count(const rbl_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+#define BIND_DEVICE(ctx) cudaSetDevice((ctx)->device)
+
+int rbl_set_parameters(rbl_ctx* ctx, double a, double dt, double kBT, double eta, const void* ref_cfg, int n_blb) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->set_parameters(a, dt, kBT, eta, ref_cfg, n_blb);
+}
+int rbl_set_flags(rbl_ctx* ctx, int block_pc, int wall) { CTX_OR_FAIL(ctx); return ctx->set_flags(block_pc, wall); }
+int rbl_set_config(rbl_ctx* ctx, const void* X, const void* Q, int n_bod) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->set_config(X, Q, n_bod); }
+int rbl_get_config(rbl_ctx* ctx, void* X, void* Q) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->get_config(X, Q); }
+int rbl_set_K_mats(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); int s = ctx->set_K_mats(); return s != RBL_OK ? s : ctx->sync(); }
+int rbl_n_bodies(const rbl_ctx* ctx) { return ctx ? ctx->n_bodies() : 0; }
+int rbl_blobs_per_body(const rbl_ctx* ctx) { return ctx ? ctx->blobs_per_body() : 0; }
+
+int rbl_blob_positions(rbl_ctx* ctx, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->blob_positions(out, false); }
+int rbl_K_dot(rbl_ctx* ctx, const void* U, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->K_dot(U, out, false); }
+int rbl_KT_dot(rbl_ctx* ctx, const void* lam, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->KT_dot(lam, out, false); }
+int rbl_Kinv_dot(rbl_ctx* ctx, const void* V, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->Kinv_dot(V, out); }
+int rbl_KTinv_dot(rbl_ctx* ctx, const void* F, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->KTinv_dot(F, out); }
+int rbl_apply_M(rbl_ctx* ctx, const void* F, const void* r, int n, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_M(F, r, n, out); }
+int rbl_apply_PC(rbl_ctx* ctx, const void* in, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_PC(in, out, false); }
+int rbl_apply_saddle(rbl_ctx* ctx, const void* x, void* out) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_saddle(x, out, false); }
+int rbl_evolve(rbl_ctx* ctx, const void* U) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->evolve(U); }
+int rbl_export_K_csc(rbl_ctx* ctx, int64_t* indptr, int32_t* indices, void* data) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->export_K(indptr, indices, data); }
+int rbl_export_Kinv_csc(rbl_ctx* ctx, int64_t* indptr, int32_t* indices, void* data) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->export_Kinv(indptr, indices, data); }
+
+int rbl_gmres(rbl_ctx* ctx, const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int it = 0; double rr = 0;
+  int s = ctx->gmres(rhs, x, tol, restart, max_iter, &it, &rr);
+  if (iters) *iters = it;
+  if (relres) *relres = rr;
+  return s;
+}
+int rbl_lanczos_sqrt(rbl_ctx* ctx, const void* W, void* out, double tol, int max_iter, int* iters) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int it = 0;
+  int s = ctx->lanczos(W, out, tol, max_iter, &it);
+  if (iters) *iters = it;
+  return s;
+}
+
+int rbl_dev_apply_M(rbl_ctx* ctx, const void* dF, const void* dr, int n, int t0, int nt, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->dev_apply_M(dF, dr, n, t0, nt, dout); }
+int rbl_dev_blob_positions(rbl_ctx* ctx, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->blob_positions(dout, true); }
+int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->K_dot(dU, dout, true); }
+int rbl_dev_KT_dot(rbl_ctx* ctx, const void* dl, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->KT_dot(dl, dout, true); }
+int rbl_dev_apply_PC(rbl_ctx* ctx, const void* din, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_PC(din, dout, true); }
+int rbl_dev_apply_saddle(rbl_ctx* ctx, const void* dx, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_saddle(dx, dout, true); }
+int rbl_sync(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->sync(); }
+void* rbl_stream(rbl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int rbl_set_stream(rbl_ctx* ctx, void* s) {
+  CTX_OR_FAIL(ctx);
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return RBL_OK;
+}
+
+static int cuda_status(rbl_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return RBL_OK;
+  return ctx->fail(e == cudaErrorMemoryAllocation ? RBL_ERR_NOMEM : RBL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+int rbl_dev_alloc(rbl_ctx* ctx, size_t bytes, void** p) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return cuda_status(ctx, cudaMalloc(p, bytes), "cudaMalloc"); }
+int rbl_dev_free(rbl_ctx* ctx, void* p) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return cuda_status(ctx, cudaFree(p), "cudaFree"); }
+int rbl_pinned_alloc(rbl_ctx* ctx, size_t bytes, void** p) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return cuda_status(ctx, cudaMallocHost(p, bytes), "cudaMallocHost"); }
+int rbl_pinned_free(rbl_ctx* ctx, void* p) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return cuda_status(ctx, cudaFreeHost(p), "cudaFreeHost"); }
+int rbl_memcpy_h2d(rbl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int s = cuda_status(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync");
+  return s != RBL_OK ? s : cuda_status(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+}
+int rbl_memcpy_d2h(rbl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int s = cuda_status(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync");
+  return s != RBL_OK ? s : cuda_status(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+}
+int rbl_timer_start(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return cuda_status(ctx, cudaEventRecord(ctx->t0, ctx->stream), "cudaEventRecord"); }
+int rbl_timer_stop(rbl_ctx* ctx, double* ms) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int s = cuda_status(ctx, cudaEventRecord(ctx->t1, ctx->stream), "cudaEventRecord");
+  if (s != RBL_OK) return s;
+  s = cuda_status(ctx, cudaEventSynchronize(ctx->t1), "cudaEventSynchronize");
+  if (s != RBL_OK) return s;
+  float f = 0;
+  s = cuda_status(ctx, cudaEventElapsedTime(&f, ctx->t0, ctx->t1), "cudaEventElapsedTime");
+  if (ms) *ms = f;
+  return s;
+}
+int rbl_flush_l2(rbl_ctx* ctx) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+  int s = cuda_status(ctx, ctx->flush_buf.ensure(bytes), "cudaMalloc(flush)");
+  if (s != RBL_OK) return s;
+  return cuda_status(ctx, cudaMemsetAsync(ctx->flush_buf.p, 1, bytes, ctx->stream), "cudaMemsetAsync");
+}
+
+int rbl_num_matvec_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_variants() : 0; }
+int rbl_matvec_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {
+  if (!ctx || !T || !threads) return RBL_ERR_INVALID;
+  return ctx->variant_info(idx, T, threads);
+}
+int rbl_set_matvec_variant(rbl_ctx* ctx, int idx) {
+  CTX_OR_FAIL(ctx);
+  if (idx >= ctx->num_variants()) return ctx->fail(RBL_ERR_INVALID, "no such matvec variant");
+  ctx->variant = idx < 0 ? -1 : idx;
+  return RBL_OK;
+}
+int64_t rbl_launch_count(const rbl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int rbl_profile_matvec(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->profile = enable != 0; return RBL_OK; }
+int rbl_matvec_profile(rbl_ctx* ctx, double* avg_ms, int64_t* launches, int reset) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int s = cuda_status(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  if (s != RBL_OK) return s;
+  double tot = 0;
+  for (auto& pr : ctx->prof_events) {
+    float f = 0;
+    s = cuda_status(ctx, cudaEventElapsedTime(&f, pr.first, pr.second), "cudaEventElapsedTime");
+    if (s != RBL_OK) return s;
+    tot += f;
+  }
+  const int64_t nl = (int64_t)ctx->prof_events.size();
+  if (avg_ms) *avg_ms = nl ? tot / nl : 0.0;
+  if (launches) *launches = nl;
+  if (reset) {
+    for (auto& pr : ctx->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    ctx->prof_events.clear();
+  }
+  return RBL_OK;
+}
+int rbl_fma_peak(rbl_ctx* ctx, int iters, double* tflops) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  if (!tflops || iters < 1) return RBL_ERR_INVALID;
+  return ctx->fma_peak(iters, tflops);
+}
+
+}  // extern "C"

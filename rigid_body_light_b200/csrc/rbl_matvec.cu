@@ -1,0 +1,587 @@
+// rbl_matvec.cu -- the O(N^2) hot path: U = B M B F, matrix-free, for sm_100a.
+//
+// Reference being replaced: CManyBodies::apply_M / rotne_prager_tensor / make_damp_mat,
+// /root/reference/src/c_rigid_obj.cpp:413-459,618-659 (dense assembly + GEMV).
+//
+// Design:
+//  * pack_records: positions + damped forces -> 8-real records (one TMA-able array).
+//  * rpy_matvec_kernel: persistent CTAs, one per resident slot of the 148 SMs.  The
+//    (target tile x source tile) unit grid is cut into `grid` equal contiguous unit
+//    ranges (stream-K), so every SM gets the same number of pair evaluations to
+//    within one 256-source tile regardless of N.  Each thread owns T targets in
+//    registers; source tiles are streamed through a 2-stage shared-memory ring by
+//    1-D TMA bulk copies (cp.async.bulk + mbarrier) issued by one thread; every
+//    thread reads the same source record per step (shared-memory broadcast, two
+//    LDS.128 per source in fp32 amortised over T targets).
+//  * Far-field fast path: per-tile bounding boxes decide, per unit and CTA-uniformly,
+//    whether any pair of the unit can have r < 2a; if not, the overlap branch and its
+//    selects are compiled out of the loop.
+//  * rpy_fixup_kernel: target tiles whose source range was split between CTAs are
+//    summed from per-CTA scratch slots in CTA order -- deterministic, no atomics.
+#include <cstdio>
+
+#include "rbl_matvec.cuh"
+
+namespace rbl {
+
+// ----------------------------------------------------------------------------------
+// small PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src,
+                                            uint32_t bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// record packing
+// ----------------------------------------------------------------------------------
+template <typename real>
+struct Vec;
+template <>
+struct Vec<float> {
+  using v4 = float4;
+};
+template <>
+struct Vec<double> {
+  using v2 = double2;
+};
+
+__device__ __forceinline__ void store_rec(float* rec, size_t k, float x, float y, float z,
+                                          float fx, float fy, float fz) {
+  float4* p = reinterpret_cast<float4*>(rec + k * kRecReals);
+  p[0] = make_float4(x, y, z, fx);
+  p[1] = make_float4(fy, fz, 2.0f * z, 4.0f * z * z);
+}
+__device__ __forceinline__ void store_rec(double* rec, size_t k, double x, double y,
+                                          double z, double fx, double fy, double fz) {
+  double2* p = reinterpret_cast<double2*>(rec + k * kRecReals);
+  p[0] = make_double2(x, y);
+  p[1] = make_double2(z, fx);
+  p[2] = make_double2(fy, fz);
+  p[3] = make_double2(2.0 * z, 4.0 * z * z);
+}
+
+// B_j of make_damp_mat (c_rigid_obj.cpp:618-639): 1 if z >= a else z/a.
+template <typename real>
+__device__ __forceinline__ real damp(real z, real a, real inv_a) {
+  return z >= a ? (real)1 : z * inv_a;
+}
+
+template <typename real>
+__global__ void pack_records_kernel(const real* __restrict__ r, const real* __restrict__ F,
+                                    int n, int n_padded, int wall, real a, real inv_a,
+                                    real* __restrict__ rec, int* __restrict__ below) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_padded) return;
+  int src = k < n ? k : n - 1;  // padding = copy of the last blob with zero force
+  real x = r[3 * (size_t)src], y = r[3 * (size_t)src + 1], z = r[3 * (size_t)src + 2];
+  real fx = 0, fy = 0, fz = 0;
+  if (k < n) {
+    real b = wall ? damp(z, a, inv_a) : (real)1;
+    fx = b * F[3 * (size_t)k];
+    fy = b * F[3 * (size_t)k + 1];
+    fz = b * F[3 * (size_t)k + 2];
+    if (wall && z < (real)0) *below = 1;  // reference throws here (c_rigid_obj.cpp:95-97)
+  }
+  store_rec(rec, (size_t)k, x, y, z, fx, fy, fz);
+}
+
+template <typename real>
+__global__ void repack_forces_kernel(const real* __restrict__ F, int n, int wall, real a,
+                                     real inv_a, real* __restrict__ rec) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  real* p = rec + (size_t)k * kRecReals;
+  real b = wall ? damp(p[2], a, inv_a) : (real)1;
+  p[3] = b * F[3 * (size_t)k];
+  p[4] = b * F[3 * (size_t)k + 1];
+  p[5] = b * F[3 * (size_t)k + 2];
+}
+
+template <typename real>
+cudaError_t pack_records(const real* r, const real* F, int n, int n_padded, bool wall,
+                         real a, real* rec, int* below, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int threads = 256, blocks = (n_padded + threads - 1) / threads;
+  pack_records_kernel<real><<<blocks, threads, 0, s>>>(r, F, n, n_padded, wall ? 1 : 0, a,
+                                                       (real)1 / a, rec, below);
+  return cudaGetLastError();
+}
+template <typename real>
+cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec,
+                          cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int threads = 256, blocks = (n + threads - 1) / threads;
+  repack_forces_kernel<real><<<blocks, threads, 0, s>>>(F, n, wall ? 1 : 0, a, (real)1 / a,
+                                                        rec);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------
+// tile bounding boxes (outward-rounded floats so the far test is conservative)
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float to_float_down(float v) { return v; }
+__device__ __forceinline__ float to_float_up(float v) { return v; }
+__device__ __forceinline__ float to_float_down(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float to_float_up(double v) { return __double2float_ru(v); }
+
+template <typename real>
+__global__ void tile_boxes_kernel(const real* __restrict__ rec, int first, int count,
+                                  int tile, float* __restrict__ boxes) {
+  const int t = blockIdx.x;
+  const int lo = t * tile;
+  const int hi = min(lo + tile, count);
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+    const real* p = rec + (size_t)(first + k) * kRecReals;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      real v = p[c];
+      mn[c] = fminf(mn[c], to_float_down(v));
+      mx[c] = fmaxf(mx[c], to_float_up(v));
+    }
+  }
+  __shared__ float smn[3][32], smx[3][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    if (lane == 0) {
+      smn[c][wid] = mn[c];
+      smx[c][wid] = mx[c];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    float a = smn[c][0], b = smx[c][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      a = fminf(a, smn[c][w]);
+      b = fmaxf(b, smx[c][w]);
+    }
+    boxes[6 * (size_t)t + c] = a;
+    boxes[6 * (size_t)t + 3 + c] = b;
+  }
+}
+
+template <typename real>
+cudaError_t tile_boxes(const real* rec, int first, int count, int tile, float* boxes,
+                       cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  int tiles = (count + tile - 1) / tile;
+  tile_boxes_kernel<real><<<tiles, 128, 0, s>>>(rec, first, count, tile, boxes);
+  return cudaGetLastError();
+}
+
+// squared gap between two boxes, evaluated in double from (outward-rounded) floats
+__device__ __forceinline__ double box_gap2(const float* __restrict__ A,
+                                           const float* __restrict__ B) {
+  double d2 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double g = fmax(fmax((double)__ldg(A + c) - (double)__ldg(B + 3 + c),
+                         (double)__ldg(B + c) - (double)__ldg(A + 3 + c)),
+                    0.0);
+    d2 += g * g;
+  }
+  return d2;
+}
+
+// ----------------------------------------------------------------------------------
+// inner loop over one staged source tile
+// ----------------------------------------------------------------------------------
+template <bool WALL, bool NEAR, int T>
+__device__ __forceinline__ void tile_compute(const float* __restrict__ sb,
+                                             const PairConsts<float>& C, const float (&xi)[T],
+                                             const float (&yi)[T], const float (&zi)[T],
+                                             float (&ux)[T], float (&uy)[T], float (&uz)[T]) {
+  const float4* __restrict__ s4 = reinterpret_cast<const float4*>(sb);
+#pragma unroll 4
+  for (int j = 0; j < kSrcTile; ++j) {
+    const float4 p = s4[2 * j];      // x y z fx
+    const float4 q = s4[2 * j + 1];  // fy fz 2z 4z^2
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      pair<float, WALL, NEAR>(C, xi[t], yi[t], zi[t], p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w,
+                              ux[t], uy[t], uz[t]);
+  }
+}
+
+template <bool WALL, bool NEAR, int T>
+__device__ __forceinline__ void tile_compute(const double* __restrict__ sb,
+                                             const PairConsts<double>& C,
+                                             const double (&xi)[T], const double (&yi)[T],
+                                             const double (&zi)[T], double (&ux)[T],
+                                             double (&uy)[T], double (&uz)[T]) {
+  const double2* __restrict__ s2 = reinterpret_cast<const double2*>(sb);
+#pragma unroll 2
+  for (int j = 0; j < kSrcTile; ++j) {
+    const double2 p0 = s2[4 * j];      // x y
+    const double2 p1 = s2[4 * j + 1];  // z fx
+    const double2 p2 = s2[4 * j + 2];  // fy fz
+    double2 p3 = make_double2(0.0, 0.0);
+    if (WALL) p3 = s2[4 * j + 3];      // 2z 4z^2
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      pair<double, WALL, NEAR>(C, xi[t], yi[t], zi[t], p0.x, p0.y, p1.x, p1.y, p2.x, p2.y,
+                               p3.x, p3.y, ux[t], uy[t], uz[t]);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// the persistent stream-K matvec kernel
+// ----------------------------------------------------------------------------------
+template <typename real, bool WALL, int T, int NT>
+__global__ void __launch_bounds__(NT) rpy_matvec_kernel(const MatvecArgs<real> A) {
+  constexpr int TT = T * NT;
+  constexpr uint32_t kTileBytes = kSrcTile * kRecReals * sizeof(real);
+  __shared__ __align__(128) real sbuf[2][kSrcTile * kRecReals];
+  __shared__ __align__(8) unsigned long long mbar[2];
+
+  const int tid = threadIdx.x;
+  const int ns = A.plan.n_src_tiles;
+  const long long U = (long long)A.plan.n_tgt_tiles * ns;
+  const long long g0 = U * blockIdx.x / gridDim.x;
+  const long long g1 = U * (blockIdx.x + 1) / gridDim.x;
+  if (g0 >= g1) return;  // CTA-uniform: more CTAs than units
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  int ttile = (int)(g0 / ns);
+  int stile = (int)(g0 - (long long)ttile * ns);
+  const int first_ttile = ttile;
+  if (tid == 0) {
+    mbar_expect_tx(&mbar[0], kTileBytes);
+    tma_load_1d(sbuf[0], A.rec + (size_t)stile * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
+  }
+
+  real xi[T], yi[T], zi[T], ux[T], uy[T], uz[T];
+  bool fresh = true;       // accumulators must be (re)initialised for `ttile`
+  bool seg_from_start = (stile == 0);
+  const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
+
+  for (long long g = g0; g < g1; ++g) {
+    const int it = (int)(g - g0);
+    const int buf = it & 1;
+    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+
+    // prefetch the next unit's source tile into the other stage (it was released by
+    // the __syncthreads at the end of the previous iteration)
+    if (tid == 0 && g + 1 < g1) {
+      int nst = stile + 1 == ns ? 0 : stile + 1;
+      mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
+      tma_load_1d(sbuf[buf ^ 1], A.rec + (size_t)nst * kSrcTile * kRecReals, kTileBytes,
+                  &mbar[buf ^ 1]);
+    }
+
+    if (fresh) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        int li = ttile * TT + tid + t * NT;
+        if (li >= A.plan.n_tgt) li = A.plan.n_tgt - 1;  // padding lanes recompute the last target
+        const real* p = A.rec + (size_t)(A.plan.tgt_first + li) * kRecReals;
+        xi[t] = p[0];
+        yi[t] = p[1];
+        zi[t] = p[2];
+        ux[t] = uy[t] = uz[t] = (real)0;
+      }
+      fresh = false;
+    }
+
+    const bool far =
+        box_gap2(A.box_tgt + 6 * (size_t)ttile, A.box_src + 6 * (size_t)stile) > near2;
+
+    mbar_wait(&mbar[buf], parity);
+    if (far)
+      tile_compute<WALL, false, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz);
+    else
+      tile_compute<WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz);
+    __syncthreads();  // every thread is done with sbuf[buf] before it is refilled
+
+    const bool tile_end = (stile + 1 == ns);
+    if (tile_end || g + 1 == g1) {
+      const bool complete = seg_from_start && tile_end;
+      if (complete) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int li = ttile * TT + tid + t * NT;
+          if (li < A.plan.n_tgt) {
+            real sc = A.C.out_scale;
+            if (WALL) sc *= damp(zi[t], A.C.a, A.C.inv_a);
+            A.out[3 * (size_t)li + 0] = ux[t] * sc;
+            A.out[3 * (size_t)li + 1] = uy[t] * sc;
+            A.out[3 * (size_t)li + 2] = uz[t] * sc;
+          }
+        }
+      } else {
+        const size_t slot = 2 * (size_t)blockIdx.x + (ttile == first_ttile ? 0 : 1);
+        real* sp = A.scratch + slot * 3 * TT;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int l = tid + t * NT;
+          sp[l] = ux[t];
+          sp[TT + l] = uy[t];
+          sp[2 * TT + l] = uz[t];
+        }
+      }
+      fresh = true;
+      seg_from_start = true;
+    }
+    if (tile_end) {
+      stile = 0;
+      ++ttile;
+    } else {
+      ++stile;
+    }
+  }
+}
+
+// Sums the scratch slots of target tiles that were split between CTAs, in CTA order.
+template <typename real, bool WALL>
+__global__ void rpy_fixup_kernel(const MatvecArgs<real> A) {
+  const int t = blockIdx.x;
+  const int TT = A.plan.tgt_tile;
+  const int ns = A.plan.n_src_tiles;
+  const long long G = A.plan.grid;
+  const long long U = (long long)A.plan.n_tgt_tiles * ns;
+  const long long b = (long long)t * ns, e = b + ns;
+  long long c = b * G / U;
+  while (c > 0 && U * c / G > b) --c;
+  while (U * (c + 1) / G <= b) ++c;
+  {
+    const long long g0 = U * c / G, g1 = U * (c + 1) / G;
+    if (g0 <= b && g1 >= e) return;  // one CTA owned the whole tile and wrote it itself
+  }
+  for (int l = threadIdx.x; l < TT; l += blockDim.x) {
+    const int li = t * TT + l;
+    if (li >= A.plan.n_tgt) break;
+    real sx = 0, sy = 0, sz = 0;
+    for (long long cc = c; cc < G; ++cc) {
+      const long long g0 = U * cc / G;
+      if (g0 >= e) break;
+      const long long g1 = U * (cc + 1) / G;
+      if (g0 >= g1) continue;
+      const int first_tt = (int)(g0 / ns);
+      const size_t slot = 2 * (size_t)cc + (t == first_tt ? 0 : 1);
+      const real* sp = A.scratch + slot * 3 * TT;
+      sx += sp[l];
+      sy += sp[TT + l];
+      sz += sp[2 * TT + l];
+    }
+    real sc = A.C.out_scale;
+    if (WALL) {
+      const real z = A.rec[(size_t)(A.plan.tgt_first + li) * kRecReals + 2];
+      sc *= damp(z, A.C.a, A.C.inv_a);
+    }
+    A.out[3 * (size_t)li + 0] = sx * sc;
+    A.out[3 * (size_t)li + 1] = sy * sc;
+    A.out[3 * (size_t)li + 2] = sz * sc;
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// variants, planning, launch
+// ----------------------------------------------------------------------------------
+#define RBL_F32_VARIANTS(X) X(4, 256) X(8, 128) X(4, 128) X(2, 256) X(8, 256) X(1, 128)
+#define RBL_F64_VARIANTS(X) X(2, 256) X(4, 128) X(2, 128) X(4, 256) X(1, 256) X(1, 128)
+
+template <>
+int matvec_num_variants<float>() { return 6; }
+template <>
+int matvec_num_variants<double>() { return 6; }
+
+template <>
+MatvecVariant matvec_variant<float>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F32_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+template <>
+MatvecVariant matvec_variant<double>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F64_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t occupancy_of(int* blocks_per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      blocks_per_sm, rpy_matvec_kernel<real, WALL, T, NT>, NT, 0);
+}
+
+template <typename real>
+static cudaError_t variant_occupancy(int variant, bool wall, int* bps);
+
+template <>
+cudaError_t variant_occupancy<float>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT)                                                              \
+  if (variant == k++)                                                         \
+    return wall ? occupancy_of<float, true, T, NT>(bps) : occupancy_of<float, false, T, NT>(bps);
+  RBL_F32_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t variant_occupancy<double>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT)                                                              \
+  if (variant == k++)                                                         \
+    return wall ? occupancy_of<double, true, T, NT>(bps) : occupancy_of<double, false, T, NT>(bps);
+  RBL_F64_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+template <typename real>
+cudaError_t matvec_plan(int variant, bool wall, int n_src, int tgt_first, int n_tgt,
+                        int sm_count, MatvecPlan* plan) {
+  if (variant < 0 || variant >= matvec_num_variants<real>()) return cudaErrorInvalidValue;
+  const MatvecVariant v = matvec_variant<real>(variant);
+  int bps = 0;
+  cudaError_t e = variant_occupancy<real>(variant, wall, &bps);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) return cudaErrorLaunchOutOfResources;
+  plan->n_src = n_src;
+  plan->n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
+  plan->tgt_first = tgt_first;
+  plan->n_tgt = n_tgt;
+  plan->tgt_tile = v.T * v.threads;
+  plan->n_tgt_tiles = (n_tgt + plan->tgt_tile - 1) / plan->tgt_tile;
+  plan->grid = sm_count * bps;
+  return cudaSuccess;
+}
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t launch_one(const MatvecArgs<real>& a, cudaStream_t s, cudaEvent_t ev0,
+                              cudaEvent_t ev1) {
+  if (ev0) cudaEventRecord(ev0, s);
+  rpy_matvec_kernel<real, WALL, T, NT><<<a.plan.grid, NT, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (ev1) cudaEventRecord(ev1, s);
+  rpy_fixup_kernel<real, WALL><<<a.plan.n_tgt_tiles, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <>
+cudaError_t matvec_launch<float>(int variant, const MatvecArgs<float>& a, cudaStream_t s,
+                                 cudaEvent_t ev0, cudaEvent_t ev1) {
+  if (a.plan.n_tgt <= 0 || a.plan.n_src <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT)                                                   \
+  if (variant == k++)                                              \
+    return a.wall ? launch_one<float, true, T, NT>(a, s, ev0, ev1) : launch_one<float, false, T, NT>(a, s, ev0, ev1);
+  RBL_F32_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t matvec_launch<double>(int variant, const MatvecArgs<double>& a, cudaStream_t s,
+                                  cudaEvent_t ev0, cudaEvent_t ev1) {
+  if (a.plan.n_tgt <= 0 || a.plan.n_src <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT)                                                   \
+  if (variant == k++)                                              \
+    return a.wall ? launch_one<double, true, T, NT>(a, s, ev0, ev1) : launch_one<double, false, T, NT>(a, s, ev0, ev1);
+  RBL_F64_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// ----------------------------------------------------------------------------------
+// FMA-pipe peak microbenchmark: 16 independent FMA chains per thread, register operands
+// ----------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, real a, real b,
+                                                       real* __restrict__ sink) {
+  real x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = (real)(threadIdx.x + k) * (real)1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+    }
+  }
+  real s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
+  if (s == (real)123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+template <typename real>
+cudaError_t fma_peak_launch(int sm_count, int iters, real* sink, double* flops,
+                            cudaStream_t s) {
+  const int blocks = sm_count * 8, threads = 256;
+  fma_peak_kernel<real><<<blocks, threads, 0, s>>>(iters, (real)0.999, (real)1e-3, sink);
+  *flops = 2.0 * 16 * 8 * (double)iters * threads * blocks;
+  return cudaGetLastError();
+}
+
+// explicit instantiations
+#define INST(real)                                                                         \
+  template cudaError_t matvec_plan<real>(int, bool, int, int, int, int, MatvecPlan*);      \
+  template cudaError_t pack_records<real>(const real*, const real*, int, int, bool, real,  \
+                                          real*, int*, cudaStream_t);                      \
+  template cudaError_t repack_forces<real>(const real*, int, bool, real, real*,            \
+                                           cudaStream_t);                                  \
+  template cudaError_t tile_boxes<real>(const real*, int, int, int, float*, cudaStream_t); \
+  template cudaError_t fma_peak_launch<real>(int, int, real*, double*, cudaStream_t);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace rbl

@@ -1,0 +1,95 @@
+// rbl_matvec.cuh -- device-side interface of the RPY mobility product U = B M B F.
+//
+// Replaces  CManyBodies::rotne_prager_tensor + apply_M + make_damp_mat
+//           (/root/reference/src/c_rigid_obj.cpp:413-459, 618-659)
+// which assemble a dense 3N x 3N matrix and run a GEMV.  Here the product is
+// matrix-free: a persistent, stream-K scheduled, TMA-staged tiled n-body kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rbl_pair.cuh"
+
+namespace rbl {
+
+// One packed source/target record: 8 reals, 32 B (fp32) / 64 B (fp64), so a record
+// is exactly two (fp32) / four (fp64) 128-bit shared-memory loads and a source tile
+// is one contiguous 16-byte-aligned span for a 1-D TMA bulk copy.
+//   [0..2] position (unscaled)   [3..5] B_j * force   [6] 2 z   [7] 4 z^2
+constexpr int kRecReals = 8;
+
+// Source tile (records per TMA stage).  Compile-time so the inner loop unrolls with
+// immediate shared-memory offsets.
+constexpr int kSrcTile = 256;
+
+struct MatvecPlan {
+  int n_src;        // real sources
+  int n_src_tiles;  // ceil(n_src / kSrcTile); the record array is padded to this
+  int tgt_first;    // index (into the record array) of the first target
+  int n_tgt;        // number of targets
+  int n_tgt_tiles;  // ceil(n_tgt / targets-per-CTA-tile)
+  int tgt_tile;     // targets per CTA tile (= threads * T of the chosen variant)
+  int grid;         // persistent CTAs (multiple of the SM count)
+};
+
+template <typename real>
+struct MatvecArgs {
+  const real* rec;       // packed records, (n_src_tiles * kSrcTile) x 8
+  const float* box_src;  // per source tile: min xyz, max xyz
+  const float* box_tgt;  // per target tile
+  real* out;             // 3 * n_tgt, local target order
+  real* scratch;         // 2 * grid partial tiles, [slot][3][tgt_tile]
+  MatvecPlan plan;
+  PairConsts<real> C;
+  int wall;
+};
+
+// Which kernel variant to launch (targets per thread x threads per CTA).  0 = default.
+// Variants exist so the tile shape can be tuned on hardware without recompiling.
+struct MatvecVariant {
+  int T;
+  int threads;
+};
+
+template <typename real>
+int matvec_num_variants();
+template <typename real>
+MatvecVariant matvec_variant(int idx);
+
+// Plans a launch: picks tile sizes and the persistent grid from the occupancy of
+// the chosen variant on the current device.
+template <typename real>
+cudaError_t matvec_plan(int variant, bool wall, int n_src, int tgt_first, int n_tgt,
+                        int sm_count, MatvecPlan* plan);
+
+// Packs positions + forces into records (and flags blobs below the wall).
+//   r, F: 3 n reals each (blob-major xyz).  rec must hold n_src_tiles*kSrcTile records.
+//   below_wall_flag: device int, set to 1 if wall && any z < 0.
+template <typename real>
+cudaError_t pack_records(const real* r, const real* F, int n, int n_padded, bool wall,
+                         real a, real* rec, int* below_wall_flag, cudaStream_t s);
+
+// Only refreshes the force part of already packed records (positions unchanged).
+template <typename real>
+cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec,
+                          cudaStream_t s);
+
+// Axis-aligned boxes of consecutive groups of `tile` records starting at `first`.
+template <typename real>
+cudaError_t tile_boxes(const real* rec, int first, int count, int tile, float* boxes,
+                       cudaStream_t s);
+
+// The product itself: matvec kernel + deterministic fix-up of split target tiles.
+// If ev0/ev1 are non-null they are recorded immediately around the main kernel (the
+// roofline's "dominant kernel" duration, measured live on the launching stream).
+template <typename real>
+cudaError_t matvec_launch(int variant, const MatvecArgs<real>& args, cudaStream_t s,
+                          cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+
+// FMA-pipe peak microbenchmark (the roofline denominator SURVEY.md section 8d asks for).
+// Returns flop executed; time it with events around the call.
+template <typename real>
+cudaError_t fma_peak_launch(int sm_count, int iters, real* sink, double* flops,
+                            cudaStream_t s);
+
+}  // namespace rbl

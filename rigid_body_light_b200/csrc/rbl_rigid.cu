@@ -1,0 +1,669 @@
+// rbl_rigid.cu -- O(N) rigid-body kernels (placement, K, K^T, preconditioner, integrator).
+// See rbl_rigid.cuh for the reference members each kernel replaces.
+#include <cmath>
+
+#include "rbl_rigid.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace rbl {
+
+namespace {
+
+// Rotation matrix of a unit quaternion stored [w,x,y,z] (Eigen toRotationMatrix, used at
+// c_rigid_obj.cpp:258,308).  Row-major R[9].
+template <typename real>
+__device__ __forceinline__ void quat_to_rot(const real* __restrict__ q, real* R) {
+  const real w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z);     R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y);     R[7] = 2 * (y * z + w * x);     R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// block-wide sum of NV values per thread; result valid in thread 0 (and in `red[0..NV)`)
+template <typename real, int NV>
+__device__ __forceinline__ void block_sum(real (&v)[NV], real* red /* [32*NV] smem */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[wid * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      real s = red[k];
+      for (int w = 1; w < nw; ++w) s += red[w * NV + k];
+      v[k] = s;
+      red[k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// 6x6 Cholesky (lower, row-major) in place; returns false if not SPD (Eigen LLT has no
+// pivoting either, c_rigid_obj.cpp:562)
+template <typename real>
+__device__ bool chol6(real* A) {
+  bool ok = true;
+  for (int j = 0; j < 6; ++j) {
+    real d = A[j * 6 + j];
+    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+    if (!(d > (real)0)) ok = false;
+    d = sqrt(d);
+    A[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      real s = A[i * 6 + j];
+      for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = s / d;
+    }
+    for (int i = 0; i < j; ++i) A[i * 6 + j] = 0;
+  }
+  return ok;
+}
+template <typename real>
+__device__ void chol6_solve(const real* __restrict__ L, real* b) {
+  for (int i = 0; i < 6; ++i) {
+    real s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    b[i] = s / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    real s = b[i];
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
+    b[i] = s / L[i * 6 + i];
+  }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------
+template <typename real>
+__global__ void normalize_quats_kernel(real* Q, int n_bod) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bod) return;
+  real w = Q[4 * b], x = Q[4 * b + 1], y = Q[4 * b + 2], z = Q[4 * b + 3];
+  real n = sqrt(w * w + x * x + y * y + z * z);
+  if (n > (real)0) {  // Eigen's normalize() leaves a zero quaternion untouched
+    Q[4 * b] = w / n; Q[4 * b + 1] = x / n; Q[4 * b + 2] = y / n; Q[4 * b + 3] = z / n;
+  }
+}
+template <typename real>
+cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  normalize_quats_kernel<real><<<(n_bod + 127) / 128, 128, 0, s>>>(Q, n_bod);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
+                                   const real* __restrict__ ref, int n_bod, int n_blb,
+                                   real* __restrict__ r) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_bod * n_blb) return;
+  const int b = (int)(i / n_blb), k = (int)(i - (long long)b * n_blb);
+  real R[9];
+  quat_to_rot(Q + 4 * (size_t)b, R);
+  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
+  r[3 * i + 0] = R[0] * cx + R[1] * cy + R[2] * cz + X[3 * (size_t)b + 0];
+  r[3 * i + 1] = R[3] * cx + R[4] * cy + R[5] * cz + X[3 * (size_t)b + 1];
+  r[3 * i + 2] = R[6] * cx + R[7] * cy + R[8] * cz + X[3 * (size_t)b + 2];
+}
+template <typename real>
+cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod, int n_blb,
+                        real* r, cudaStream_t s) {
+  const long long n = (long long)n_bod * n_blb;
+  if (n <= 0) return cudaSuccess;
+  place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void k_dot_kernel(const real* __restrict__ U, const real* __restrict__ r,
+                             const real* __restrict__ X, int n_bod, int n_blb, real sign,
+                             const real* add, real* out) {  // add may alias out
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_bod * n_blb) return;
+  const int b = (int)(i / n_blb);
+  const real* u = U + 6 * (size_t)b;
+  const real px = r[3 * i] - X[3 * (size_t)b], py = r[3 * i + 1] - X[3 * (size_t)b + 1],
+             pz = r[3 * i + 2] - X[3 * (size_t)b + 2];
+  real vx = u[0] + (u[4] * pz - u[5] * py);
+  real vy = u[1] + (u[5] * px - u[3] * pz);
+  real vz = u[2] + (u[3] * py - u[4] * px);
+  vx *= sign; vy *= sign; vz *= sign;
+  if (add) { vx += add[3 * i]; vy += add[3 * i + 1]; vz += add[3 * i + 2]; }
+  out[3 * i] = vx; out[3 * i + 1] = vy; out[3 * i + 2] = vz;
+}
+template <typename real>
+cudaError_t k_dot(const real* U, const real* r, const real* X, int n_bod, int n_blb,
+                  real sign, const real* add, real* out, cudaStream_t s) {
+  const long long n = (long long)n_bod * n_blb;
+  if (n <= 0) return cudaSuccess;
+  k_dot_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(U, r, X, n_bod, n_blb, sign, add, out);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void kt_dot_kernel(const real* __restrict__ lam, const real* __restrict__ r,
+                              const real* __restrict__ X, int n_blb, real* __restrict__ out) {
+  __shared__ real red[32 * 6];
+  const int b = blockIdx.x;
+  const real X0 = X[3 * (size_t)b], X1 = X[3 * (size_t)b + 1], X2 = X[3 * (size_t)b + 2];
+  real v[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = threadIdx.x; k < n_blb; k += blockDim.x) {
+    const size_t i = (size_t)b * n_blb + k;
+    const real lx = lam[3 * i], ly = lam[3 * i + 1], lz = lam[3 * i + 2];
+    const real px = r[3 * i] - X0, py = r[3 * i + 1] - X1, pz = r[3 * i + 2] - X2;
+    v[0] += lx; v[1] += ly; v[2] += lz;
+    v[3] += py * lz - pz * ly;
+    v[4] += pz * lx - px * lz;
+    v[5] += px * ly - py * lx;
+  }
+  block_sum<real, 6>(v, red);
+  if (threadIdx.x < 6) out[6 * (size_t)b + threadIdx.x] = red[threadIdx.x];
+}
+static inline int body_block(int n_blb) { return n_blb <= 32 ? 32 : n_blb <= 64 ? 64 : n_blb <= 128 ? 128 : 256; }
+template <typename real>
+cudaError_t kt_dot(const real* lam, const real* r, const real* X, int n_bod, int n_blb,
+                   real* out, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  kt_dot_kernel<real><<<n_bod, body_block(n_blb), 0, s>>>(lam, r, X, n_blb, out);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void ktk_inv_blocks_kernel(const real* __restrict__ Q, const real* __restrict__ ref,
+                                      int n_bod, int n_blb, real* __restrict__ S,
+                                      int* __restrict__ singular) {
+  // every thread recomputes the (tiny) reference-shape moments; n_blb is small
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bod) return;
+  double sumr2 = 0, m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < n_blb; ++k) {
+    const double x = ref[3 * k], y = ref[3 * k + 1], z = ref[3 * k + 2];
+    sumr2 += x * x + y * y + z * z;
+    m[0] += x * x; m[1] += x * y; m[2] += x * z;
+    m[4] += y * y; m[5] += y * z; m[8] += z * z;
+  }
+  m[3] = m[1]; m[6] = m[2]; m[7] = m[5];
+  real Rr[9];
+  quat_to_rot(Q + 4 * (size_t)b, Rr);
+  double R[9], T[9], D[9];
+  for (int i = 0; i < 9; ++i) R[i] = Rr[i];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = R[3 * i] * m[j] + R[3 * i + 1] * m[3 + j] + R[3 * i + 2] * m[6 + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      D[3 * i + j] = (i == j ? sumr2 : 0.0) - (T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2]);
+  const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
+  const double det = D[0] * c00 + D[1] * c01 + D[2] * c02;
+  if (det < 1.0e-13) *singular = 1;  // c_rigid_obj.cpp:312-316
+  const double id = 1.0 / det;
+  real* o = S + 9 * (size_t)b;
+  o[0] = (real)(c00 * id); o[1] = (real)((D[2] * D[7] - D[1] * D[8]) * id); o[2] = (real)((D[1] * D[5] - D[2] * D[4]) * id);
+  o[3] = (real)(c01 * id); o[4] = (real)((D[0] * D[8] - D[2] * D[6]) * id); o[5] = (real)((D[2] * D[3] - D[0] * D[5]) * id);
+  o[6] = (real)(c02 * id); o[7] = (real)((D[1] * D[6] - D[0] * D[7]) * id); o[8] = (real)((D[0] * D[4] - D[1] * D[3]) * id);
+}
+template <typename real>
+cudaError_t ktk_inv_blocks(const real* Q, const real* ref, int n_bod, int n_blb, real* S,
+                           int* singular, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  ktk_inv_blocks_kernel<real><<<(n_bod + 127) / 128, 128, 0, s>>>(Q, ref, n_bod, n_blb, S, singular);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void ktk_inv_apply_kernel(const real* __restrict__ S, int n_bod, real inv_nblb,
+                                     real* __restrict__ v) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bod) return;
+  real* p = v + 6 * (size_t)b;
+  const real* m = S + 9 * (size_t)b;
+  const real t0 = p[3], t1 = p[4], t2 = p[5];
+  p[0] *= inv_nblb; p[1] *= inv_nblb; p[2] *= inv_nblb;
+  p[3] = m[0] * t0 + m[1] * t1 + m[2] * t2;
+  p[4] = m[3] * t0 + m[4] * t1 + m[5] * t2;
+  p[5] = m[6] * t0 + m[7] * t1 + m[8] * t2;
+}
+template <typename real>
+cudaError_t ktk_inv_apply(const real* S, int n_bod, int n_blb, real* v, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  ktk_inv_apply_kernel<real><<<(n_bod + 127) / 128, 128, 0, s>>>(S, n_bod, (real)1 / (real)n_blb, v);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------
+// preconditioner
+// ----------------------------------------------------------------------------------
+template <typename real>
+__global__ void pc_diag_build_kernel(const real* __restrict__ r, int n, real a, real scale,
+                                     int wall, real* __restrict__ dinv, int* __restrict__ below) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const real f43 = (real)4 / (real)3;
+  real mxx = f43, mzz = f43;
+  if (wall) {
+    const real h = r[3 * (size_t)i + 2] / a;
+    if (h < (real)0) *below = 1;  // c_rigid_obj.cpp:95-97
+    const real inv = (real)1 / h, i3 = inv * inv * inv, i5 = i3 * inv * inv;
+    mxx += -(9 * inv - 2 * i3 + i5) / (real)12;  // :102-103
+    mzz += -(9 * inv - 4 * i3 + i5) / (real)6;   // :104
+  }
+  dinv[3 * (size_t)i] = scale / mxx;  // inverse of a diagonal 3x3 (:524), times 8 pi eta a (:540)
+  dinv[3 * (size_t)i + 1] = scale / mxx;
+  dinv[3 * (size_t)i + 2] = scale / mzz;
+}
+template <typename real>
+cudaError_t pc_diag_build(const real* r, int n, real a, real eta, bool wall, real* dinv,
+                          int* below, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const real scale = (real)(8.0 * M_PI * (double)eta * (double)a);
+  pc_diag_build_kernel<real><<<(n + 255) / 256, 256, 0, s>>>(r, n, a, scale, wall ? 1 : 0, dinv, below);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void pc_diag_mul_kernel(const real* __restrict__ dinv, const real* __restrict__ in,
+                                   int sz, int ncols, long long total, real* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long per_body = (long long)sz * ncols;
+  const long long b = i / per_body;
+  const int row = (int)((i - b * per_body) % sz);
+  out[i] = dinv[b * sz + row] * in[i];
+}
+template <typename real>
+cudaError_t pc_diag_mul(const real* dinv, const real* in, int n_bod, int n_blb, int ncols,
+                        real* out, cudaStream_t s) {
+  const long long total = (long long)n_bod * 3 * n_blb * ncols;
+  if (total <= 0) return cudaSuccess;
+  pc_diag_mul_kernel<real><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dinv, in, 3 * n_blb, ncols, total, out);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void pc_fill_kcols_kernel(const real* __restrict__ r, const real* __restrict__ X,
+                                     int n_bod, int n_blb, real* __restrict__ Kc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_bod * n_blb) return;
+  const int b = (int)(i / n_blb), k = (int)(i - (long long)b * n_blb);
+  const int sz = 3 * n_blb;
+  const real px = r[3 * i] - X[3 * (size_t)b], py = r[3 * i + 1] - X[3 * (size_t)b + 1],
+             pz = r[3 * i + 2] - X[3 * (size_t)b + 2];
+  real* o = Kc + (size_t)b * 6 * sz + 3 * k;
+  // rows of K for blob k (c_rigid_obj.cpp:370-382): [I | -[rho]x]
+  const real col[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, -pz, py}, {pz, 0, -px}, {-py, px, 0}};
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    o[(size_t)c * sz + 0] = col[c][0];
+    o[(size_t)c * sz + 1] = col[c][1];
+    o[(size_t)c * sz + 2] = col[c][2];
+  }
+}
+template <typename real>
+cudaError_t pc_fill_kcols(const real* r, const real* X, int n_bod, int n_blb, real* Kc,
+                          cudaStream_t s) {
+  const long long n = (long long)n_bod * n_blb;
+  if (n <= 0) return cudaSuccess;
+  pc_fill_kcols_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r, X, n_bod, n_blb, Kc);
+  return cudaGetLastError();
+}
+
+// 3x3 block of the (8 pi eta a)-normalised mobility between blobs at ri, rj, following the
+// reference's formulas for ENTRIES (c_rigid_obj.cpp:31-142) -- set-up path, not hot.
+template <typename real>
+__device__ void mobility_block(const real* ri, const real* rj, bool self, real a, bool wall,
+                               real* B) {
+  const real f43 = (real)4 / (real)3;
+  const real inv_a = (real)1 / a;
+  real rx = (ri[0] - rj[0]) * inv_a, ry = (ri[1] - rj[1]) * inv_a, rz = (ri[2] - rj[2]) * inv_a;
+  if (self) {
+    B[0] = f43; B[1] = 0; B[2] = 0; B[3] = 0; B[4] = f43; B[5] = 0; B[6] = 0; B[7] = 0; B[8] = f43;
+  } else {
+    const real r2 = rx * rx + ry * ry + rz * rz;
+    const real rr = sqrt(r2);
+    const real invr = (real)1 / rr, invr2 = invr * invr;
+    real c1, c2, sc;
+    if (rr >= (real)2) {
+      c1 = (real)1 + (real)2 / ((real)3 * r2);
+      c2 = ((real)1 - (real)2 * invr2) * invr2;
+      sc = invr;
+    } else {
+      c1 = f43 * ((real)1 - (real)0.28125 * rr);
+      c2 = f43 * (real)0.09375 * invr;
+      sc = 1;
+    }
+    B[0] = (c1 + c2 * rx * rx) * sc; B[1] = (c2 * rx * ry) * sc; B[2] = (c2 * rx * rz) * sc;
+    B[4] = (c1 + c2 * ry * ry) * sc; B[5] = (c2 * ry * rz) * sc; B[8] = (c1 + c2 * rz * rz) * sc;
+    B[3] = B[1]; B[6] = B[2]; B[7] = B[5];
+  }
+  if (wall) {
+    const real hj = rj[2] * inv_a;
+    if (self) {
+      const real inv = (real)1 / hj, i3 = inv * inv * inv, i5 = i3 * inv * inv;
+      B[0] += -(9 * inv - 2 * i3 + i5) / (real)12;
+      B[4] += -(9 * inv - 2 * i3 + i5) / (real)12;
+      B[8] += -(9 * inv - 4 * i3 + i5) / (real)6;
+    } else {
+      const real Rz = (ri[2] + rj[2]) * inv_a;
+      const real hh = hj / Rz;
+      const real invR = (real)1 / sqrt(rx * rx + ry * ry + Rz * Rz);
+      const real ex = rx * invR, ey = ry * invR, ez = Rz * invR;
+      const real invR3 = invR * invR * invR, invR5 = invR3 * invR * invR;
+      const real f1 = -(3 * (1 + 2 * hh * (1 - hh) * ez * ez) * invR + 2 * (1 - 3 * ez * ez) * invR3 - 2 * (1 - 5 * ez * ez) * invR5) / (real)3;
+      const real f2 = -(3 * (1 - 6 * hh * (1 - hh) * ez * ez) * invR - 6 * (1 - 5 * ez * ez) * invR3 + 10 * (1 - 7 * ez * ez) * invR5) / (real)3;
+      const real f3 = ez * (3 * hh * (1 - 6 * (1 - hh) * ez * ez) * invR - 6 * (1 - 5 * ez * ez) * invR3 + 10 * (2 - 7 * ez * ez) * invR5) * (real)2 / (real)3;
+      const real f4 = ez * (3 * hh * invR - 10 * invR5) * (real)2 / (real)3;
+      const real f5 = -(3 * hh * hh * ez * ez * invR + 3 * ez * ez * invR3 + (2 - 15 * ez * ez) * invR5) * (real)4 / (real)3;
+      B[0] += f1 + f2 * ex * ex; B[1] += f2 * ex * ey; B[2] += f2 * ex * ez + f3 * ex;
+      B[3] += f2 * ey * ex; B[4] += f1 + f2 * ey * ey; B[5] += f2 * ey * ez + f3 * ey;
+      B[6] += f2 * ez * ex + f4 * ex; B[7] += f2 * ez * ey + f4 * ey;
+      B[8] += f1 + f2 * ez * ez + f3 * ez + f4 * ez + f5;
+    }
+  }
+}
+
+template <typename real>
+__global__ void pc_block_assemble_kernel(const real* __restrict__ r, int n_blb, real a,
+                                         real norm, int wall, real* __restrict__ M,
+                                         int* __restrict__ below) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_blb * n_blb) return;
+  const int i = idx / n_blb, j = idx - i * n_blb;
+  if (i > j) return;  // upper triangle, mirrored below (c_rigid_obj.cpp:449-452)
+  const real* rb = r + 3 * (size_t)b * n_blb;
+  if (wall && i == j && rb[3 * i + 2] < (real)0) *below = 1;
+  real B[9];
+  mobility_block(rb + 3 * i, rb + 3 * j, i == j, a, wall != 0, B);
+  const int sz = 3 * n_blb;
+  real* Mb = M + (size_t)b * sz * sz;
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const real v = B[3 * p + q] * norm;
+      Mb[(size_t)(3 * i + p) * sz + 3 * j + q] = v;
+      if (i != j) Mb[(size_t)(3 * j + q) * sz + 3 * i + p] = v;
+    }
+}
+template <typename real>
+cudaError_t pc_block_assemble(const real* r, int count, int n_blb, real a, real eta,
+                              bool wall, real* M, int* below, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  const real norm = (real)((real)1.0 / (8.0 * M_PI * (double)eta * (double)a));
+  dim3 grid((n_blb * n_blb + 255) / 256, count);
+  pc_block_assemble_kernel<real><<<grid, 256, 0, s>>>(r, n_blb, a, norm, wall ? 1 : 0, M, below);
+  return cudaGetLastError();
+}
+
+// In-place Gauss-Jordan inverse without pivoting (safe for SPD), one CTA per matrix.
+template <typename real>
+__global__ void pc_block_invert_kernel(real* __restrict__ M, int sz, int* __restrict__ not_spd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* row = reinterpret_cast<real*>(smem_raw);
+  real* col = row + sz;
+  real* A = M + (size_t)blockIdx.x * sz * sz;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = 0; k < sz; ++k) {
+    for (int j = threadIdx.x; j < sz; j += blockDim.x) {
+      row[j] = A[(size_t)k * sz + j];
+      col[j] = A[(size_t)j * sz + k];
+    }
+    __syncthreads();
+    const real piv = row[k];
+    if (threadIdx.x == 0 && !(piv > (real)0)) *not_spd = 1;
+    const real p = (real)1 / piv;
+    for (int i = wid; i < sz; i += nw) {
+      real* Ai = A + (size_t)i * sz;
+      if (i == k) {
+        for (int j = lane; j < sz; j += 32) Ai[j] = (j == k) ? p : row[j] * p;
+      } else {
+        const real f = col[i] * p;
+        for (int j = lane; j < sz; j += 32) Ai[j] = (j == k) ? -f : Ai[j] - f * row[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+template <typename real>
+cudaError_t pc_block_invert(real* M, int count, int sz, int* not_spd, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  const size_t smem = 2 * (size_t)sz * sizeof(real);
+  const int threads = sz <= 128 ? 256 : 1024;
+  cudaError_t e = cudaFuncSetAttribute(pc_block_invert_kernel<real>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  pc_block_invert_kernel<real><<<count, threads, smem, s>>>(M, sz, not_spd);
+  return cudaGetLastError();
+}
+
+// out[b][c][:] = Minv_b in[b][c][:]; 192 output rows per CTA (blob aligned), thread per row,
+// symmetric matrix read column-wise so the loads coalesce.
+template <typename real>
+__global__ void pc_block_mul_kernel(const real* __restrict__ Minv, size_t stride,
+                                    const real* __restrict__ Q, const real* __restrict__ in,
+                                    int sz, int ncols, real* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* x = reinterpret_cast<real*>(smem_raw);  // sz
+  __shared__ real tile[192];
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 192 + threadIdx.x;
+  const real* A = Minv + stride * b;
+  const bool rot = (stride == 0) && (Q != nullptr);
+  real R[9];
+  if (rot) quat_to_rot(Q + 4 * (size_t)b, R);
+  for (int c = 0; c < ncols; ++c) {
+    const real* xin = in + ((size_t)b * ncols + c) * sz;
+    if (rot) {  // body frame: x = R^T x_lab per blob
+      for (int k = threadIdx.x; k < sz / 3; k += blockDim.x) {
+        const real vx = xin[3 * k], vy = xin[3 * k + 1], vz = xin[3 * k + 2];
+        x[3 * k + 0] = R[0] * vx + R[3] * vy + R[6] * vz;
+        x[3 * k + 1] = R[1] * vx + R[4] * vy + R[7] * vz;
+        x[3 * k + 2] = R[2] * vx + R[5] * vy + R[8] * vz;
+      }
+    } else {
+      for (int j = threadIdx.x; j < sz; j += blockDim.x) x[j] = xin[j];
+    }
+    __syncthreads();
+    real acc = 0;
+    if (row < sz) {
+#pragma unroll 8
+      for (int j = 0; j < sz; ++j) acc += A[(size_t)j * sz + row] * x[j];
+    }
+    real* o = out + ((size_t)b * ncols + c) * sz;
+    if (rot) {
+      tile[threadIdx.x] = acc;
+      __syncthreads();
+      if (row < sz) {
+        const int k3 = (threadIdx.x / 3) * 3, p = threadIdx.x - k3;
+        o[row] = R[3 * p] * tile[k3] + R[3 * p + 1] * tile[k3 + 1] + R[3 * p + 2] * tile[k3 + 2];
+      }
+    } else if (row < sz) {
+      o[row] = acc;
+    }
+    __syncthreads();
+  }
+}
+template <typename real>
+cudaError_t pc_block_mul(const real* Minv, size_t stride, const real* Q, const real* in,
+                         int n_bod, int n_blb, int ncols, real* out, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  const int sz = 3 * n_blb;
+  const size_t smem = (size_t)sz * sizeof(real);
+  cudaError_t e = cudaFuncSetAttribute(pc_block_mul_kernel<real>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((sz + 191) / 192, n_bod);
+  pc_block_mul_kernel<real><<<grid, 192, smem, s>>>(Minv, stride, Q, in, sz, ncols, out);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void pc_ninv_chol_kernel(const real* __restrict__ Y, const real* __restrict__ r,
+                                    const real* __restrict__ X, int n_blb, real* __restrict__ L,
+                                    int* __restrict__ not_spd) {
+  __shared__ real red[32 * 6];
+  __shared__ real N[36];
+  const int b = blockIdx.x, sz = 3 * n_blb;
+  const real X0 = X[3 * (size_t)b], X1 = X[3 * (size_t)b + 1], X2 = X[3 * (size_t)b + 2];
+  for (int c = 0; c < 6; ++c) {
+    const real* y = Y + ((size_t)b * 6 + c) * sz;
+    real v[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = threadIdx.x; k < n_blb; k += blockDim.x) {
+      const size_t i = (size_t)b * n_blb + k;
+      const real lx = y[3 * k], ly = y[3 * k + 1], lz = y[3 * k + 2];
+      const real px = r[3 * i] - X0, py = r[3 * i + 1] - X1, pz = r[3 * i + 2] - X2;
+      v[0] += lx; v[1] += ly; v[2] += lz;
+      v[3] += py * lz - pz * ly;
+      v[4] += pz * lx - px * lz;
+      v[5] += px * ly - py * lx;
+    }
+    block_sum<real, 6>(v, red);
+    if (threadIdx.x < 6) N[threadIdx.x * 6 + c] = red[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // symmetrise (K^T Minv K is symmetric up to rounding), factor
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < i; ++j) {
+        const real m = (real)0.5 * (N[i * 6 + j] + N[j * 6 + i]);
+        N[i * 6 + j] = m;
+        N[j * 6 + i] = m;
+      }
+    if (!chol6(N)) *not_spd = 1;
+    for (int i = 0; i < 36; ++i) L[36 * (size_t)b + i] = N[i];
+  }
+}
+template <typename real>
+cudaError_t pc_ninv_chol(const real* Y, const real* r, const real* X, int n_bod, int n_blb,
+                         real* L, int* not_spd, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  pc_ninv_chol_kernel<real><<<n_bod, body_block(n_blb), 0, s>>>(Y, r, X, n_blb, L, not_spd);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void pc_finish_kernel(const real* __restrict__ y, const real* __restrict__ F,
+                                 const real* __restrict__ Y, const real* __restrict__ L,
+                                 const real* __restrict__ r, const real* __restrict__ X,
+                                 int n_bod, int n_blb, real* __restrict__ out) {
+  __shared__ real red[32 * 6];
+  __shared__ real Ub[6];
+  const int b = blockIdx.x, sz = 3 * n_blb;
+  const real X0 = X[3 * (size_t)b], X1 = X[3 * (size_t)b + 1], X2 = X[3 * (size_t)b + 2];
+  const real* yb = y + (size_t)b * sz;
+  real v[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = threadIdx.x; k < n_blb; k += blockDim.x) {
+    const size_t i = (size_t)b * n_blb + k;
+    const real lx = yb[3 * k], ly = yb[3 * k + 1], lz = yb[3 * k + 2];
+    const real px = r[3 * i] - X0, py = r[3 * i + 1] - X1, pz = r[3 * i + 2] - X2;
+    v[0] += lx; v[1] += ly; v[2] += lz;
+    v[3] += py * lz - pz * ly;
+    v[4] += pz * lx - px * lz;
+    v[5] += px * ly - py * lx;
+  }
+  block_sum<real, 6>(v, red);
+  if (threadIdx.x == 0) {
+    real rhs[6];
+    for (int c = 0; c < 6; ++c) rhs[c] = -F[6 * (size_t)b + c] - red[c];  // :601
+    chol6_solve(L + 36 * (size_t)b, rhs);                                  // :605-608
+    for (int c = 0; c < 6; ++c) Ub[c] = rhs[c];
+  }
+  __syncthreads();
+  const size_t n3 = (size_t)n_bod * sz;
+  const real* Yb = Y + (size_t)b * 6 * sz;
+  for (int i = threadIdx.x; i < sz; i += blockDim.x) {
+    real acc = yb[i];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc += Yb[(size_t)c * sz + i] * Ub[c];  // Mt^-1 (slip + K U), :610
+    out[(size_t)b * sz + i] = acc;
+  }
+  if (threadIdx.x < 6) out[n3 + 6 * (size_t)b + threadIdx.x] = Ub[threadIdx.x];
+}
+template <typename real>
+cudaError_t pc_finish(const real* y, const real* F, const real* Y, const real* L,
+                      const real* r, const real* X, int n_bod, int n_blb, real* out,
+                      cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  pc_finish_kernel<real><<<n_bod, body_block(n_blb), 0, s>>>(y, F, Y, L, r, X, n_bod, n_blb, out);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------
+// integrator (Q_from_Om :679-689, update_X_Q :691-710)
+// ----------------------------------------------------------------------------------
+template <typename real>
+__global__ void integrate_kernel(const real* __restrict__ U, real scale, int n_bod,
+                                 const real* X, const real* Q, real* Xo, real* Qo) {
+  // X/Xo and Q/Qo may alias (in-place evolve): each thread reads its body, then writes it
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bod) return;
+  const real* u = U + 6 * (size_t)b;
+  const real ox = u[3] * scale, oy = u[4] * scale, oz = u[5] * scale;
+  const double th = (double)sqrt(ox * ox + oy * oy + oz * oz);  // Om.norm() in `real`, then double
+  double rw = cos(th / 2.0), rx = 0, ry = 0, rz = 0;
+  if (th > 1.0e-10) {
+    const double sc = sin(th / 2.0) / th;
+    rx = sc * ox; ry = sc * oy; rz = sc * oz;
+  }
+  real pw = (real)rw, px = (real)rx, py = (real)ry, pz = (real)rz;
+  real n = sqrt(pw * pw + px * px + py * py + pz * pz);
+  pw /= n; px /= n; py /= n; pz /= n;
+  const real qw = Q[4 * (size_t)b], qx = Q[4 * (size_t)b + 1], qy = Q[4 * (size_t)b + 2], qz = Q[4 * (size_t)b + 3];
+  real w = pw * qw - px * qx - py * qy - pz * qz;
+  real x = pw * qx + px * qw + py * qz - pz * qy;
+  real y = pw * qy - px * qz + py * qw + pz * qx;
+  real z = pw * qz + px * qy - py * qx + pz * qw;
+  n = sqrt(w * w + x * x + y * y + z * z);
+  Qo[4 * (size_t)b] = w / n; Qo[4 * (size_t)b + 1] = x / n; Qo[4 * (size_t)b + 2] = y / n; Qo[4 * (size_t)b + 3] = z / n;
+  Xo[3 * (size_t)b] = X[3 * (size_t)b] + u[0] * scale;
+  Xo[3 * (size_t)b + 1] = X[3 * (size_t)b + 1] + u[1] * scale;
+  Xo[3 * (size_t)b + 2] = X[3 * (size_t)b + 2] + u[2] * scale;
+}
+template <typename real>
+cudaError_t integrate(const real* U, real scale, int n_bod, const real* X, const real* Q,
+                      real* Xo, real* Qo, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  integrate_kernel<real><<<(n_bod + 127) / 128, 128, 0, s>>>(U, scale, n_bod, X, Q, Xo, Qo);
+  return cudaGetLastError();
+}
+
+#define INST(real)                                                                                  \
+  template cudaError_t normalize_quats<real>(real*, int, cudaStream_t);                             \
+  template cudaError_t place_blobs<real>(const real*, const real*, const real*, int, int, real*,    \
+                                         cudaStream_t);                                             \
+  template cudaError_t k_dot<real>(const real*, const real*, const real*, int, int, real,           \
+                                   const real*, real*, cudaStream_t);                               \
+  template cudaError_t kt_dot<real>(const real*, const real*, const real*, int, int, real*,         \
+                                    cudaStream_t);                                                  \
+  template cudaError_t ktk_inv_blocks<real>(const real*, const real*, int, int, real*, int*,        \
+                                            cudaStream_t);                                          \
+  template cudaError_t ktk_inv_apply<real>(const real*, int, int, real*, cudaStream_t);             \
+  template cudaError_t pc_diag_build<real>(const real*, int, real, real, bool, real*, int*,         \
+                                           cudaStream_t);                                           \
+  template cudaError_t pc_diag_mul<real>(const real*, const real*, int, int, int, real*,            \
+                                         cudaStream_t);                                             \
+  template cudaError_t pc_fill_kcols<real>(const real*, const real*, int, int, real*,               \
+                                           cudaStream_t);                                           \
+  template cudaError_t pc_block_assemble<real>(const real*, int, int, real, real, bool, real*,      \
+                                               int*, cudaStream_t);                                 \
+  template cudaError_t pc_block_invert<real>(real*, int, int, int*, cudaStream_t);                  \
+  template cudaError_t pc_block_mul<real>(const real*, size_t, const real*, const real*, int, int,  \
+                                          int, real*, cudaStream_t);                                \
+  template cudaError_t pc_ninv_chol<real>(const real*, const real*, const real*, int, int, real*,   \
+                                          int*, cudaStream_t);                                      \
+  template cudaError_t pc_finish<real>(const real*, const real*, const real*, const real*,          \
+                                       const real*, const real*, int, int, real*, cudaStream_t);    \
+  template cudaError_t integrate<real>(const real*, real, int, const real*, const real*, real*,     \
+                                       real*, cudaStream_t);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace rbl

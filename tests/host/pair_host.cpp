@@ -1,0 +1,35 @@
+// pair_host.cpp -- compiles the kernel's per-pair arithmetic (rbl_pair.cuh) for the
+// HOST so the division-free / branch-free reformulation can be checked against the
+// oracle on a machine without a GPU (tests/test_pair_math_host.py).  Test code only:
+// this is not a CPU fallback and is never loaded by the package.
+#include "../../rigid_body_light_b200/csrc/rbl_pair.cuh"
+
+template <typename real>
+static void matvec(const real* F, const real* r, int n, double a, double eta, int wall,
+                   int near, real* U) {
+  rbl::PairConsts<real> C = rbl::make_pair_consts<real>(a, eta);
+  for (int i = 0; i < n; ++i) {
+    real ux = 0, uy = 0, uz = 0;
+    for (int j = 0; j < n; ++j) {
+      real zj = r[3 * j + 2];
+      real bj = wall ? (zj >= (real)a ? (real)1 : zj * C.inv_a) : (real)1;
+      real fx = bj * F[3 * j], fy = bj * F[3 * j + 1], fz = bj * F[3 * j + 2];
+      real z2 = 2 * zj, zz4 = 4 * zj * zj;
+      if (wall) {
+        if (near) rbl::pair<real, true, true>(C, r[3*i], r[3*i+1], r[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+        else      rbl::pair<real, true, false>(C, r[3*i], r[3*i+1], r[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+      } else {
+        if (near) rbl::pair<real, false, true>(C, r[3*i], r[3*i+1], r[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+        else      rbl::pair<real, false, false>(C, r[3*i], r[3*i+1], r[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+      }
+    }
+    real zi = r[3 * i + 2];
+    real bi = wall ? (zi >= (real)a ? (real)1 : zi * C.inv_a) : (real)1;
+    U[3 * i] = ux * C.out_scale * bi;
+    U[3 * i + 1] = uy * C.out_scale * bi;
+    U[3 * i + 2] = uz * C.out_scale * bi;
+  }
+}
+
+extern "C" void pair_matvec_host_f64(const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { matvec<double>(F, r, n, a, eta, wall, near, U); }
+extern "C" void pair_matvec_host_f32(const float* F, const float* r, int n, double a, double eta, int wall, int near, float* U) { matvec<float>(F, r, n, a, eta, wall, near, U); }
