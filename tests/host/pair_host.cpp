@@ -33,3 +33,28 @@ static void matvec(const real* F, const real* r, int n, double a, double eta, in
 
 extern "C" void pair_matvec_host_f64(const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { matvec<double>(F, r, n, a, eta, wall, near, U); }
 extern "C" void pair_matvec_host_f32(const float* F, const float* r, int n, double a, double eta, int wall, int near, float* U) { matvec<float>(F, r, n, a, eta, wall, near, U); }
+
+// targets and sources in separate arrays (no self pairs): lets the NEAR=false fast path,
+// which is only legal when every pair has r >= 2a, be compared with the general path
+template <typename real>
+static void cross(const real* rt, int nt, const real* F, const real* r, int n, double a, double eta,
+                  int wall, int near, real* U) {
+  rbl::PairConsts<real> C = rbl::make_pair_consts<real>(a, eta);
+  for (int i = 0; i < nt; ++i) {
+    real ux = 0, uy = 0, uz = 0;
+    for (int j = 0; j < n; ++j) {
+      real zj = r[3 * j + 2];
+      real fx = F[3 * j], fy = F[3 * j + 1], fz = F[3 * j + 2];
+      real z2 = 2 * zj, zz4 = 4 * zj * zj;
+      if (wall) {
+        if (near) rbl::pair<real, true, true>(C, rt[3*i], rt[3*i+1], rt[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+        else      rbl::pair<real, true, false>(C, rt[3*i], rt[3*i+1], rt[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+      } else {
+        if (near) rbl::pair<real, false, true>(C, rt[3*i], rt[3*i+1], rt[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+        else      rbl::pair<real, false, false>(C, rt[3*i], rt[3*i+1], rt[3*i+2], r[3*j], r[3*j+1], zj, fx, fy, fz, z2, zz4, ux, uy, uz);
+      }
+    }
+    U[3 * i] = ux; U[3 * i + 1] = uy; U[3 * i + 2] = uz;
+  }
+}
+extern "C" void pair_cross_host_f64(const double* rt, int nt, const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { cross<double>(rt, nt, F, r, n, a, eta, wall, near, U); }

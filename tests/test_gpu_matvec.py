@@ -1,0 +1,230 @@
+"""Parity of the CUDA mobility product with the oracle (GPU box only, -m gpu).
+
+Calls go through the reference-facing host class (Rigid.RigidBody -> c_rigid.CManyBodies ->
+C ABI) and, for the sharded/device entry points, through the C ABI directly via ctypes.
+Tolerances are BASELINE.json's: <= 1e-12 relative L2 in double, <= 1e-5 in float, with the
+float comparison made on the SAME float32-representable inputs on both sides."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import CASE_NAMES, TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["double", "single"]
+
+
+def _dtype(precision):
+    return np.float64 if precision == "double" else np.float32
+
+
+def _solver(g, precision, wall=None, block=False):
+    from Rigid import RigidBody
+
+    wall = bool(g["wall"]) if wall is None else wall
+    return RigidBody(g["cfg"], g["X"], g["Q"], float(g["a"]), float(g["eta"]), float(g["dt"]),
+                     wall_PC=wall, block_PC=block, precision=precision)
+
+
+def _oracle_for(orc, F, r, a, eta, wall, precision, rows=None):
+    dt = _dtype(precision)
+    F = np.asarray(F, dt).astype(np.float64)
+    r = np.asarray(r, dt).astype(np.float64)
+    return orc.apply_M(F, r, a, eta, wall, rows=rows)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_apply_M_matches_golden(orc, name, precision):
+    g = load_golden(name)
+    cb = _solver(g, precision)
+    assert cb.precision == precision
+    out = cb.apply_M(g["lam"], g["r"])
+    assert out.dtype == _dtype(precision) and out.shape == (g["lam"].size,)
+    if precision == "double":
+        assert rel_err(out, g["MF"]) < TOL["double"]
+    else:
+        want = _oracle_for(orc, g["lam"], g["r"], float(g["a"]), float(g["eta"]), bool(g["wall"]), precision)
+        assert rel_err(out, want) < TOL["single"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_apply_M_extra_free_blob(orc, precision):
+    """positions/forces may be longer than N_bodies*N_blobs (tests/test_interface.py:171-177)."""
+    g = load_golden("case_overlap_free")
+    cb = _solver(g, precision)
+    r = np.concatenate([g["r"].reshape(-1), [7.0, -3.0, 2.0]])
+    F = np.concatenate([g["lam"], [0.3, -0.2, 0.9]])
+    out = cb.apply_M(F, r)
+    assert rel_err(out, _oracle_for(orc, F, r, float(g["a"]), float(g["eta"]), False, precision)) < TOL[precision]
+
+
+def _random_cloud(n, wall, seed, a=0.11):
+    """non-overlapping-ish random blobs with a few deliberately overlapping pairs"""
+    rng = np.random.default_rng(seed)
+    side = max(2.0, (n ** (1 / 3)) * 3 * a)
+    r = rng.uniform(0, side, (n, 3))
+    if wall:
+        r[:, 2] = rng.uniform(0.2 * a, side, n)  # some inside the damping layer z < a
+    if n > 4:
+        r[1] = r[0] + [0.7 * a, 0, 0.1 * a]  # overlapping pair: r < 2a branch
+        r[3] = r[2] + [0, 2.0 * a, 0]        # exactly touching
+    return r, rng.standard_normal(3 * n)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("wall", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 31, 255, 256, 257, 1000, 1025, 4099])
+def test_ragged_sizes(orc, n, wall, precision):
+    """empty-ish / ragged inputs around the 256-source tile and the target-tile sizes"""
+    from rigid_body_light_b200._lib import Context
+
+    a, eta = 0.11, 0.9
+    r, F = _random_cloud(n, wall, seed=n)
+    ctx = Context(precision)
+    ctx.set_parameters(a, 0.01, 1.0, eta, np.zeros((1, 3)))
+    ctx.set_flags(0, wall)
+    out = ctx.apply_M(F, r)
+    assert rel_err(out, _oracle_for(orc, F, r, a, eta, wall, precision)) < TOL[precision]
+    ctx.close()
+
+
+def test_zero_blobs_is_a_no_op():
+    from rigid_body_light_b200._lib import Context
+
+    ctx = Context("double")
+    ctx.set_parameters(0.1, 0.01, 1.0, 1.0, np.zeros((1, 3)))
+    assert ctx.apply_M(np.zeros(0), np.zeros(0)).size == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("wall", [False, True])
+def test_every_kernel_variant_agrees(orc, wall, precision):
+    """all (targets/thread x threads/CTA) tile shapes compute the same product"""
+    from rigid_body_light_b200._lib import Context
+
+    a, eta = 0.11, 1.0
+    r, F = _random_cloud(3000, wall, seed=99)
+    want = _oracle_for(orc, F, r, a, eta, wall, precision)
+    ctx = Context(precision)
+    ctx.set_parameters(a, 0.01, 1.0, eta, np.zeros((1, 3)))
+    ctx.set_flags(0, wall)
+    nv = ctx.L.rbl_num_matvec_variants(ctx.h)
+    assert nv >= 2
+    for v in range(nv):
+        ctx.call("rbl_set_matvec_variant", v)
+        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], v
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_suspension_10k_blobs_full_oracle(orc, precision):
+    """64 spheres of shell_N_162 above the wall (10 368 blobs), every row against the oracle"""
+    from Rigid import RigidBody
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(64, 162, True)
+    cb = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, precision=precision)
+    r = cb.get_blob_positions()
+    F = np.random.default_rng(2).standard_normal(r.size)
+    out = cb.apply_M(F, r)
+    assert rel_err(out, _oracle_for(orc, F, r, s["a"], 1.0, True, precision)) < TOL[precision]
+
+
+@pytest.fixture(scope="module")
+def config2():
+    """BASELINE.json configs[1]: 1000 spheres of shell_N_162 above a wall, 162 000 blobs"""
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(1000, 162, True)
+    rng = np.random.default_rng(2)
+    return s, rng.standard_normal(3 * 162000), rng.standard_normal(3 * 162000)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_sampled_rows_and_properties(orc, config2, precision):
+    """At the benchmark size the oracle checks 96 sampled target rows; the whole vector is
+    checked through size-independent properties: symmetry <x, M y> = <M x, y> (M = B M B is
+    symmetric), linearity, and run-to-run bit reproducibility (no atomics)."""
+    from Rigid import RigidBody
+
+    s, F1, F2 = config2
+    cb = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, precision=precision)
+    r = cb.get_blob_positions()
+    dt = _dtype(precision)
+    F1, F2 = F1.astype(dt), F2.astype(dt)
+    u1 = cb.apply_M(F1, r)
+    u2 = cb.apply_M(F2, r)
+    rows = np.random.default_rng(5).choice(162000, 96, replace=False)
+    rows[:3] = [0, 161999, 81000]
+    want = _oracle_for(orc, F1, r, s["a"], 1.0, True, precision, rows=rows)
+    got = u1.reshape(-1, 3)[rows].reshape(-1)
+    assert rel_err(got, want) < TOL[precision]
+    sym = abs(np.dot(F2.astype(np.float64), u1.astype(np.float64)) - np.dot(F1.astype(np.float64), u2.astype(np.float64)))
+    scale = np.linalg.norm(F2) * np.linalg.norm(u1)
+    assert sym / scale < (1e-12 if precision == "double" else 2e-6)
+    u12 = cb.apply_M(F1 + dt(0.5) * F2, r)
+    assert rel_err(u12, u1.astype(np.float64) + 0.5 * u2.astype(np.float64)) < (1e-13 if precision == "double" else 2e-6)
+    assert np.array_equal(cb.apply_M(F1, r), u1)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_sharded_target_ranges_tile_the_full_product(orc, precision):
+    """rbl_dev_apply_M on body-aligned target ranges (what each rank of a multi-GPU run
+    computes) concatenates to the single-GPU result, bit for bit within a range layout."""
+    import torch
+
+    from rigid_body_light_b200._lib import Context
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(48, 42, True)
+    ref = s["cfg"] - s["cfg"].mean(axis=0)
+    dt = _dtype(precision)
+    tdt = torch.float64 if precision == "double" else torch.float32
+    ctx = Context(precision)
+    ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
+    ctx.set_flags(0, 1)
+    ctx.set_config(s["X"], s["Q"])
+    n = 48 * 42
+    r = torch.empty(3 * n, dtype=tdt, device="cuda")
+    ctx.call("rbl_dev_blob_positions", r.data_ptr())
+    ctx.call("rbl_sync")
+    F = torch.from_numpy(np.random.default_rng(3).standard_normal(3 * n).astype(dt)).cuda()
+    full = torch.empty(3 * n, dtype=tdt, device="cuda")
+    ctx.call("rbl_dev_apply_M", F.data_ptr(), r.data_ptr(), n, 0, n, full.data_ptr())
+    parts = []
+    for lo, hi in [(0, 13), (13, 14), (14, 40), (40, 48)]:  # body ranges
+        t0, nt = lo * 42, (hi - lo) * 42
+        o = torch.empty(3 * nt, dtype=tdt, device="cuda")
+        ctx.call("rbl_dev_apply_M", F.data_ptr(), r.data_ptr(), n, t0, nt, o.data_ptr())
+        parts.append(o)
+    ctx.call("rbl_sync")
+    got = torch.cat(parts).cpu().numpy()
+    want = _oracle_for(orc, F.cpu().numpy(), r.cpu().numpy(), s["a"], 1.0, True, precision)
+    assert rel_err(got, want) < TOL[precision]
+    assert rel_err(full.cpu().numpy(), want) < TOL[precision]
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_blob_below_wall_raises(precision):
+    """tests/test_wall.py:24-38"""
+    from Rigid import RigidBody
+    from rigid_body_light_b200.shells import icosphere_shell
+
+    _, cfg = icosphere_shell(12)
+    cb = RigidBody(cfg, np.array([[0.0, 0.0, 0.0]]), np.array([[1.0, 0, 0, 0]]), 1.0, 1.0, 1.0, wall_PC=True,
+                   precision=precision)
+    vec = np.random.default_rng(0).standard_normal(3 * 12 + 6)
+    with pytest.raises(RuntimeError):
+        cb.apply_M(vec[:36], cb.get_blob_positions())
+    with pytest.raises(RuntimeError):
+        cb.apply_saddle(vec)
+    with pytest.raises(RuntimeError):
+        cb.apply_PC(vec)
+    # the context stays usable afterwards
+    cb.set_config(np.array([[0.0, 0.0, 2.0]]), np.array([[1.0, 0, 0, 0]]))
+    assert np.linalg.norm(cb.apply_M(vec[:36], cb.get_blob_positions())) > 0

@@ -1,0 +1,196 @@
+"""Parity of the O(N) rigid-body kernels, the preconditioner, the fused saddle operator,
+the integrator and the Krylov drivers with the oracle / golden fixtures (-m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import CASE_NAMES, TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+PRECISIONS = ["double", "single"]
+# O(N) kernels are a handful of flops per output: float results carry ~1e-7
+TOL_ON = {"double": 1e-13, "single": 2e-6}
+# the preconditioner involves dense per-body inverses (cond ~1e2..1e4): stated tolerance
+TOL_PC = {"double": 1e-9, "single": 2e-3}
+
+
+def _solver(g, precision, block=False):
+    from Rigid import RigidBody
+
+    return RigidBody(g["cfg"], g["X"], g["Q"], float(g["a"]), float(g["eta"]), float(g["dt"]),
+                     wall_PC=bool(g["wall"]), block_PC=block, precision=precision)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_config_positions_K_KT_Kinv(name, precision):
+    g = load_golden(name)
+    cb = _solver(g, precision)
+    X, Q = cb.get_config()
+    assert X.shape == g["X"].shape and Q.shape == g["Q"].shape
+    assert np.allclose(X, g["X"], rtol=1e-6) and rel_err(Q, g["Qn"]) < TOL_ON[precision]
+    assert rel_err(cb.get_blob_positions(), g["r"]) < TOL_ON[precision]
+    assert cb.get_blob_positions().shape == g["r"].shape
+    assert rel_err(cb.K_dot(g["U"]), g["KU"]) < TOL_ON[precision]
+    assert rel_err(cb.KT_dot(g["lam"]), g["KTlam"]) < TOL_ON[precision]
+    assert cb.K_dot(g["U"].reshape(-1, 3)).shape == g["r"].shape
+    assert cb.KT_dot(g["lam"]).shape == (2 * g["X"].shape[0], 3)
+    assert rel_err(cb.Kinv_dot(g["lam"]), g["Kinv_lam"]) < 10 * TOL_ON[precision]
+    assert rel_err(cb.KTinv_dot(g["U"]), g["KinvT_U"]) < 10 * TOL_ON[precision]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["case_overlap_free", "case_touch_wall"])
+def test_sparse_K_and_Kinv_exports(name, precision):
+    """get_K / get_Kinv return scipy CSC matrices (tests/test_interface.py:112-122) equal
+    to the matrices Make_K_Kinv assembles (c_rigid_obj.cpp:328-393)."""
+    import scipy.sparse as sp
+
+    g = load_golden(name)
+    cb = _solver(g, precision)
+    K, Kinv = cb.get_K(), cb.get_Kinv()
+    n3, n6 = g["r"].size, 6 * g["X"].shape[0]
+    assert sp.issparse(K) and K.shape == (n3, n6) and Kinv.shape == (n6, n3)
+    assert rel_err(K @ g["U"], g["KU"]) < TOL_ON[precision]
+    assert rel_err(K.T @ g["lam"], g["KTlam"]) < TOL_ON[precision]
+    assert rel_err(Kinv @ g["lam"], g["Kinv_lam"]) < 10 * TOL_ON[precision]
+    assert np.abs((Kinv @ K).toarray() - np.eye(n6)).max() < (1e-11 if precision == "double" else 1e-4)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_fused_saddle_matches_golden_and_composition(orc, name, precision):
+    g = load_golden(name)
+    cb = _solver(g, precision)
+    out = cb.apply_saddle(g["vec"])
+    n3 = g["r"].size
+    if precision == "double":
+        assert rel_err(out, g["saddle"]) < TOL["double"]
+    else:
+        assert rel_err(out, g["saddle"]) < 5 * TOL["single"]
+    # the reference composes it in Python (Rigid.py:73-80); same numbers
+    lam, U = g["vec"][:n3], g["vec"][n3:]
+    slip = cb.apply_M(lam, cb.get_blob_positions()) - cb.K_dot(U).reshape(-1)
+    comp = np.concatenate([slip, cb.KT_dot(lam).reshape(-1)])
+    assert rel_err(out, comp) < (1e-14 if precision == "double" else 1e-6)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("name", ["case_overlap_wall", "case_overlap_free", "case_touch_wall", "case_touch_free"])
+def test_apply_PC_matches_golden(name, block, precision):
+    g = load_golden(name)
+    cb = _solver(g, precision, block=block)
+    out = cb.apply_PC(g["vec"])
+    assert out.shape == g["vec"].shape
+    assert rel_err(out, g["pc_block" if block else "pc_diag"]) < TOL_PC[precision]
+    # second call re-uses the built factorisation (PC_mat_Set, c_rigid_obj.cpp:591-596)
+    assert np.array_equal(cb.apply_PC(g["vec"]), out)
+
+
+@pytest.mark.parametrize("block", [False, True])
+def test_pc_inverts_its_saddle_matrix_on_device(orc, block):
+    """test_PC (c_rigid_obj.cpp:569-587) with the shared free-space factorisation:
+    many bodies, different orientations, one reference-shape inverse."""
+    from Rigid import RigidBody
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(27, 42, False)
+    cb = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, block_PC=block, precision="double")
+    ref = orc.remove_mean(s["cfg"])
+    pc = orc.PC(s["X"], s["Q"], ref, s["a"], 1.0, False, block)
+    vec = np.random.default_rng(1).standard_normal(3 * 27 * 42 + 6 * 27)
+    assert rel_err(cb.apply_PC(vec), pc.apply(vec)) < TOL_PC["double"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_evolve_matches_oracle_and_invalidates_pc(orc, precision):
+    g = load_golden("case_touch_wall")
+    cb = _solver(g, precision)
+    before = cb.apply_PC(g["vec"])
+    cb.evolve_rigid_bodies(g["U"])
+    X, Q = cb.get_config()
+    assert rel_err(X, g["X_evolved"]) < TOL_ON[precision] and rel_err(Q, g["Q_evolved"]) < TOL_ON[precision]
+    ref = orc.remove_mean(g["cfg"])
+    r = orc.blob_positions(g["X_evolved"], g["Q_evolved"], ref)
+    assert rel_err(cb.get_blob_positions(), r) < TOL_ON[precision]
+    assert rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r, g["X_evolved"], ref.shape[0])) < TOL_ON[precision]
+    after = cb.apply_PC(g["vec"])  # rebuilt for the new configuration (:877)
+    want = orc.PC(g["X_evolved"], g["Q_evolved"], ref, float(g["a"]), float(g["eta"]), True, False).apply(g["vec"])
+    assert rel_err(after, want) < TOL_PC[precision]
+    assert not np.array_equal(before, after)
+
+
+def test_set_config_keeps_a_built_pc_like_the_reference(orc):
+    """setConfig does not reset PC_mat_Set (only evolve_X_Q does, c_rigid_obj.cpp:877)."""
+    g = load_golden("case_touch_free")
+    cb = _solver(g, "double")
+    built = cb.apply_PC(g["vec"])
+    cb.set_config(g["X"] + 0.0, g["Q"])  # same configuration
+    assert np.array_equal(cb.apply_PC(g["vec"]), built)
+
+
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_gmres_solves_the_saddle_system(orc, name, block):
+    """Device GMRES (absent from the reference): the solution satisfies the
+    reference operator to the requested tolerance and matches a dense solve of the oracle."""
+    g = load_golden(name)
+    cb = _solver(g, "double", block=block)
+    rhs = g["vec"]
+    x, iters, relres = cb.gmres(rhs, tol=1e-10, restart=80, max_iter=400)
+    assert relres <= 1e-10 and 0 < iters < 400
+    assert rel_err(cb.apply_saddle(x), rhs) < 1e-9
+    # dense oracle solve of [M -K; K^T 0] x = rhs
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    M = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
+    K = orc.K_dense(g["r"], g["X"], g["cfg"].shape[0])
+    n3, n6 = M.shape[0], K.shape[1]
+    A = np.block([[M, -K], [K.T, np.zeros((n6, n6))]])
+    assert rel_err(x, np.linalg.solve(A, rhs)) < 1e-7
+
+
+def test_gmres_single_precision_converges(orc):
+    g = load_golden("case_touch_wall")
+    cb = _solver(g, "single", block=True)
+    x, iters, relres = cb.gmres(g["vec"], tol=1e-4, restart=60, max_iter=200)
+    assert relres <= 1e-4
+    assert rel_err(cb.apply_saddle(x), g["vec"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_overlap_free"])
+def test_lanczos_sqrt_matches_dense_sqrtm(orc, name):
+    """(B M B)^{1/2} W against scipy's sqrtm of the oracle's dense matrix (the reference's
+    M_half_W uses the Cholesky factor instead, c_rigid_obj.cpp:661-675: a different square
+    root with the same covariance L L^T = S S^T = B M B)."""
+    from scipy.linalg import sqrtm
+
+    g = load_golden(name)
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    cb = _solver(g, "double")
+    M = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
+    if wall:
+        B = orc.damp_diag(g["r"], a)
+        M = B[:, None] * M * B[None, :]
+    W = np.random.default_rng(9).standard_normal(M.shape[0])
+    out, iters = cb.brownian_sqrt(W, tol=1e-10, max_iter=150)
+    want = np.real(sqrtm(M)) @ W
+    assert rel_err(out, want) < 1e-7
+    assert 1 < iters <= 150
+
+
+def test_lanczos_covariance_statistics(orc):
+    """Test_Mhalf-style check (c_rigid_obj.cpp:895-915): the empirical covariance of
+    M^{1/2} W samples approaches M."""
+    g = load_golden("case_overlap_free")
+    cb = _solver(g, "double")
+    M = np.asarray(orc.dense_mobility(g["r"], float(g["a"]), float(g["eta"]), False))
+    rng = np.random.default_rng(11)
+    n, ns = M.shape[0], 600
+    C = np.zeros_like(M)
+    for _ in range(ns):
+        v, _it = cb.brownian_sqrt(rng.standard_normal(n), tol=1e-6, max_iter=60)
+        C += np.outer(v, v)
+    err = np.linalg.norm(C / ns - M) / np.linalg.norm(M)
+    # Wishart sampling error: E|C/ns - M|_F^2 = (tr(M)^2 + |M|_F^2) / ns
+    expected = np.sqrt((np.trace(M) ** 2 + np.linalg.norm(M) ** 2) / ns) / np.linalg.norm(M)
+    assert err < 1.5 * expected and err > 0.5 * expected
