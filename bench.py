@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the RPY mobility hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): 1000 spheres
+of shell_N_162 above a wall = 162 000 blobs; one STEP = one application of the saddle
+operator [M lam - K U ; K^T lam], i.e. one wall-corrected RPY mobility product B M B lam over
+N^2 = 2.6244e10 ordered blob pairs plus the K / K^T products.  Metric: ordered blob-pair
+interactions per second (whole job).  Strong scaling: bodies are partitioned over the ranks,
+lambda is all-gathered over NCCL each step.
+
+`value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
+`e2e`     : the same step through the host-buffer C ABI (rbl_apply_saddle at N=1; pinned
+            host -> device -> sharded step -> host at N>1), copies inside the timed region.
+`roofline`: the matvec kernel alone (events recorded around every launch inside the timed
+            region) against the FMA-pipe peak measured live by a microbenchmark.  The bound
+            is FP32 (FP64) CUDA-core issue, not HBM and not tensor cores.
+`cpu_baseline` / --impl reference: the reference ALGORITHM (dense 3N x 3N assembly + GEMV,
+            c_rigid_obj.cpp:413-459,641-659, single thread like the reference) restated in
+            oracle/rbl_oracle.c, on a bounded sample of the same suspension.  The only place
+            bench.py touches oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rpy_blob_pair_interactions_per_s"
+UNIT = "pairs/s"
+FLOPS_PER_PAIR = {True: 127.0, False: 35.0}  # SURVEY.md section 8d convention
+WORKLOADS = {
+    # name: (bodies, shell, wall)
+    "cfg2": (1000, 162, True),    # BASELINE.json configs[1]  (default, the bench line)
+    "cfg3": (4096, 42, True),     # configs[2] geometry
+    "cfg4": (1000, 2562, False),  # configs[3]
+    "cfg5": (10000, 642, True),   # configs[4]
+    "small": (64, 42, True),      # CI-sized
+}
+NVSMI_FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                "clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = None
+        self.p = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={NVSMI_FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_suspension(workload):
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    nb, shell, wall = WORKLOADS[workload]
+    s = sphere_suspension(nb, shell, wall)
+    s["wall"] = wall
+    s["n_bodies"], s["n_blb"] = nb, shell
+    return s
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from rigid_body_light_b200._lib import Context
+    from rigid_body_light_b200.sharding import CudaShard, ShardedSaddle, body_ranges, slice_system
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    s = build_suspension(args.workload)
+    nb, n_blb, wall = s["n_bodies"], s["n_blb"], s["wall"]
+    n_all = nb * n_blb
+    ranges = body_ranges(nb, world)
+    lo, hi = ranges[rank]
+    ref = s["cfg"] - s["cfg"].mean(axis=0)
+    vec = np.random.default_rng(2).standard_normal(3 * n_all + 6 * nb)
+    x_local_np = slice_system(vec, ranges, n_blb, rank)
+    pairs = float(n_all) * float(n_all)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    results = {}
+    for precision in (["single", "double"] if args.dtype == "both" else [args.dtype]):
+        tdt = torch.float32 if precision == "single" else torch.float64
+        ndt = np.float32 if precision == "single" else np.float64
+        ctx = Context(precision, device=local_rank)
+        ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
+        ctx.set_flags(0, int(wall))
+        ctx.set_config(s["X"][lo:hi], s["Q"][lo:hi])
+        shard = CudaShard(ctx, (hi - lo) * n_blb, tdt)
+        op = ShardedSaddle(shard, nb, n_blb, rank, world, dist if world > 1 else None)
+        x_local = torch.from_numpy(x_local_np.astype(ndt)).cuda()
+        out_local = torch.empty_like(x_local)
+        op.refresh_positions()
+        peak = max(ctx.fma_peak(20000) for _ in range(3))  # TFLOP/s, live, this GPU, this precision
+
+        def step():
+            ctx.call("rbl_flush_l2")  # inputs (5 MB) are smaller than the 126 MB L2: flush between steps
+            op.apply(x_local, out_local)
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        ctx.call("rbl_profile_matvec", 1)
+        ctx.matvec_profile(reset=True)
+        launches0 = ctx.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = ctx.launch_count() - launches0
+        kern_ms, kern_n = ctx.matvec_profile(reset=True)
+        ctx.call("rbl_profile_matvec", 0)
+        kern_ms = max_over_ranks(kern_ms)
+        ms_step = ms_total / args.steps
+
+        # end to end: host buffers, copies inside the timed region
+        nbytes = x_local.numel() * x_local.element_size()
+        if world == 1:
+            import ctypes
+
+            hx, ho = ctypes.c_void_p(), ctypes.c_void_p()
+            ctx.call("rbl_pinned_alloc", nbytes, ctypes.byref(hx))
+            ctx.call("rbl_pinned_alloc", nbytes, ctypes.byref(ho))
+            ctypes.memmove(hx, x_local_np.astype(ndt).ctypes.data, nbytes)
+            for _ in range(max(1, args.warmup)):
+                ctx.call("rbl_apply_saddle", hx, ho)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.call("rbl_apply_saddle", hx, ho)  # H2D + step + D2H, synchronous
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            host_out = np.frombuffer((ctypes.c_char * nbytes).from_address(ho.value), dtype=ndt).copy()
+            ctx.call("rbl_pinned_free", hx)
+            ctx.call("rbl_pinned_free", ho)
+        else:
+            hx = torch.from_numpy(x_local_np.astype(ndt)).pin_memory()
+            ho = torch.empty_like(hx).pin_memory()
+            for _ in range(max(1, args.warmup)):
+                x_local.copy_(hx, non_blocking=True); op.apply(x_local, out_local); ho.copy_(out_local, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                x_local.copy_(hx, non_blocking=True)
+                op.apply(x_local, out_local)
+                ho.copy_(out_local, non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+            host_out = ho.numpy().copy()
+        dev_out = out_local.cpu().numpy()
+        assert np.array_equal(dev_out, host_out), "host-buffer and device-resident paths disagree"
+        ctx.call("rbl_sync")
+
+        alg_tflops = (float((hi - lo) * n_blb) * n_all) * FLOPS_PER_PAIR[wall] / (kern_ms * 1e-3) / 1e12
+        results[precision] = {
+            "value": pairs / (ms_step * 1e-3), "ms_per_step": ms_step, "gpu_launches": int(launches),
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": int(nbytes) * world},
+            "roofline": {"bound": "fp32_cuda_core" if precision == "single" else "fp64_cuda_core",
+                         "kernel": "rbl::rpy_matvec_kernel", "achieved": alg_tflops, "peak": peak,
+                         "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": None,
+                         "kernel_ms": kern_ms, "kernel_launches_timed": int(kern_n),
+                         "algorithmic_flops_per_pair": FLOPS_PER_PAIR[wall],
+                         "peak_source": "FMA-chain microbenchmark run live on this GPU (rbl_fma_peak); nominal "
+                                        + ("74.4" if precision == "single" else "37.2") + " TFLOP/s at 148 SM x 1.965 GHz"},
+            "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()),
+        }
+        ctx.close()
+        del op, shard, x_local, out_local
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(args.workload, "single" if args.dtype != "double" else "double", budget_s=12.0)
+
+    if rank == 0:
+        head_p = "single" if args.dtype in ("both", "single") else "double"
+        head = results[head_p]
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if head_p == "single" else "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {nb} spheres of shell_N_{n_blb} "
+                                   f"{'above a wall' if wall else 'in free space'} = {n_all} blobs; step = apply_saddle "
+                                   f"(wall-corrected RPY matvec + K + K^T)",
+                       "pairs_per_step": pairs, "parallelism": f"body-range shards x{world}, NCCL all-gather of lambda",
+                       "l2": "256 MiB memset between steps inside the timed region (inputs < L2)",
+                       "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+            "clocks": head["clocks"], "cpu_baseline": cpu,
+        }
+        if "double" in results and head_p == "single":
+            d = results["double"]
+            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port), bounded sample
+# --------------------------------------------------------------------------------------
+def _sample_inputs(workload, n_bodies_sample, ndt):
+    from oracle import oracle as orc
+
+    s = build_suspension(workload)
+    nb = min(n_bodies_sample, s["n_bodies"])
+    ref = orc.remove_mean(s["cfg"])
+    r = orc.blob_positions(s["X"][:nb], s["Q"][:nb], ref).astype(ndt)
+    F = np.random.default_rng(2).standard_normal(r.size).astype(ndt)
+    return s, nb, r, F
+
+
+def cpu_reference_sample(workload, precision, budget_s, steps=1, warmup=0):
+    """Times apply_M exactly as the reference runs it (dense assembly + GEMV, 1 thread) on the
+    first bodies of the workload, sized so one step takes about budget_s/(steps+warmup)."""
+    from oracle import oracle as orc
+
+    ndt = np.float32 if precision == "single" else np.float64
+    nb_total, n_blb, wall = WORKLOADS[workload]
+    # calibrate on a small piece
+    s, nb, r, F = _sample_inputs(workload, max(1, 600 // n_blb), ndt)
+    t0 = time.perf_counter()
+    orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+    rate = (r.shape[0] ** 2) / max(time.perf_counter() - t0, 1e-6)
+    per_step = budget_s / max(1, steps + warmup)
+    n_target = int(np.sqrt(rate * per_step))
+    mem_cap = int(np.sqrt(6e9 / (9 * np.dtype(ndt).itemsize)))  # dense matrix <= 6 GB
+    nb_s = max(1, min(nb_total, min(n_target, mem_cap) // n_blb))
+    s, nb, r, F = _sample_inputs(workload, nb_s, ndt)
+    n = r.shape[0]
+    for _ in range(warmup):
+        orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+    dt = (time.perf_counter() - t0) / steps
+    # best-effort CPU: matrix-free OpenMP oracle on all host cores, sampled target rows of the
+    # FULL workload (float64 with long-double row sums; a courtesy number, not the reference)
+    sf, nbf, rf, Ff = _sample_inputs(workload, nb_total, np.float64)
+    rows = np.random.default_rng(5).choice(rf.shape[0], min(rf.shape[0], 512), replace=False)
+    t0 = time.perf_counter()
+    orc.apply_M(Ff, rf, sf["a"], 1.0, wall, rows=rows)
+    dt_mf = time.perf_counter() - t0
+    return {
+        "value": n * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"first {nb} bodies of {workload} ({n} blobs, {precision}): dense {3*n}x{3*n} assembly + GEMV "
+                  f"like c_rigid_obj.cpp:413-459,641-659, single thread (the reference has no threading); "
+                  f"the full workload would need {9 * (nb_total * n_blb) ** 2 * np.dtype(ndt).itemsize / 1e9:.0f} GB",
+        "ms_per_step": dt * 1e3,
+        "best_effort_all_cores": {"value": rows.size * rf.shape[0] / dt_mf, "unit": UNIT, "cores": orc.num_threads(),
+                                  "kind": "port", "sample": f"matrix-free OpenMP oracle, {rows.size} sampled target rows "
+                                                            f"x {rf.shape[0]} sources of the full workload, float64"},
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    precision = "single" if args.dtype in ("both", "single") else "double"
+    nb, n_blb, wall = WORKLOADS[args.workload]
+    cpu = cpu_reference_sample(args.workload, precision, budget_s=100.0, steps=args.steps, warmup=args.warmup)
+    n_all = nb * n_blb
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32" if precision == "single" else "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {nb} spheres of shell_N_{n_blb} "
+                               f"{'above a wall' if wall else 'in free space'} = {n_all} blobs; step = apply_M on a bounded "
+                               f"sample (the reference's dense algorithm cannot hold the full workload)",
+                   "sample": cpu["sample"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="both", choices=["both", "single", "double"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

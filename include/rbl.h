@@ -119,6 +119,12 @@ int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout);
 int rbl_dev_KT_dot(rbl_ctx* ctx, const void* dlambda, void* dout);
 int rbl_dev_apply_PC(rbl_ctx* ctx, const void* din, void* dout);
 int rbl_dev_apply_saddle(rbl_ctx* ctx, const void* dx, void* dout);
+/* One rank's share of apply_saddle when bodies are partitioned across GPUs: the context
+ * holds this rank's bodies (blobs [tgt_first, tgt_first + N_local) of the global n_blobs);
+ * dlambda_all / dr_all are the all-gathered forces and positions (3*n_blobs).
+ * dout_local = [ (M lambda)_local - K_local U_local ; K_local^T lambda_local ]. */
+int rbl_dev_apply_saddle_shard(rbl_ctx* ctx, const void* dlambda_all, const void* dr_all,
+                               int n_blobs, int tgt_first, const void* dU_local, void* dout_local);
 int rbl_sync(rbl_ctx* ctx);
 /* the context's cudaStream_t (as void*); set_stream lets a host share its own stream */
 void* rbl_stream(rbl_ctx* ctx);

@@ -55,6 +55,7 @@ SYMBOLS = {
     "rbl_dev_KT_dot": (_i, [_vp, _vp, _vp]),
     "rbl_dev_apply_PC": (_i, [_vp, _vp, _vp]),
     "rbl_dev_apply_saddle": (_i, [_vp, _vp, _vp]),
+    "rbl_dev_apply_saddle_shard": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rbl_sync": (_i, [_vp]),
     "rbl_stream": (_vp, [_vp]),
     "rbl_set_stream": (_i, [_vp, _vp]),

@@ -76,6 +76,7 @@ struct rbl_ctx {
   virtual int dev_apply_M(const void* F, const void* r, int n, int t0, int nt, void* out) = 0;
   virtual int apply_PC(const void* in, void* out, bool dev) = 0;
   virtual int apply_saddle(const void* x, void* out, bool dev) = 0;
+  virtual int saddle_shard(const void* lam_all, const void* r_all, int n_all, int t0, const void* U, void* out) = 0;
   virtual int evolve(const void* U) = 0;
   virtual int export_K(int64_t* indptr, int32_t* indices, void* data) = 0;
   virtual int export_Kinv(int64_t* indptr, int32_t* indices, void* data) = 0;
@@ -185,7 +186,7 @@ struct Ctx final : rbl_ctx {
       if (flags[FLAG_SINGULAR])
         return fail(RBL_ERR_SINGULAR, "K^T*K is singular (is your rigid body a dimer?)");
       pc_set = false;
-      return fail(RBL_ERR_SINGULAR, "preconditioner block is not positive definite");
+      return fail(RBL_ERR_SINGULAR, "preconditioner block is singular");
     }
     return RBL_OK;
   }
@@ -408,6 +409,17 @@ struct Ctx final : rbl_ctx {
     RET(dev_apply_M(dx, d_r.p, n, 0, n, dout));
     LAUNCH(1, rbl::k_dot<real>(dx + 3 * (size_t)n, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)-1, dout, dout, stream));
     LAUNCH(1, rbl::kt_dot<real>(dx, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dout + 3 * (size_t)n, stream));
+    return RBL_OK;
+  }
+  int saddle_shard(const void* lam_all, const void* r_all, int n_all, int t0, const void* U, void* out) override {
+    RET(need_K());
+    const int nl = (int)N();
+    if (t0 < 0 || t0 + nl > n_all) return fail(RBL_ERR_INVALID, "saddle shard: local blob range outside the global range");
+    real* dout = static_cast<real*>(out);
+    const real* lam_local = static_cast<const real*>(lam_all) + 3 * (size_t)t0;
+    RET(dev_apply_M(lam_all, r_all, n_all, t0, nl, dout));
+    LAUNCH(1, rbl::k_dot<real>(static_cast<const real*>(U), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)-1, dout, dout, stream));
+    LAUNCH(1, rbl::kt_dot<real>(lam_local, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dout + 3 * (size_t)nl, stream));
     return RBL_OK;
   }
   int apply_saddle(const void* x, void* out, bool dev) override {
@@ -968,6 +980,10 @@ int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout) { CTX_OR_FAIL(ctx); 
 int rbl_dev_KT_dot(rbl_ctx* ctx, const void* dl, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->KT_dot(dl, dout, true); }
 int rbl_dev_apply_PC(rbl_ctx* ctx, const void* din, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_PC(din, dout, true); }
 int rbl_dev_apply_saddle(rbl_ctx* ctx, const void* dx, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->apply_saddle(dx, dout, true); }
+int rbl_dev_apply_saddle_shard(rbl_ctx* ctx, const void* dl, const void* dr, int n, int t0, const void* dU, void* dout) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->saddle_shard(dl, dr, n, t0, dU, dout);
+}
 int rbl_sync(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->sync(); }
 void* rbl_stream(rbl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int rbl_set_stream(rbl_ctx* ctx, void* s) {

@@ -45,38 +45,42 @@ __device__ __forceinline__ void block_sum(real (&v)[NV], real* red /* [32*NV] sm
   __syncthreads();
 }
 
-// 6x6 Cholesky (lower, row-major) in place; returns false if not SPD (Eigen LLT has no
-// pivoting either, c_rigid_obj.cpp:562)
+// 6x6 inverse in place by Gauss-Jordan with partial pivoting.  The reference factors
+// N^-1 = K^T Mt^-1 K with Eigen's LLT and solves (c_rigid_obj.cpp:554-567,605-608); for the
+// SPD matrices of physical configurations the explicit inverse gives the same U to rounding,
+// and it stays finite where LLT silently breaks down (blobs inside the wall-overlap layer make
+// Mt indefinite).  Returns false only for a (numerically) singular matrix.
 template <typename real>
-__device__ bool chol6(real* A) {
+__device__ bool inv6(real* A) {
+  int perm[6];
   bool ok = true;
-  for (int j = 0; j < 6; ++j) {
-    real d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
-    if (!(d > (real)0)) ok = false;
-    d = sqrt(d);
-    A[j * 6 + j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      real s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
-      A[i * 6 + j] = s / d;
+  for (int i = 0; i < 6; ++i) perm[i] = i;
+  for (int k = 0; k < 6; ++k) {
+    int p = k;
+    real best = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[i * 6 + k]) > best) { best = fabs(A[i * 6 + k]); p = i; }
+    if (!(best > (real)0) || !isfinite(best)) ok = false;
+    if (p != k) {
+      for (int j = 0; j < 6; ++j) { real t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
+      int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
     }
-    for (int i = 0; i < j; ++i) A[i * 6 + j] = 0;
+    const real piv = (real)1 / A[k * 6 + k];
+    A[k * 6 + k] = (real)1;
+    for (int j = 0; j < 6; ++j) A[k * 6 + j] *= piv;
+    for (int i = 0; i < 6; ++i) {
+      if (i == k) continue;
+      const real f = A[i * 6 + k];
+      A[i * 6 + k] = (real)0;
+      for (int j = 0; j < 6; ++j) A[i * 6 + j] -= f * A[k * 6 + j];
+    }
   }
+  // undo the row swaps: columns of the inverse are permuted
+  real T[36];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) T[i * 6 + perm[j]] = A[i * 6 + j];
+  for (int i = 0; i < 36; ++i) A[i] = T[i];
   return ok;
-}
-template <typename real>
-__device__ void chol6_solve(const real* __restrict__ L, real* b) {
-  for (int i = 0; i < 6; ++i) {
-    real s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
-    b[i] = s / L[i * 6 + i];
-  }
-  for (int i = 5; i >= 0; --i) {
-    real s = b[i];
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
-    b[i] = s / L[i * 6 + i];
-  }
 }
 
 }  // namespace
@@ -417,7 +421,7 @@ __global__ void pc_block_invert_kernel(real* __restrict__ M, int sz, int* __rest
     }
     __syncthreads();
     const real piv = row[k];
-    if (threadIdx.x == 0 && !(piv > (real)0)) *not_spd = 1;
+    if (threadIdx.x == 0 && (piv == (real)0 || !isfinite(piv))) *not_spd = 1;  // singular
     const real p = (real)1 / piv;
     for (int i = wid; i < sz; i += nw) {
       real* Ai = A + (size_t)i * sz;
@@ -536,7 +540,7 @@ __global__ void pc_ninv_chol_kernel(const real* __restrict__ Y, const real* __re
         N[i * 6 + j] = m;
         N[j * 6 + i] = m;
       }
-    if (!chol6(N)) *not_spd = 1;
+    if (!inv6(N)) *not_spd = 1;  // N_b = (K^T Mt^-1 K)^-1, the body mobility of the PC
     for (int i = 0; i < 36; ++i) L[36 * (size_t)b + i] = N[i];
   }
 }
@@ -572,8 +576,12 @@ __global__ void pc_finish_kernel(const real* __restrict__ y, const real* __restr
   if (threadIdx.x == 0) {
     real rhs[6];
     for (int c = 0; c < 6; ++c) rhs[c] = -F[6 * (size_t)b + c] - red[c];  // :601
-    chol6_solve(L + 36 * (size_t)b, rhs);                                  // :605-608
-    for (int c = 0; c < 6; ++c) Ub[c] = rhs[c];
+    const real* Nb = L + 36 * (size_t)b;                                   // :605-608
+    for (int c = 0; c < 6; ++c) {
+      real acc = 0;
+      for (int d = 0; d < 6; ++d) acc += Nb[c * 6 + d] * rhs[d];
+      Ub[c] = acc;
+    }
   }
   __syncthreads();
   const size_t n3 = (size_t)n_bod * sz;

@@ -63,7 +63,8 @@ cudaError_t pc_fill_kcols(const real* r, const real* X, int n_bod, int n_blb, re
 template <typename real>
 cudaError_t pc_block_assemble(const real* r, int count, int n_blb, real a, real eta,
                               bool wall, real* M, int* below_wall, cudaStream_t s);
-// in-place batched inverse of SPD matrices, one CTA per matrix (Gauss-Jordan, no pivot)
+// in-place batched inverse of symmetric (SPD for physical configurations) matrices, one
+// CTA per matrix (Gauss-Jordan without pivoting; flags only exactly singular pivots)
 template <typename real>
 cudaError_t pc_block_invert(real* M, int count, int sz, int* not_spd, cudaStream_t s);
 // out[b][c][:] = Minv_b in[b][c][:], c < ncols (1 or 6).  stride = sz*sz for per-body
@@ -73,11 +74,11 @@ template <typename real>
 cudaError_t pc_block_mul(const real* Minv, size_t stride, const real* Q, const real* in,
                          int n_bod, int n_blb, int ncols, real* out, cudaStream_t s);
 
-// N^-1_b = K_b^T Y_b and its Cholesky factor L (row-major lower 6x6, 36 reals per body)
+// N^-1_b = K_b^T Y_b, inverted: L holds N_b (row-major 6x6, 36 reals per body)
 template <typename real>
 cudaError_t pc_ninv_chol(const real* Y, const real* r, const real* X, int n_bod, int n_blb,
                          real* L, int* not_spd, cudaStream_t s);
-// out = [y + Y U ; U],  U_b = (L L^T)^-1 (-F_b - K_b^T y_b)
+// out = [y + Y U ; U],  U_b = N_b (-F_b - K_b^T y_b)
 template <typename real>
 cudaError_t pc_finish(const real* y, const real* F, const real* Y, const real* L,
                       const real* r, const real* X, int n_bod, int n_blb, real* out,
