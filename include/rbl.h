@@ -109,6 +109,20 @@ int rbl_gmres(rbl_ctx* ctx, const void* rhs, void* x, double tol, int restart, i
 int rbl_lanczos_sqrt(rbl_ctx* ctx, const void* W, void* out, double tol, int max_iter,
                      int* iters);
 
+/* One rigid-body Brownian-dynamics step: the trapezoidal-slip midpoint scheme
+ * that RHS_and_Midpoint (:917-976) sets up but never finishes, composed on the device:
+ *   M^{1/2}W_1, M^{1/2}W_2 by Lanczos;  RFD drift (M(q+) - M(q-)) W_r / delta with
+ *   q+- = q +- (delta/2) K^-1 W_r (:769-796);  BI = sqrt(kBT/dt) (M^{1/2}W_1 - M^{1/2}W_2) (:945-948);
+ *   midpoint q' = q + (dt/2) K^-1 (2 sqrt(kBT/dt) M^{1/2}W_1) (:954-958), K and PC rebuilt THERE;
+ *   GMRES solve of  apply_saddle([lambda;U]) = [slip - kBT*RFD - BI ; F_ext]  at q';
+ *   q <- q + dt*U from the ORIGINAL configuration (evolve_X_Q, :865-878).
+ * F_ext: 6*n_bod.  slip: 3*N or NULL (zero).  W1, W2, Wr: 3*N standard-normal vectors supplied by
+ * the caller (the reference seeds its generator from the wall clock, :731); all three NULL or
+ * kBT == 0 gives the deterministic step.  U_out: 6*n_bod rigid velocities of the step. */
+int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W1, const void* W2,
+                const void* Wr, double kBT, double gmres_tol, int restart, int max_iter,
+                double lanczos_tol, int lanczos_max_iter, void* U_out, int* gmres_iters, double* relres);
+
 /* ---- device-resident API (device pointers, asynchronous on the context stream) ---- */
 /* Targets [tgt_first, tgt_first+n_tgt) of the n_blobs sources: out has 3*n_tgt reals.
  * This is the entry a multi-GPU host shards by body range. */

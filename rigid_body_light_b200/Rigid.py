@@ -136,6 +136,30 @@ class RigidBody:
         self._need(W, 3 * self.total_blobs, "W", "3*N_blobs")
         return self.cb.lanczos_sqrt(W.reshape(-1), tol, max_iter)
 
+    def bd_step(self, F_ext, slip=None, kBT=0.0, noise=None, rng=None, tol=1e-8, restart=60, max_iter=300,
+                lanczos_tol=1e-6, lanczos_max_iter=100):
+        """Advance the bodies by one (Brownian) step with the trapezoidal-slip midpoint scheme
+        the reference sets up in RHS_and_Midpoint (c_rigid_obj.cpp:917-976), entirely on the
+        device.  ``F_ext``: external force/torque per body (6*N_bodies); ``slip``: prescribed
+        blob slip (3*N_blobs) or None; ``noise`` = (W1, W2, Wr) standard-normal 3*N_blobs
+        vectors, drawn from ``rng`` (numpy Generator) when kBT > 0 and noise is None.
+        Returns (U, gmres_iterations, relative_residual)."""
+        F_ext = np.asarray(F_ext)
+        self._need(F_ext, 6 * self.N_bodies, "F_ext", "6*N_bodies")
+        n3 = 3 * self.total_blobs
+        if slip is not None:
+            slip = np.asarray(slip)
+            self._need(slip, n3, "slip", "3*N_blobs")
+            slip = slip.reshape(-1)
+        W1 = W2 = Wr = None
+        if kBT > 0:
+            if noise is None:
+                rng = np.random.default_rng() if rng is None else rng
+                noise = tuple(rng.standard_normal(n3) for _ in range(3))
+            W1, W2, Wr = (np.asarray(w).reshape(-1) for w in noise)
+        return self.cb.bd_step(F_ext.reshape(-1), slip, W1, W2, Wr, float(kBT), tol, restart, max_iter,
+                               lanczos_tol, lanczos_max_iter)
+
     # -- size checks (RuntimeError like Rigid.py:117-135) -------------------------------
     def _need(self, vec, n, name, what):
         if vec.size != n:

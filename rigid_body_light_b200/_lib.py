@@ -49,6 +49,7 @@ SYMBOLS = {
     "rbl_export_Kinv_csc": (_i, [_vp, _vp, _vp, _vp]),
     "rbl_gmres": (_i, [_vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     "rbl_lanczos_sqrt": (_i, [_vp, _vp, _vp, _d, _i, _pi]),
+    "rbl_bd_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _d, _i, _vp, _pi, _pd]),
     "rbl_dev_apply_M": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rbl_dev_blob_positions": (_i, [_vp, _vp]),
     "rbl_dev_K_dot": (_i, [_vp, _vp, _vp]),

@@ -165,6 +165,29 @@ class CManyBodies {
     check(rbl_lanczos_sqrt(ctx_, W.data(), out.mutable_data(), tol, max_iter, &iters));
     return py::make_tuple(out, iters);
   }
+  // one Brownian-dynamics step (noise supplied by the caller; None -> deterministic)
+  py::tuple bd_step(Arr F_ext, py::object slip, py::object W1, py::object W2, py::object Wr, double kBT, double tol,
+                    int restart, int max_iter, double ltol, int lmax) {
+    want(F_ext, n6(), "bd_step F_ext");
+    auto opt = [&](py::object o, const char* what, Arr& keep) -> const real* {
+      if (o.is_none()) return nullptr;
+      keep = Arr::ensure(o);
+      if (!keep) throw std::runtime_error(std::string(what) + ": not convertible to a float array");
+      want(keep, n3(), what);
+      return keep.data();
+    };
+    Arr k0, k1, k2, k3;
+    const real* ps = opt(slip, "bd_step slip", k0);
+    const real* p1 = opt(W1, "bd_step W1", k1);
+    const real* p2 = opt(W2, "bd_step W2", k2);
+    const real* pr = opt(Wr, "bd_step Wr", k3);
+    py::array_t<real> U(n6());
+    int iters = 0;
+    double relres = 0;
+    check(rbl_bd_step(ctx_, F_ext.data(), ps, p1, p2, pr, kBT, tol, restart, max_iter, ltol, lmax, U.mutable_data(),
+                      &iters, &relres));
+    return py::make_tuple(U, iters, relres);
+  }
   std::uintptr_t handle() const { return reinterpret_cast<std::uintptr_t>(ctx_); }
 };
 
@@ -198,5 +221,9 @@ PYBIND11_MODULE(RBL_MODULE_NAME, m) {
            py::arg("max_iter") = 300)
       .def("lanczos_sqrt", &CManyBodies::lanczos_sqrt, py::arg("W"), py::arg("tol") = 1e-6,
            py::arg("max_iter") = 100)
+      .def("bd_step", &CManyBodies::bd_step, py::arg("F_ext"), py::arg("slip") = py::none(), py::arg("W1") = py::none(),
+           py::arg("W2") = py::none(), py::arg("Wr") = py::none(), py::arg("kBT") = 0.0, py::arg("tol") = 1e-8,
+           py::arg("restart") = 60, py::arg("max_iter") = 300, py::arg("lanczos_tol") = 1e-6,
+           py::arg("lanczos_max_iter") = 100)
       .def("handle", &CManyBodies::handle, "address of the rbl_ctx (for ctypes users of include/rbl.h)");
 }

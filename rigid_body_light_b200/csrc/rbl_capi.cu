@@ -82,6 +82,9 @@ struct rbl_ctx {
   virtual int export_Kinv(int64_t* indptr, int32_t* indices, void* data) = 0;
   virtual int gmres(const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) = 0;
   virtual int lanczos(const void* W, void* out, double tol, int max_iter, int* iters) = 0;
+  virtual int bd_step(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, double kBT,
+                      double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
+                      double* relres) = 0;
   virtual int sync() = 0;
   virtual int fma_peak(int iters, double* tflops) = 0;
   virtual int num_variants() const = 0;
@@ -137,6 +140,8 @@ struct Ctx final : rbl_ctx {
   bool pc_shared = false;
   // krylov
   DevBuf d_V, d_w, d_z, d_tmp, d_partial, d_coef, d_dots;
+  // BD step
+  DevBuf d_rhs, d_sol, d_mh1, d_mh2, d_rfd, d_noise, d_uom, d_Xs, d_Qs, d_Xp, d_Qp, d_rp, d_t1, d_t2;
 
   enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, N_FLAGS = 4 };
 
@@ -606,6 +611,18 @@ struct Ctx final : rbl_ctx {
 
   int gmres(const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) override {
     if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    const size_t n = sys_size();
+    CK(d_in1.ensure(n * sizeof(real)));   // rhs
+    CK(d_out0.ensure(n * sizeof(real)));  // x
+    RET(h2d(d_in1.p, rhs, n * sizeof(real)));
+    RET(dev_gmres(d_in1.as<real>(), d_out0.as<real>(), tol, restart, max_iter, iters, relres));
+    RET(d2h(x, d_out0.p, n * sizeof(real)));
+    return sync();
+  }
+
+  // device-resident core: b and xs are device vectors of sys_size() reals (distinct from the
+  // solver's own work buffers)
+  int dev_gmres(const real* b, real* xs, double tol, int restart, int max_iter, int* iters, double* relres) {
     if (restart < 1 || max_iter < 1) return fail(RBL_ERR_INVALID, "gmres: restart and max_iter must be >= 1");
     RET(need_K());
     const size_t n = sys_size(), n_head = 3 * (size_t)N();
@@ -614,8 +631,6 @@ struct Ctx final : rbl_ctx {
     CK(d_w.ensure(n * sizeof(real)));
     CK(d_z.ensure(n * sizeof(real)));
     CK(d_tmp.ensure(n * sizeof(real)));
-    CK(d_in1.ensure(n * sizeof(real)));   // rhs
-    CK(d_out0.ensure(n * sizeof(real)));  // x
     CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
     CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
     CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
@@ -623,19 +638,15 @@ struct Ctx final : rbl_ctx {
     real* w = d_w.as<real>();
     real* z = d_z.as<real>();
     real* tmp = d_tmp.as<real>();
-    real* b = d_in1.as<real>();
-    real* xs = d_out0.as<real>();
-    RET(h2d(b, rhs, n * sizeof(real)));
     CK(cudaMemsetAsync(xs, 0, n * sizeof(real), stream));
     double bnorm = 0;
     RET(dev_norm(b, n, &bnorm));
     int total = 0;
     double res = bnorm;
     if (bnorm == 0) {
-      RET(d2h(x, xs, n * sizeof(real)));
       *iters = 0;
       *relres = 0;
-      return sync();
+      return RBL_OK;
     }
     std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), hcol;
     std::vector<real> coef(m + 1);
@@ -713,10 +724,9 @@ struct Ctx final : rbl_ctx {
       CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
       if (res / bnorm <= tol) break;
     }
-    RET(d2h(x, xs, n * sizeof(real)));
     *iters = total;
     *relres = res / bnorm;
-    return sync();
+    return RBL_OK;
   }
 
   // symmetric tridiagonal eigen-decomposition by cyclic Jacobi on the dense k x k matrix
@@ -756,6 +766,17 @@ struct Ctx final : rbl_ctx {
 
   int lanczos(const void* W, void* out, double tol, int max_iter, int* iters) override {
     if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    const size_t n = 3 * (size_t)N();
+    CK(d_in1.ensure(n * sizeof(real)));
+    CK(d_out0.ensure(n * sizeof(real)));
+    RET(h2d(d_in1.p, W, n * sizeof(real)));
+    RET(dev_lanczos(d_in1.as<real>(), d_out0.as<real>(), tol, max_iter, iters));
+    RET(d2h(out, d_out0.p, n * sizeof(real)));
+    return sync();
+  }
+
+  // device-resident core: dout = (B M B)^{1/2} dW at the CURRENT configuration (d_r)
+  int dev_lanczos(const real* dW, real* dout, double tol, int max_iter, int* iters) {
     if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
     RET(need_K());
     const size_t n = 3 * (size_t)N();
@@ -763,20 +784,18 @@ struct Ctx final : rbl_ctx {
     const int m = max_iter;
     CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
     CK(d_w.ensure(n * sizeof(real)));
-    CK(d_out0.ensure(n * sizeof(real)));
     CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
     CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
     CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
     real* V = d_V.as<real>();
     real* w = d_w.as<real>();
-    RET(h2d(w, W, n * sizeof(real)));
+    LAUNCH(1, rbl::scale_copy<real>(dW, (real)1, w, n, false, stream));
     double wnorm = 0;
     RET(dev_norm(w, n, &wnorm));
     if (wnorm == 0) {
-      CK(cudaMemsetAsync(d_out0.p, 0, n * sizeof(real), stream));
-      RET(d2h(out, d_out0.p, n * sizeof(real)));
+      CK(cudaMemsetAsync(dout, 0, n * sizeof(real), stream));
       *iters = 0;
-      return sync();
+      return RBL_OK;
     }
     LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / wnorm), V, n, false, stream));
     std::vector<double> alpha, beta, y_prev, y, s;
@@ -823,10 +842,92 @@ struct Ctx final : rbl_ctx {
     std::vector<real> coef(k);
     for (int i = 0; i < k; ++i) coef[i] = (real)y[i];
     RET(h2d(d_coef.p, coef.data(), k * sizeof(real)));
-    CK(cudaMemsetAsync(d_out0.p, 0, n * sizeof(real), stream));
-    LAUNCH(1, rbl::multi_axpy<real>(V, n, k, d_coef.as<real>(), (real)1, d_out0.as<real>(), n, stream));
-    RET(d2h(out, d_out0.p, n * sizeof(real)));
+    CK(cudaMemsetAsync(dout, 0, n * sizeof(real), stream));
+    LAUNCH(1, rbl::multi_axpy<real>(V, n, k, d_coef.as<real>(), (real)1, dout, n, stream));
+    CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
     *iters = k;
+    return RBL_OK;
+  }
+
+
+  // ---- Brownian-dynamics step (see rbl_bd_step in include/rbl.h) -------------------------------
+  int kinv_dev(const real* v3n, real* out6) {  // out = (K^T K)^-1 K^T v   (:390,406)
+    LAUNCH(1, rbl::kt_dot<real>(v3n, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, out6, stream));
+    LAUNCH(1, rbl::ktk_inv_apply<real>(d_S.as<real>(), n_bod, n_blb, out6, stream));
+    return RBL_OK;
+  }
+  int bd_step(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, double kBT_,
+              double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
+              double* relres) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!F_ext || !U_out) return fail(RBL_ERR_INVALID, "bd_step: F_ext and U_out are required");
+    const bool brownian = kBT_ > 0 && W1 && W2 && Wr;
+    if (kBT_ > 0 && !brownian) return fail(RBL_ERR_INVALID, "bd_step: kBT > 0 needs the three noise vectors W1, W2, Wr");
+    if (brownian && !(dt > 0)) return fail(RBL_ERR_INVALID, "bd_step: dt must be positive");
+    RET(need_K());
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod, n = n3 + n6;
+    const int nb = (int)N();
+    CK(d_rhs.ensure(n * sizeof(real)));
+    CK(d_sol.ensure(n * sizeof(real)));
+    real* rhs = d_rhs.as<real>();
+    real* sol = d_sol.as<real>();
+    if (slip) RET(h2d(rhs, slip, n3 * sizeof(real)));
+    else CK(cudaMemsetAsync(rhs, 0, n3 * sizeof(real), stream));
+    RET(h2d(rhs + n3, F_ext, n6 * sizeof(real)));
+    if (brownian) {
+      for (DevBuf* b : {&d_mh1, &d_mh2, &d_rfd, &d_noise, &d_rp, &d_t1, &d_t2}) CK(b->ensure(n3 * sizeof(real)));
+      CK(d_uom.ensure(n6 * sizeof(real)));
+      for (DevBuf* b : {&d_Xs, &d_Xp}) CK(b->ensure(3 * (size_t)n_bod * sizeof(real)));
+      for (DevBuf* b : {&d_Qs, &d_Qp}) CK(b->ensure(4 * (size_t)n_bod * sizeof(real)));
+      real* noise = d_noise.as<real>();
+      int it = 0;
+      // Brownian increments at q^n  (M_half_W, :661-675, via Lanczos)
+      RET(h2d(noise, W1, n3 * sizeof(real)));
+      RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it));
+      RET(h2d(noise, W2, n3 * sizeof(real)));
+      RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it));
+      // random finite difference  (M_RFD, :769-796)
+      const double delta = sizeof(real) == 8 ? 1.0e-4 : 4.0e-3;
+      RET(h2d(noise, Wr, n3 * sizeof(real)));
+      RET(kinv_dev(noise, d_uom.as<real>()));
+      real* Mpm[2] = {d_t1.as<real>(), d_t2.as<real>()};
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        LAUNCH(1, rbl::integrate<real>(d_uom.as<real>(), (real)((sgn ? -0.5 : 0.5) * delta), n_bod, d_X.as<real>(),
+                                       d_Q.as<real>(), d_Xp.as<real>(), d_Qp.as<real>(), stream));
+        LAUNCH(1, rbl::place_blobs<real>(d_Xp.as<real>(), d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb,
+                                         d_rp.as<real>(), stream));
+        RET(dev_apply_M(noise, d_rp.p, nb, 0, nb, Mpm[sgn]));
+      }
+      LAUNCH(1, rbl::scale_copy<real>(d_t1.as<real>(), (real)(1.0 / delta), d_rfd.as<real>(), n3, false, stream));
+      LAUNCH(1, rbl::scale_copy<real>(d_t2.as<real>(), (real)(-1.0 / delta), d_rfd.as<real>(), n3, true, stream));
+      // RHS slip -= kBT * RFD + c2 (M^{1/2}W1 - M^{1/2}W2)   (:945-948,963)
+      const double c1 = 2.0 * std::sqrt(kBT_ / dt), c2 = std::sqrt(kBT_ / dt);
+      LAUNCH(1, rbl::scale_copy<real>(d_rfd.as<real>(), (real)(-kBT_), rhs, n3, true, stream));
+      LAUNCH(1, rbl::scale_copy<real>(d_mh1.as<real>(), (real)(-c2), rhs, n3, true, stream));
+      LAUNCH(1, rbl::scale_copy<real>(d_mh2.as<real>(), (real)(c2), rhs, n3, true, stream));
+      // midpoint configuration q' = q + (dt/2) K^-1 (c1 M^{1/2}W1)   (:954-958), installed
+      RET(kinv_dev(d_mh1.as<real>(), d_uom.as<real>()));
+      CK(cudaMemcpyAsync(d_Xs.p, d_X.p, 3 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemcpyAsync(d_Qs.p, d_Q.p, 4 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      LAUNCH(1, rbl::integrate<real>(d_uom.as<real>(), (real)(0.5 * dt * c1), n_bod, d_X.as<real>(), d_Q.as<real>(),
+                                     d_X.as<real>(), d_Q.as<real>(), stream));
+      RET(set_K_mats());
+      pc_set = false;
+    }
+    int st = dev_gmres(rhs, sol, tol, restart, max_iter, iters, relres);
+    if (brownian) {  // back to q^n whatever the solver said
+      CK(cudaMemcpyAsync(d_X.p, d_Xs.p, 3 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemcpyAsync(d_Q.p, d_Qs.p, 4 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      r_valid = false;
+      pc_set = false;
+    }
+    if (st != RBL_OK) return st;
+    // q^{n+1} = q^n + dt U   (evolve_X_Q, :865-878)
+    LAUNCH(1, rbl::integrate<real>(sol + n3, (real)dt, n_bod, d_X.as<real>(), d_Q.as<real>(), d_X.as<real>(),
+                                   d_Q.as<real>(), stream));
+    RET(set_K_mats());
+    pc_set = false;
+    RET(d2h(U_out, sol + n3, n6 * sizeof(real)));
     return sync();
   }
 
@@ -971,6 +1072,17 @@ int rbl_lanczos_sqrt(rbl_ctx* ctx, const void* W, void* out, double tol, int max
   int it = 0;
   int s = ctx->lanczos(W, out, tol, max_iter, &it);
   if (iters) *iters = it;
+  return s;
+}
+
+int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr,
+                double kBT, double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
+                double* relres) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int it = 0; double rr = 0;
+  int s = ctx->bd_step(F_ext, slip, W1, W2, Wr, kBT, tol, restart, max_iter, ltol, lmax, U_out, &it, &rr);
+  if (iters) *iters = it;
+  if (relres) *relres = rr;
   return s;
 }
 

@@ -242,7 +242,7 @@ __device__ __forceinline__ void tile_compute(const float* __restrict__ sb,
   float lx[T], ly[T], lz[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) lx[t] = ly[t] = lz[t] = 0.0f;
-#pragma unroll 4
+#pragma unroll 2
   for (int j = 0; j < kSrcTile; ++j) {
     const float4 p = s4[2 * j];      // x y z fx
     const float4 q = s4[2 * j + 1];  // fy fz 2z 4z^2

@@ -194,3 +194,56 @@ def test_lanczos_covariance_statistics(orc):
     # Wishart sampling error: E|C/ns - M|_F^2 = (tr(M)^2 + |M|_F^2) / ns
     expected = np.sqrt((np.trace(M) ** 2 + np.linalg.norm(M) ** 2) / ns) / np.linalg.norm(M)
     assert err < 1.5 * expected and err > 0.5 * expected
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_step_deterministic(orc, name):
+    """kBT = 0: one solve at q^n + evolve, against the dense oracle."""
+    g = load_golden(name)
+    cb = _solver(g, "double", block=True)
+    nb = g["X"].shape[0]
+    F = np.random.default_rng(21).standard_normal(6 * nb)
+    slip = np.random.default_rng(22).standard_normal(g["r"].size) * 0.1
+    U, iters, relres = cb.bd_step(F, slip=slip, kBT=0.0, tol=1e-11, restart=100, max_iter=400)
+    ref = orc.remove_mean(g["cfg"])
+    Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.0,
+                             bool(g["wall"]), F, slip, None, None, None)
+    assert relres <= 1e-11
+    assert rel_err(U, Uo) < 1e-8
+    X, Q = cb.get_config()
+    assert rel_err(X, Xo) < 1e-10 and rel_err(Q, Qo) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_step_brownian_given_noise(orc, name):
+    """kBT > 0 with the noise vectors supplied: the whole stochastic step (Lanczos square
+    roots, RFD drift, midpoint, solve, evolve) is deterministic and must match the dense
+    oracle composition."""
+    g = load_golden(name)
+    cb = _solver(g, "double", block=True)
+    nb, n3 = g["X"].shape[0], g["r"].size
+    rng = np.random.default_rng(31)
+    F = rng.standard_normal(6 * nb)
+    noise = tuple(rng.standard_normal(n3) for _ in range(3))
+    kBT = 0.004
+    U, iters, relres = cb.bd_step(F, kBT=kBT, noise=noise, tol=1e-11, restart=100, max_iter=400,
+                                  lanczos_tol=1e-12, lanczos_max_iter=200)
+    ref = orc.remove_mean(g["cfg"])
+    Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), kBT,
+                             bool(g["wall"]), F, None, *noise)
+    assert rel_err(U, Uo) < 1e-6
+    X, Q = cb.get_config()
+    assert rel_err(X, Xo) < 1e-8 and rel_err(Q, Qo) < 1e-8
+    # the context is back on a consistent configuration: K matches the evolved positions
+    r_new = orc.blob_positions(Xo, Qo, ref)
+    assert rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r_new, Xo, ref.shape[0])) < 1e-8
+
+
+def test_bd_step_needs_noise_when_brownian():
+    g = load_golden("case_touch_free")
+    cb = _solver(g, "double")
+    nb = g["X"].shape[0]
+    with pytest.raises(RuntimeError):
+        cb.cb.bd_step(np.zeros(6 * nb), None, None, None, None, 1.0, 1e-8, 60, 100, 1e-6, 50)
+    U, it, rr = cb.bd_step(np.ones(6 * nb), kBT=0.01, rng=np.random.default_rng(0))  # draws its own noise
+    assert np.all(np.isfinite(U)) and rr <= 1e-8
