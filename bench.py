@@ -206,7 +206,8 @@ def run_ours(args):
             hx, ho = ctypes.c_void_p(), ctypes.c_void_p()
             ctx.call("rbl_pinned_alloc", nbytes, ctypes.byref(hx))
             ctx.call("rbl_pinned_alloc", nbytes, ctypes.byref(ho))
-            ctypes.memmove(hx, x_local_np.astype(ndt).ctypes.data, nbytes)
+            x_host = np.ascontiguousarray(x_local_np.astype(ndt))  # keep alive across the memmove
+            ctypes.memmove(hx, x_host.ctypes.data, nbytes)
             for _ in range(max(1, args.warmup)):
                 ctx.call("rbl_apply_saddle", hx, ho)
             barrier()
@@ -232,9 +233,19 @@ def run_ours(args):
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
             host_out = ho.numpy().copy()
         dev_out = out_local.cpu().numpy()
-        assert np.array_equal(dev_out, host_out), "host-buffer and device-resident paths disagree"
+        if not np.array_equal(dev_out, host_out):
+            dd = np.abs(dev_out.astype(np.float64) - host_out.astype(np.float64))
+            raise AssertionError(f"host-buffer and device-resident paths disagree ({precision}): {int((dd > 0).sum())} of "
+                                 f"{dd.size} entries, max |diff| {dd.max():.3e} at {int(dd.argmax())} (3N = {3 * (hi - lo) * n_blb}); "
+                                 f"dev {dev_out[int(dd.argmax())]!r} host {host_out[int(dd.argmax())]!r}")
         ctx.call("rbl_sync")
 
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(f"{args.workload}/{precision}/{world}")
+        except Exception:
+            pass
         alg_tflops = (float((hi - lo) * n_blb) * n_all) * FLOPS_PER_PAIR[wall] / (kern_ms * 1e-3) / 1e12
         results[precision] = {
             "value": pairs / (ms_step * 1e-3), "ms_per_step": ms_step, "gpu_launches": int(launches),
@@ -242,7 +253,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": int(nbytes) * world},
             "roofline": {"bound": "fp32_cuda_core" if precision == "single" else "fp64_cuda_core",
                          "kernel": "rbl::rpy_matvec_kernel", "achieved": alg_tflops, "peak": peak,
-                         "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); "
+                                         "algorithmic bytes = packed records, 162000 x 32 B (fp32) / 64 B (fp64)",
                          "kernel_ms": kern_ms, "kernel_launches_timed": int(kern_n),
                          "algorithmic_flops_per_pair": FLOPS_PER_PAIR[wall],
                          "peak_source": "FMA-chain microbenchmark run live on this GPU (rbl_fma_peak); nominal "
