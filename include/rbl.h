@@ -139,6 +139,14 @@ int rbl_dev_apply_saddle(rbl_ctx* ctx, const void* dx, void* dout);
  * dout_local = [ (M lambda)_local - K_local U_local ; K_local^T lambda_local ]. */
 int rbl_dev_apply_saddle_shard(rbl_ctx* ctx, const void* dlambda_all, const void* dr_all,
                                int n_blobs, int tgt_first, const void* dU_local, void* dout_local);
+/* Partial product for multi-GPU hosts using the symmetric kernel: dout (3*n_blobs, already scaled)
+ * holds the contribution of share `part` of `n_parts` of the unordered-pair work; the full product
+ * is the SUM of the n_parts partial outputs (all-reduce). */
+int rbl_dev_apply_M_part(rbl_ctx* ctx, const void* dF, const void* dr, int n_blobs, int part, int n_parts,
+                         void* dout);
+/* dout_local = [ dMlambda_local - K_local U_local ; K_local^T lambda_local ] for the context's bodies */
+int rbl_dev_saddle_finish(rbl_ctx* ctx, const void* dMlambda_local, const void* dlambda_local,
+                          const void* dU_local, void* dout_local);
 int rbl_sync(rbl_ctx* ctx);
 /* the context's cudaStream_t (as void*); set_stream lets a host share its own stream */
 void* rbl_stream(rbl_ctx* ctx);
@@ -162,6 +170,13 @@ int rbl_num_matvec_variants(const rbl_ctx* ctx);
 /* targets per thread and threads per CTA of variant idx */
 int rbl_matvec_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_matvec_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
+/* Product kernel selection.  0 (default): the symmetric kernel (one evaluation per unordered pair,
+ * floating-point atomics: reproducible to rounding) whenever targets == sources, the ordered kernel
+ * otherwise.  1: always the ordered kernel (bit-reproducible, every ordered pair evaluated). */
+int rbl_set_matvec_mode(rbl_ctx* ctx, int mode);
+int rbl_num_sym_variants(const rbl_ctx* ctx);
+int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
+int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t rbl_launch_count(const rbl_ctx* ctx);
 /* average duration (ms, CUDA events around the kernel alone) of the matvec kernel over

@@ -57,6 +57,8 @@ SYMBOLS = {
     "rbl_dev_apply_PC": (_i, [_vp, _vp, _vp]),
     "rbl_dev_apply_saddle": (_i, [_vp, _vp, _vp]),
     "rbl_dev_apply_saddle_shard": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "rbl_dev_apply_M_part": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rbl_dev_saddle_finish": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rbl_sync": (_i, [_vp]),
     "rbl_stream": (_vp, [_vp]),
     "rbl_set_stream": (_i, [_vp, _vp]),
@@ -72,6 +74,10 @@ SYMBOLS = {
     "rbl_num_matvec_variants": (_i, [_vp]),
     "rbl_matvec_variant_info": (_i, [_vp, _i, _pi, _pi]),
     "rbl_set_matvec_variant": (_i, [_vp, _i]),
+    "rbl_set_matvec_mode": (_i, [_vp, _i]),
+    "rbl_num_sym_variants": (_i, [_vp]),
+    "rbl_sym_variant_info": (_i, [_vp, _i, _pi, _pi]),
+    "rbl_set_sym_variant": (_i, [_vp, _i]),
     "rbl_launch_count": (_i64, [_vp]),
     "rbl_profile_matvec": (_i, [_vp, _i]),
     "rbl_matvec_profile": (_i, [_vp, _pd, _pi64, _i]),

@@ -89,6 +89,10 @@ struct rbl_ctx {
   virtual int fma_peak(int iters, double* tflops) = 0;
   virtual int num_variants() const = 0;
   virtual int variant_info(int idx, int* T, int* threads) const = 0;
+  virtual int num_sym_variants() const = 0;
+  virtual int sym_variant_info(int idx, int* T, int* threads) const = 0;
+  virtual int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) = 0;
+  virtual int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) = 0;
 
   // shared plumbing
   cudaStream_t stream = nullptr;
@@ -96,6 +100,8 @@ struct rbl_ctx {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int64_t launches = 0;
   int variant = -1;
+  int sym_variant = -1;
+  int mode = 0;  // 0: symmetric kernel when targets == sources; 1: ordered kernel always
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   DevBuf flush_buf;
@@ -132,7 +138,7 @@ struct Ctx final : rbl_ctx {
   // device state
   DevBuf d_ref, d_X, d_Q, d_r, d_S;
   // matvec workspace
-  DevBuf d_rec, d_box_src, d_box_tgt, d_scratch, d_flags;
+  DevBuf d_rec, d_box_src, d_box_tgt, d_scratch, d_flags, d_raw;
   // staging for the host-pointer API
   DevBuf d_in0, d_in1, d_out0;
   // preconditioner
@@ -360,10 +366,60 @@ struct Ctx final : rbl_ctx {
     return n_tgt >= 16384 ? 0 : rbl::matvec_num_variants<real>() - 1;
   }
 
+  int pick_sym_variant(int n) const {
+    if (sym_variant >= 0) return sym_variant;
+    return n >= 16384 ? 0 : rbl::matvec_sym_num_variants<real>() - 1;
+  }
+
+  // symmetric kernel: share `part` of `n_parts` of the unordered-pair work; out = partial product
+  int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) override {
+    if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
+    if (n < 0 || n_parts < 1 || part < 0 || part >= n_parts) return fail(RBL_ERR_INVALID, "apply_M_part: bad share");
+    if (n == 0) return RBL_OK;
+    const int v = pick_sym_variant(n);
+    rbl::SymArgs<real> A;
+    CK(rbl::matvec_sym_plan<real>(v, wall, n, part, n_parts, sm_count, &A.plan));
+    const size_t n_pad = (size_t)A.plan.n_src_tiles * rbl::kSrcTile;
+    CK(d_rec.ensure(n_pad * rbl::kRecReals * sizeof(real)));
+    CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
+    CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
+    CK(d_raw.ensure(3 * n_pad * sizeof(real)));
+    LAUNCH(1, rbl::pack_records<real>(static_cast<const real*>(r), static_cast<const real*>(F), n, (int)n_pad, wall,
+                                      (real)a, d_rec.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream));
+    A.rec = d_rec.as<real>();
+    A.box_src = d_box_src.as<float>();
+    A.box_tgt = d_box_tgt.as<float>();
+    A.raw = d_raw.as<real>();
+    A.out = static_cast<real*>(out);
+    A.C = rbl::make_pair_consts<real>(a, eta);
+    A.wall = wall ? 1 : 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      prof_events.emplace_back(e0, e1);
+    }
+    LAUNCH(2, rbl::matvec_sym_launch<real>(v, A, stream, e0, e1));
+    return RBL_OK;
+  }
+
+  int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) override {
+    RET(need_K());
+    const size_t n3 = 3 * (size_t)N();
+    real* dout = static_cast<real*>(out);
+    LAUNCH(1, rbl::k_dot<real>(static_cast<const real*>(U), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)-1,
+                               static_cast<const real*>(Mlam), dout, stream));
+    LAUNCH(1, rbl::kt_dot<real>(static_cast<const real*>(lam), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dout + n3, stream));
+    return RBL_OK;
+  }
+
   int dev_apply_M(const void* F, const void* r, int n, int t0, int nt, void* out) override {
     if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
     if (n < 0 || t0 < 0 || nt < 0 || t0 + nt > n) return fail(RBL_ERR_INVALID, "apply_M: bad target range");
     if (n == 0 || nt == 0) return RBL_OK;
+    if (mode == 0 && t0 == 0 && nt == n) return dev_apply_M_part(F, r, n, 0, 1, out);
     const int v = pick_variant(nt);
     rbl::MatvecArgs<real> A;
     CK(rbl::matvec_plan<real>(v, wall, n, t0, nt, sm_count, &A.plan));
@@ -946,6 +1002,14 @@ struct Ctx final : rbl_ctx {
     *tflops = flops / (ms * 1e-3) / 1e12;
     return RBL_OK;
   }
+  int num_sym_variants() const override { return rbl::matvec_sym_num_variants<real>(); }
+  int sym_variant_info(int idx, int* T, int* threads) const override {
+    if (idx < 0 || idx >= rbl::matvec_sym_num_variants<real>()) return RBL_ERR_INVALID;
+    const rbl::MatvecVariant v = rbl::matvec_sym_variant<real>(idx);
+    *T = v.T;
+    *threads = v.threads;
+    return RBL_OK;
+  }
   int num_variants() const override { return rbl::matvec_num_variants<real>(); }
   int variant_info(int idx, int* T, int* threads) const override {
     if (idx < 0 || idx >= rbl::matvec_num_variants<real>()) return RBL_ERR_INVALID;
@@ -1096,6 +1160,14 @@ int rbl_dev_apply_saddle_shard(rbl_ctx* ctx, const void* dl, const void* dr, int
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
   return ctx->saddle_shard(dl, dr, n, t0, dU, dout);
 }
+int rbl_dev_apply_M_part(rbl_ctx* ctx, const void* dF, const void* dr, int n, int part, int n_parts, void* dout) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->dev_apply_M_part(dF, dr, n, part, n_parts, dout);
+}
+int rbl_dev_saddle_finish(rbl_ctx* ctx, const void* dM, const void* dl, const void* dU, void* dout) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->saddle_finish(dM, dl, dU, dout);
+}
 int rbl_sync(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->sync(); }
 void* rbl_stream(rbl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int rbl_set_stream(rbl_ctx* ctx, void* s) {
@@ -1153,6 +1225,23 @@ int rbl_set_matvec_variant(rbl_ctx* ctx, int idx) {
   CTX_OR_FAIL(ctx);
   if (idx >= ctx->num_variants()) return ctx->fail(RBL_ERR_INVALID, "no such matvec variant");
   ctx->variant = idx < 0 ? -1 : idx;
+  return RBL_OK;
+}
+int rbl_set_matvec_mode(rbl_ctx* ctx, int mode) {
+  CTX_OR_FAIL(ctx);
+  if (mode != 0 && mode != 1) return ctx->fail(RBL_ERR_INVALID, "matvec mode must be 0 (symmetric) or 1 (ordered)");
+  ctx->mode = mode;
+  return RBL_OK;
+}
+int rbl_num_sym_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym_variants() : 0; }
+int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {
+  if (!ctx || !T || !threads) return RBL_ERR_INVALID;
+  return ctx->sym_variant_info(idx, T, threads);
+}
+int rbl_set_sym_variant(rbl_ctx* ctx, int idx) {
+  CTX_OR_FAIL(ctx);
+  if (idx >= ctx->num_sym_variants()) return ctx->fail(RBL_ERR_INVALID, "no such symmetric matvec variant");
+  ctx->sym_variant = idx < 0 ? -1 : idx;
   return RBL_OK;
 }
 int64_t rbl_launch_count(const rbl_ctx* ctx) { return ctx ? ctx->launches : 0; }

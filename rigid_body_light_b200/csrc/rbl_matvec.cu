@@ -552,6 +552,298 @@ cudaError_t matvec_launch<double>(int variant, const MatvecArgs<double>& a, cuda
   return cudaErrorInvalidValue;
 }
 
+
+// ----------------------------------------------------------------------------------
+// symmetric kernel: one evaluation per unordered pair
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void load_full_rec(const float* p, float& x, float& y, float& z, float& fx,
+                                              float& fy, float& fz, float& z2, float& nz4) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  x = a.x; y = a.y; z = a.z; fx = a.w; fy = b.x; fz = b.y; z2 = b.z; nz4 = -b.w;
+}
+__device__ __forceinline__ void load_full_rec(const double* p, double& x, double& y, double& z, double& fx,
+                                              double& fy, double& fz, double& z2, double& nz4) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+  x = a.x; y = a.y; z = b.x; fx = b.y; fy = c.x; fz = c.y; z2 = d.x; nz4 = -d.y;
+}
+
+template <typename real>
+__device__ __forceinline__ real warp_sum(real v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one staged source tile against the thread's T targets, both directions.  Every 32 sources
+// each lane ends up holding the warp-total reaction of source (j0 + lane) and adds it to the
+// global accumulators (coalesced RED.ADD).
+template <typename real, bool WALL, bool NEAR, int T>
+__device__ __forceinline__ void tile_compute_sym(const real* __restrict__ sb, const PairConsts<real>& C,
+                                                 const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
+                                                 const real (&fxi)[T], const real (&fyi)[T], const real (&fzi)[T],
+                                                 const real (&z2i)[T], const real (&nz4i)[T], real (&ux)[T],
+                                                 real (&uy)[T], real (&uz)[T], real* __restrict__ raw_tile) {
+  const int lane = threadIdx.x & 31;
+  real lx[T], ly[T], lz[T];  // per-tile accumulators (two-level summation, see tile_compute)
+#pragma unroll
+  for (int t = 0; t < T; ++t) lx[t] = ly[t] = lz[t] = (real)0;
+  for (int j0 = 0; j0 < kSrcTile; j0 += 32) {
+    real rx = 0, ry = 0, rz = 0;
+#pragma unroll 2
+    for (int jj = 0; jj < 32; ++jj) {
+      real xj, yj, zj, fxj, fyj, fzj, z2j, nz4j;
+      load_full_rec(sb + (size_t)(j0 + jj) * kRecReals, xj, yj, zj, fxj, fyj, fzj, z2j, nz4j);
+      real ax = 0, ay = 0, az = 0;
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], z2i[t], nz4i[t], xj, yj, zj,
+                                   fxj, fyj, fzj, z2j, nz4j, lx[t], ly[t], lz[t], ax, ay, az);
+      ax = warp_sum(ax);
+      ay = warp_sum(ay);
+      az = warp_sum(az);
+      if (lane == jj) { rx = ax; ry = ay; rz = az; }
+    }
+    real* o = raw_tile + 3 * (size_t)(j0 + lane);
+    atomicAdd(o, rx);
+    atomicAdd(o + 1, ry);
+    atomicAdd(o + 2, rz);
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    ux[t] += lx[t];
+    uy[t] += ly[t];
+    uz[t] += lz[t];
+  }
+}
+
+// first unit index of row I of the triangle: rows have n_src_tiles - I*diag units
+__device__ __host__ __forceinline__ long long sym_row_offset(long long I, int ns, int diag) {
+  return I * ns - (long long)diag * (I * (I - 1) / 2);
+}
+
+template <typename real, bool WALL, int T, int NT>
+__global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> A) {
+  constexpr int TT = T * NT;
+  constexpr uint32_t kTileBytes = kSrcTile * kRecReals * sizeof(real);
+  __shared__ __align__(128) real sbuf[2][kSrcTile * kRecReals];
+  __shared__ __align__(8) unsigned long long mbar[2];
+
+  const int tid = threadIdx.x;
+  const int ns = A.plan.n_src_tiles, D = A.plan.diag, ntt = A.plan.n_tgt_tiles;
+  const long long span = A.plan.u1 - A.plan.u0;
+  const long long g0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
+  const long long g1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
+  if (g0 >= g1) return;
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // locate the row of g0: largest I with offset(I) <= g0
+  int I;
+  {
+    int lo = 0, hi = ntt - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sym_row_offset(mid, ns, D) <= g0) lo = mid; else hi = mid - 1;
+    }
+    I = lo;
+  }
+  int J = I * D + (int)(g0 - sym_row_offset(I, ns, D));  // source tile of the first unit
+  if (tid == 0) {
+    mbar_expect_tx(&mbar[0], kTileBytes);
+    tma_load_1d(sbuf[0], A.rec + (size_t)J * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
+  }
+
+  real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], z2i[T], nz4i[T], ux[T], uy[T], uz[T];
+  bool fresh = true;
+  const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
+
+  for (long long g = g0; g < g1; ++g) {
+    const int it = (int)(g - g0);
+    const int buf = it & 1;
+    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+    const bool row_end = (J + 1 == ns);
+
+    if (tid == 0 && g + 1 < g1) {
+      const int nJ = row_end ? (I + 1) * D : J + 1;
+      mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
+      tma_load_1d(sbuf[buf ^ 1], A.rec + (size_t)nJ * kSrcTile * kRecReals, kTileBytes, &mbar[buf ^ 1]);
+    }
+
+    if (fresh) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        int li = I * TT + tid + t * NT;
+        const bool pad = li >= A.plan.n;
+        if (pad) li = A.plan.n - 1;
+        load_full_rec(A.rec + (size_t)li * kRecReals, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], z2i[t], nz4i[t]);
+        if (pad) fxi[t] = fyi[t] = fzi[t] = (real)0;  // padding lanes exert nothing
+        ux[t] = uy[t] = uz[t] = (real)0;
+      }
+      fresh = false;
+    }
+
+    const bool far = box_gap2(A.box_tgt + 6 * (size_t)I, A.box_src + 6 * (size_t)J) > near2;
+    const bool diagonal = J < (I + 1) * D;  // source tile lies inside this target tile: ordered
+
+    mbar_wait(&mbar[buf], parity);
+    if (diagonal) {
+      tile_compute<WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz);
+    } else {
+      real* raw_tile = A.raw + 3 * (size_t)J * kSrcTile;
+      if (far)
+        tile_compute_sym<real, WALL, false, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, z2i, nz4i, ux, uy, uz, raw_tile);
+      else
+        tile_compute_sym<real, WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, z2i, nz4i, ux, uy, uz, raw_tile);
+    }
+    __syncthreads();
+
+    if (row_end || g + 1 == g1) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int li = I * TT + tid + t * NT;
+        if (li < A.plan.n) {
+          atomicAdd(A.raw + 3 * (size_t)li + 0, ux[t]);
+          atomicAdd(A.raw + 3 * (size_t)li + 1, uy[t]);
+          atomicAdd(A.raw + 3 * (size_t)li + 2, uz[t]);
+        }
+      }
+      fresh = true;
+    }
+    if (row_end) {
+      ++I;
+      J = I * D;
+    } else {
+      ++J;
+    }
+  }
+}
+
+template <typename real, bool WALL>
+__global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.plan.n) return;
+  real sc = A.C.out_scale;
+  if (WALL) sc *= damp(A.rec[(size_t)i * kRecReals + 2], A.C.a, A.C.inv_a);
+  A.out[3 * (size_t)i + 0] = A.raw[3 * (size_t)i + 0] * sc;
+  A.out[3 * (size_t)i + 1] = A.raw[3 * (size_t)i + 1] * sc;
+  A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
+}
+
+#define RBL_F32_SYM_VARIANTS(X) X(4, 256) X(8, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F64_SYM_VARIANTS(X) X(2, 256) X(2, 128) X(4, 128) X(1, 256)
+
+template <>
+int matvec_sym_num_variants<float>() { return 6; }
+template <>
+int matvec_sym_num_variants<double>() { return 4; }
+template <>
+MatvecVariant matvec_sym_variant<float>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F32_SYM_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+template <>
+MatvecVariant matvec_sym_variant<double>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F64_SYM_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t sym_occupancy_of(int* bps) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym_kernel<real, WALL, T, NT>, NT, 0);
+}
+template <typename real>
+static cudaError_t sym_variant_occupancy(int variant, bool wall, int* bps);
+template <>
+cudaError_t sym_variant_occupancy<float>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return wall ? sym_occupancy_of<float, true, T, NT>(bps) : sym_occupancy_of<float, false, T, NT>(bps);
+  RBL_F32_SYM_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t sym_variant_occupancy<double>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return wall ? sym_occupancy_of<double, true, T, NT>(bps) : sym_occupancy_of<double, false, T, NT>(bps);
+  RBL_F64_SYM_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+template <typename real>
+cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts, int sm_count, SymPlan* plan) {
+  if (variant < 0 || variant >= matvec_sym_num_variants<real>() || n_parts < 1 || part < 0 || part >= n_parts)
+    return cudaErrorInvalidValue;
+  const MatvecVariant v = matvec_sym_variant<real>(variant);
+  int bps = 0;
+  cudaError_t e = sym_variant_occupancy<real>(variant, wall, &bps);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) return cudaErrorLaunchOutOfResources;
+  plan->n = n;
+  plan->n_src_tiles = (n + kSrcTile - 1) / kSrcTile;
+  plan->tgt_tile = v.T * v.threads;
+  plan->diag = plan->tgt_tile / kSrcTile;
+  plan->n_tgt_tiles = (n + plan->tgt_tile - 1) / plan->tgt_tile;
+  plan->units = sym_row_offset(plan->n_tgt_tiles, plan->n_src_tiles, plan->diag);
+  plan->u0 = plan->units * part / n_parts;
+  plan->u1 = plan->units * (part + 1) / n_parts;
+  plan->grid = sm_count * bps;
+  return cudaSuccess;
+}
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t sym_launch_one(const SymArgs<real>& a, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+  static_assert((T * NT) % kSrcTile == 0, "target tile must be a multiple of the source tile");
+  cudaError_t e = cudaMemsetAsync(a.raw, 0, 3 * (size_t)a.plan.n_src_tiles * kSrcTile * sizeof(real), s);
+  if (e != cudaSuccess) return e;
+  if (ev0) cudaEventRecord(ev0, s);
+  if (a.plan.u1 > a.plan.u0) rpy_matvec_sym_kernel<real, WALL, T, NT><<<a.plan.grid, NT, 0, s>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (ev1) cudaEventRecord(ev1, s);
+  rpy_sym_scale_kernel<real, WALL><<<(a.plan.n + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <>
+cudaError_t matvec_sym_launch<float>(int variant, const SymArgs<float>& a, cudaStream_t s, cudaEvent_t ev0,
+                                     cudaEvent_t ev1) {
+  if (a.plan.n <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return a.wall ? sym_launch_one<float, true, T, NT>(a, s, ev0, ev1) : sym_launch_one<float, false, T, NT>(a, s, ev0, ev1);
+  RBL_F32_SYM_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t matvec_sym_launch<double>(int variant, const SymArgs<double>& a, cudaStream_t s, cudaEvent_t ev0,
+                                      cudaEvent_t ev1) {
+  if (a.plan.n <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return a.wall ? sym_launch_one<double, true, T, NT>(a, s, ev0, ev1) : sym_launch_one<double, false, T, NT>(a, s, ev0, ev1);
+  RBL_F64_SYM_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 // ----------------------------------------------------------------------------------
 // FMA-pipe peak microbenchmark: 16 independent FMA chains per thread, register operands
 // ----------------------------------------------------------------------------------
@@ -591,6 +883,7 @@ cudaError_t fma_peak_launch(int sm_count, int iters, real* sink, double* flops,
   template cudaError_t repack_forces<real>(const real*, int, bool, real, real*,            \
                                            cudaStream_t);                                  \
   template cudaError_t tile_boxes<real>(const real*, int, int, int, float*, cudaStream_t); \
+  template cudaError_t matvec_sym_plan<real>(int, bool, int, int, int, int, SymPlan*);           \
   template cudaError_t fma_peak_launch<real>(int, int, real*, double*, cudaStream_t);
 INST(float)
 INST(double)

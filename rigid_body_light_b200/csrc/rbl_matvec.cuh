@@ -86,6 +86,49 @@ template <typename real>
 cudaError_t matvec_launch(int variant, const MatvecArgs<real>& args, cudaStream_t s,
                           cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 
+// ---- symmetric product (targets == sources) ----------------------------------------------
+// Evaluates every UNORDERED blob pair once and applies the block in both directions
+// (pair_sym); 1.25-1.4x fewer instructions per ordered pair than the ordered kernel.  The
+// reaction on the source side is reduced across the warp and accumulated with global
+// floating-point atomics, so results are reproducible to rounding, not bit for bit (the
+// ordered kernel stays available for that).  Work = the upper triangle of the
+// (target tile x 256-source tile) grid, linearised row by row; [part, n_parts) selects a
+// contiguous share of it (multi-GPU: the partial products are summed with an all-reduce).
+struct SymPlan {
+  int n;            // blobs (targets == sources)
+  int n_src_tiles;  // ceil(n / kSrcTile)
+  int n_tgt_tiles;  // ceil(n / tgt_tile)
+  int tgt_tile;     // T * threads, a multiple of kSrcTile
+  int diag;         // tgt_tile / kSrcTile: source tiles per row that overlap the target tile
+  long long units;  // units of the whole triangle
+  long long u0, u1; // this launch's share
+  int grid;
+};
+
+template <typename real>
+struct SymArgs {
+  const real* rec;
+  const float* box_src;
+  const float* box_tgt;
+  real* raw;   // 3 * n_src_tiles * kSrcTile accumulators, zeroed by the launcher
+  real* out;   // 3 * n
+  SymPlan plan;
+  PairConsts<real> C;
+  int wall;
+};
+
+template <typename real>
+int matvec_sym_num_variants();
+template <typename real>
+MatvecVariant matvec_sym_variant(int idx);
+template <typename real>
+cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts, int sm_count,
+                            SymPlan* plan);
+// memset(raw) + symmetric kernel + scale kernel (out = raw * B_i / (8 pi eta))
+template <typename real>
+cudaError_t matvec_sym_launch(int variant, const SymArgs<real>& args, cudaStream_t s,
+                              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+
 // FMA-pipe peak microbenchmark (the roofline denominator SURVEY.md section 8d asks for).
 // Returns flop executed; time it with events around the call.
 template <typename real>

@@ -3,9 +3,12 @@ contiguous ranges.
 
 Every rank owns the bodies [b0, b1): their blob placement, K, K^T and preconditioner are
 rank-local.  The mobility product needs every source, so each application all-gathers the
-constraint forces lambda (3N reals) over NCCL/NVLink and each rank evaluates its own target
-rows against all sources with ``rbl_dev_apply_saddle_shard``.  Blob positions are all-gathered
-once per configuration, not per application.
+constraint forces lambda (3N reals) over NCCL/NVLink; the O(N^2) work itself is the upper
+triangle of the tile grid of the SYMMETRIC kernel, cut into ``world`` equal contiguous shares
+(``rbl_dev_apply_M_part``): every rank produces a partial product over all blobs, the partial
+products are summed with one all-reduce (3N reals), and each rank finishes its own rows with
+its local K and K^T (``rbl_dev_saddle_finish``).  Blob positions are all-gathered once per
+configuration, not per application.
 
 The collective plumbing is ``torch.distributed`` (backend "nccl" on GPUs; the same code runs
 under "gloo" on CPU tensors for the host-logic tests).  The arithmetic is behind a small
@@ -30,8 +33,10 @@ def body_ranges(n_bodies: int, world: int):
 
 class ShardedSaddle:
     """apply_saddle over ``world`` ranks.  ``backend`` must provide
-    ``positions() -> tensor(3*n_local)`` and
-    ``saddle_shard(lam_all, r_all, n_all, t0, U_local, out_local)``."""
+    ``positions() -> tensor(3*n_local)``,
+    ``saddle_shard(lam_all, r_all, n_all, t0, U_local, out_local)`` (single rank),
+    ``apply_M_part(lam_all, r_all, n_all, part, n_parts, out_all)`` and
+    ``saddle_finish(Mlam_local, lam_local, U_local, out_local)``."""
 
     def __init__(self, backend, n_bodies, n_blb, rank, world, dist=None):
         import torch
@@ -86,7 +91,15 @@ class ShardedSaddle:
             self.refresh_positions()
         n3 = 3 * self.n_local
         self._allgather(x_local[:n3], self.lam_all)
-        self.backend.saddle_shard(self.lam_all, self.r_all, self.n_all, self.t0, x_local[n3:], out_local)
+        if self.world == 1:
+            self.backend.saddle_shard(self.lam_all, self.r_all, self.n_all, self.t0, x_local[n3:], out_local)
+            return out_local
+        if getattr(self, "_mbuf", None) is None:
+            self._mbuf = self.torch.empty_like(self.lam_all)
+        self.backend.apply_M_part(self.lam_all, self.r_all, self.n_all, self.rank, self.world, self._mbuf)
+        self.dist.all_reduce(self._mbuf)  # sum of the partial products
+        lo = 3 * self.t0
+        self.backend.saddle_finish(self._mbuf[lo:lo + n3], x_local[:n3], x_local[n3:], out_local)
         return out_local
 
 
@@ -111,6 +124,14 @@ class CudaShard:
     def saddle_shard(self, lam_all, r_all, n_all, t0, U_local, out_local):
         self.ctx.call("rbl_dev_apply_saddle_shard", lam_all.data_ptr(), r_all.data_ptr(), n_all, t0,
                       U_local.data_ptr(), out_local.data_ptr())
+
+    def apply_M_part(self, lam_all, r_all, n_all, part, n_parts, out_all):
+        self.ctx.call("rbl_dev_apply_M_part", lam_all.data_ptr(), r_all.data_ptr(), n_all, part, n_parts,
+                      out_all.data_ptr())
+
+    def saddle_finish(self, Mlam_local, lam_local, U_local, out_local):
+        self.ctx.call("rbl_dev_saddle_finish", Mlam_local.data_ptr(), lam_local.data_ptr(), U_local.data_ptr(),
+                      out_local.data_ptr())
 
 
 def slice_system(vec, ranges, n_blb, rank):

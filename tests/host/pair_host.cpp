@@ -2,6 +2,8 @@
 // HOST so the division-free / branch-free reformulation can be checked against the
 // oracle on a machine without a GPU (tests/test_pair_math_host.py).  Test code only:
 // this is not a CPU fallback and is never loaded by the package.
+#include <vector>
+
 #include "../../rigid_body_light_b200/csrc/rbl_pair.cuh"
 
 template <typename real>
@@ -58,3 +60,36 @@ static void cross(const real* rt, int nt, const real* F, const real* r, int n, d
   }
 }
 extern "C" void pair_cross_host_f64(const double* rt, int nt, const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { cross<double>(rt, nt, F, r, n, a, eta, wall, near, U); }
+
+// symmetric (unordered-pair) evaluation: every pair i<j once through pair_sym, the diagonal
+// through the ordered general path -- the arithmetic of the symmetric CUDA kernel
+template <typename real>
+static void matvec_sym(const real* F, const real* r, int n, double a, double eta, int wall, int near, real* U) {
+  rbl::PairConsts<real> C = rbl::make_pair_consts<real>(a, eta);
+  std::vector<real> f(3 * (size_t)n), acc(3 * (size_t)n, 0);
+  for (int j = 0; j < n; ++j) {
+    real zj = r[3 * j + 2];
+    real bj = wall ? (zj >= (real)a ? (real)1 : zj * C.inv_a) : (real)1;
+    for (int c = 0; c < 3; ++c) f[3 * j + c] = bj * F[3 * j + c];
+  }
+  for (int i = 0; i < n; ++i) {
+    real zi = r[3 * i + 2];
+    // self term: ordered general path
+    if (wall) rbl::pair<real, true, true>(C, r[3*i], r[3*i+1], zi, r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], 2*zi, 4*zi*zi, acc[3*i], acc[3*i+1], acc[3*i+2]);
+    else      rbl::pair<real, false, true>(C, r[3*i], r[3*i+1], zi, r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], 2*zi, 4*zi*zi, acc[3*i], acc[3*i+1], acc[3*i+2]);
+    for (int j = i + 1; j < n; ++j) {
+      real zj = r[3 * j + 2];
+#define ARGS r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], 2*zi, -4*zi*zi, r[3*j], r[3*j+1], zj, f[3*j], f[3*j+1], f[3*j+2], 2*zj, -4*zj*zj, acc[3*i], acc[3*i+1], acc[3*i+2], acc[3*j], acc[3*j+1], acc[3*j+2]
+      if (wall) { if (near) rbl::pair_sym<real, true, true>(C, ARGS); else rbl::pair_sym<real, true, false>(C, ARGS); }
+      else      { if (near) rbl::pair_sym<real, false, true>(C, ARGS); else rbl::pair_sym<real, false, false>(C, ARGS); }
+#undef ARGS
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    real zi = r[3 * i + 2];
+    real bi = wall ? (zi >= (real)a ? (real)1 : zi * C.inv_a) : (real)1;
+    for (int c = 0; c < 3; ++c) U[3 * i + c] = acc[3 * i + c] * C.out_scale * bi;
+  }
+}
+extern "C" void pair_matvec_sym_host_f64(const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { matvec_sym<double>(F, r, n, a, eta, wall, near, U); }
+extern "C" void pair_matvec_sym_host_f32(const float* F, const float* r, int n, double a, double eta, int wall, int near, float* U) { matvec_sym<float>(F, r, n, a, eta, wall, near, U); }

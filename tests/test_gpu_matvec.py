@@ -114,9 +114,73 @@ def test_every_kernel_variant_agrees(orc, wall, precision):
     ctx.set_flags(0, wall)
     nv = ctx.L.rbl_num_matvec_variants(ctx.h)
     assert nv >= 2
+    ctx.call("rbl_set_matvec_mode", 1)  # ordered kernel
     for v in range(nv):
         ctx.call("rbl_set_matvec_variant", v)
-        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], v
+        out = ctx.apply_M(F, r)
+        assert rel_err(out, want) < TOL[precision], v
+        assert np.array_equal(ctx.apply_M(F, r), out), v  # bit-reproducible
+    ctx.call("rbl_set_matvec_mode", 0)  # symmetric kernel
+    ns = ctx.L.rbl_num_sym_variants(ctx.h)
+    assert ns >= 2
+    for v in range(ns):
+        ctx.call("rbl_set_sym_variant", v)
+        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], ("sym", v)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_both_kernels_on_a_suspension(orc, mode, precision):
+    """ordered and symmetric kernels against the oracle on touching spheres above the wall
+    (several target tiles, several source tiles, far and near tile pairs)"""
+    from rigid_body_light_b200._lib import Context
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(30, 162, True)
+    ref = s["cfg"] - s["cfg"].mean(axis=0)
+    ctx = Context(precision)
+    ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
+    ctx.set_flags(0, 1)
+    ctx.set_config(s["X"], s["Q"])
+    ctx.call("rbl_set_matvec_mode", mode)
+    n = 30 * 162
+    r = np.empty(3 * n, ctx.real)
+    ctx.call("rbl_blob_positions", r.ctypes.data)
+    F = np.random.default_rng(8).standard_normal(3 * n)
+    want = _oracle_for(orc, F, r, s["a"], 1.0, True, precision)
+    for v in range(ctx.L.rbl_num_sym_variants(ctx.h) if mode == 0 else ctx.L.rbl_num_matvec_variants(ctx.h)):
+        ctx.call("rbl_set_sym_variant" if mode == 0 else "rbl_set_matvec_variant", v)
+        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], (mode, v)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_partial_products_sum_to_the_product(orc, n_parts, precision):
+    """rbl_dev_apply_M_part: the shares of the unordered-pair work a multi-GPU run hands to its
+    ranks sum (all-reduce) to the full product."""
+    import torch
+
+    from rigid_body_light_b200._lib import Context
+
+    a, eta = 0.11, 1.0
+    r, F = _random_cloud(5000, True, seed=5)
+    dt = _dtype(precision)
+    tdt = torch.float64 if precision == "double" else torch.float32
+    ctx = Context(precision)
+    ctx.set_parameters(a, 0.01, 1.0, eta, np.zeros((1, 3)))
+    ctx.set_flags(0, 1)
+    dr = torch.from_numpy(r.reshape(-1).astype(dt)).cuda()
+    dF = torch.from_numpy(F.astype(dt)).cuda()
+    total = torch.zeros(3 * 5000, dtype=tdt, device="cuda")
+    part = torch.empty_like(total)
+    for p in range(n_parts):
+        ctx.call("rbl_dev_apply_M_part", dF.data_ptr(), dr.data_ptr(), 5000, p, n_parts, part.data_ptr())
+        ctx.call("rbl_sync")
+        total += part
+    want = _oracle_for(orc, F, r, a, eta, True, precision)
+    assert rel_err(total.cpu().numpy(), want) < TOL[precision]
     ctx.close()
 
 
@@ -170,7 +234,10 @@ def test_full_size_sampled_rows_and_properties(orc, config2, precision):
     lin = rel_err(u12, u1.astype(np.float64) + 0.5 * u2.astype(np.float64))
     print(f"[{precision}] sampled-row error {rel_err(got, want):.3e}  symmetry {sym / scale:.3e}  linearity {lin:.3e}")
     assert lin < (1e-13 if precision == "double" else 5e-6)
-    assert np.array_equal(cb.apply_M(F1, r), u1)
+    # the default (symmetric) kernel accumulates with floating-point atomics: reproducible to
+    # rounding; the ordered kernel is bit-reproducible
+    again = cb.apply_M(F1, r)
+    assert rel_err(again, u1) < (1e-14 if precision == "double" else 2e-6)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -23,11 +23,12 @@ def host_lib():
     return ctypes.CDLL(so)
 
 
-def _host_matvec(L, F, r, a, eta, wall, near, dt):
+def _host_matvec(L, F, r, a, eta, wall, near, dt, sym=False):
     F = np.ascontiguousarray(F, dt)
     r = np.ascontiguousarray(r, dt).reshape(-1)
     U = np.empty_like(F)
-    fn = L.pair_matvec_host_f64 if dt == np.float64 else L.pair_matvec_host_f32
+    name = "pair_matvec_sym_host_" if sym else "pair_matvec_host_"
+    fn = getattr(L, name + ("f64" if dt == np.float64 else "f32"))
     fn(ctypes.c_void_p(F.ctypes.data), ctypes.c_void_p(r.ctypes.data), ctypes.c_int(r.size // 3), ctypes.c_double(a),
        ctypes.c_double(eta), ctypes.c_int(wall), ctypes.c_int(near), ctypes.c_void_p(U.ctypes.data))
     return U
@@ -80,3 +81,22 @@ def test_far_only_path_equals_general_path_when_separated(host_lib):
                                      ctypes.c_double(1.0), ctypes.c_int(0), ctypes.c_int(near), ctypes.c_void_p(U.ctypes.data))
         out.append(U)
     assert rel_err(out[1], out[0]) > 1e-3
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_symmetric_pair_evaluation_double(host_lib, name):
+    """pair_sym: one evaluation per unordered pair applied in both directions (the arithmetic
+    of the symmetric CUDA kernel) reproduces the full ordered product."""
+    g = load_golden(name)
+    u = _host_matvec(host_lib, g["lam"], g["r"], float(g["a"]), float(g["eta"]), int(g["wall"]), 1, np.float64, sym=True)
+    assert rel_err(u, g["MF"]) < TOL["double"]
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_symmetric_pair_evaluation_float(host_lib, orc, name):
+    g = load_golden(name)
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    r32, f32 = g["r"].astype(np.float32), g["lam"].astype(np.float32)
+    want = orc.apply_M(f32.astype(np.float64), r32.astype(np.float64), a, eta, wall)
+    u = _host_matvec(host_lib, f32, r32, a, eta, int(wall), 1, np.float32, sym=True)
+    assert rel_err(u, want) < TOL["single"]

@@ -52,6 +52,22 @@ def _worker(rank, world, port, n_bodies, shell, out_q):
             F = orc.KT_dot(lam_all.numpy()[3 * t0:3 * (t0 + nl)], rl, Xl, n_blb)
             out_local.copy_(torch.from_numpy(np.concatenate([slip, F])))
 
+        def apply_M_part(self, lam_all, r_all, n_all, part, n_parts, out_all):
+            # any decomposition whose parts SUM to the product will do for the host logic: this
+            # double gives part p the rows [n p/P, n (p+1)/P) and zeros elsewhere
+            r0, r1 = n_all * part // n_parts, n_all * (part + 1) // n_parts
+            out = np.zeros(3 * n_all)
+            out[3 * r0:3 * r1] = orc.apply_M(lam_all.numpy(), r_all.numpy(), s["a"], 1.0, True, rows=(r0, r1 - r0))
+            out_all.copy_(torch.from_numpy(out))
+
+        def saddle_finish(self, Mlam_local, lam_local, U_local, out_local):
+            nl = (hi - lo) * n_blb
+            rl = orc.blob_positions(Xl, Ql, ref)
+            slip = Mlam_local.numpy() - orc.K_dot(U_local.numpy(), rl, Xl, n_blb)
+            F = orc.KT_dot(lam_local.numpy(), rl, Xl, n_blb)
+            assert slip.size == 3 * nl
+            out_local.copy_(torch.from_numpy(np.concatenate([slip, F])))
+
     op = ShardedSaddle(OracleShard(), n_bodies, n_blb, rank, world, dist)
     vec = np.random.default_rng(2).standard_normal(3 * n_bodies * n_blb + 6 * n_bodies)
     x_local = torch.from_numpy(slice_system(vec, ranges, n_blb, rank))

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--precisions", default="single,double")
     ap.add_argument("--walls", default="1,0")
     ap.add_argument("--variants", default="all")
+    ap.add_argument("--kernel", default="symmetric", choices=["symmetric", "ordered"])
     args = ap.parse_args()
     for precision in args.precisions.split(","):
         ctx = Context(precision)
@@ -43,13 +44,18 @@ def main():
             F = torch.randn(3 * n, dtype=tdt, device="cuda")
             out = torch.empty(3 * n, dtype=tdt, device="cuda")
             ctx.call("rbl_sync")
-            nv = ctx.L.rbl_num_matvec_variants(ctx.h)
+            ctx.call("rbl_set_matvec_mode", 1 if args.kernel == "ordered" else 0)
+            nv = ctx.L.rbl_num_matvec_variants(ctx.h) if args.kernel == "ordered" else ctx.L.rbl_num_sym_variants(ctx.h)
             vs = range(nv) if args.variants == "all" else [int(v) for v in args.variants.split(",")]
             ctx.call("rbl_profile_matvec", 1)
             for v in vs:
                 T, th = ctypes.c_int(), ctypes.c_int()
-                ctx.L.rbl_matvec_variant_info(ctx.h, v, ctypes.byref(T), ctypes.byref(th))
-                ctx.call("rbl_set_matvec_variant", v)
+                if args.kernel == "ordered":
+                    ctx.L.rbl_matvec_variant_info(ctx.h, v, ctypes.byref(T), ctypes.byref(th))
+                    ctx.call("rbl_set_matvec_variant", v)
+                else:
+                    ctx.L.rbl_sym_variant_info(ctx.h, v, ctypes.byref(T), ctypes.byref(th))
+                    ctx.call("rbl_set_sym_variant", v)
                 ctx.call("rbl_dev_apply_M", F.data_ptr(), r.data_ptr(), n, 0, n, out.data_ptr())  # warm-up
                 ctx.call("rbl_sync")
                 ctx.matvec_profile(reset=True)
@@ -60,7 +66,7 @@ def main():
                 kms, nl = ctx.matvec_profile(reset=True)
                 pairs = float(n) * n
                 tf = pairs * FLOPS[wall] / (kms * 1e-3) / 1e12
-                print(json.dumps({"probe": "matvec", "precision": precision, "wall": wall, "variant": v, "T": T.value,
+                print(json.dumps({"probe": "matvec", "kernel": args.kernel, "precision": precision, "wall": wall, "variant": v, "T": T.value,
                                   "threads": th.value, "n": n, "ms_call": round(ms, 3), "ms_kernel": round(kms, 3),
                                   "gpairs_s": round(pairs / (ms * 1e-3) / 1e9, 1), "alg_tflops": round(tf, 2),
                                   "frac_of_fma_peak": round(tf / peak, 3), "sum": float(out.double().abs().sum())}),

@@ -122,6 +122,55 @@ __global__ void __launch_bounds__(NT) k_const(const float* __restrict__ tgt, flo
   }
 }
 
+
+template <int T, int NT, bool NEAR, int UNROLL>
+__global__ void __launch_bounds__(NT) k_sym(const float4* __restrict__ src, const float4* __restrict__ tgtrec,
+                                            float* __restrict__ out, float* __restrict__ raw, int reps,
+                                            PairConsts<float> C) {
+  __shared__ float4 sb[2 * 256];
+  float xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], z2i[T], nz4i[T], ux[T], uy[T], uz[T];
+  const int lane = threadIdx.x & 31;
+  for (int t = 0; t < T; ++t) {
+    int i = (blockIdx.x * NT + threadIdx.x) * T + t;
+    float4 p = tgtrec[2 * (i % NSRC)], q = tgtrec[2 * (i % NSRC) + 1];
+    xi[t] = p.x + 20.f + 0.001f * (i % 97); yi[t] = p.y; zi[t] = p.z; fxi[t] = p.w; fyi[t] = q.x; fzi[t] = q.y; z2i[t] = q.z; nz4i[t] = -q.w;
+    ux[t] = uy[t] = uz[t] = 0;
+  }
+  for (int r = 0; r < reps; ++r)
+    for (int tile = 0; tile < NSRC / 256; ++tile) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < 512; k += NT) sb[k] = src[tile * 512 + k];
+      __syncthreads();
+      for (int j0 = 0; j0 < 256; j0 += 32) {
+        float rx = 0, ry = 0, rz = 0;
+#pragma unroll UNROLL
+        for (int jj = 0; jj < 32; ++jj) {
+          const float4 p = sb[2 * (j0 + jj)], q = sb[2 * (j0 + jj) + 1];
+          float ax = 0, ay = 0, az = 0;
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            pair_sym<float, true, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], z2i[t], nz4i[t], p.x, p.y, p.z, p.w,
+                                        q.x, q.y, q.z, -q.w, ux[t], uy[t], uz[t], ax, ay, az);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            ay += __shfl_xor_sync(0xffffffffu, ay, o);
+            az += __shfl_xor_sync(0xffffffffu, az, o);
+          }
+          if (lane == jj) { rx = ax; ry = ay; rz = az; }
+        }
+        const int jg = tile * 256 + j0 + lane;
+        atomicAdd(raw + 3 * jg, rx);
+        atomicAdd(raw + 3 * jg + 1, ry);
+        atomicAdd(raw + 3 * jg + 2, rz);
+      }
+    }
+  for (int t = 0; t < T; ++t) {
+    int i = (blockIdx.x * NT + threadIdx.x) * T + t;
+    out[3 * i] = ux[t]; out[3 * i + 1] = uy[t]; out[3 * i + 2] = uz[t];
+  }
+}
+
 static std::vector<float> g_ref;
 template <typename F>
 static void run(const char* name, int T, int NT, int ctas_per_sm, int reps, float* out, F launch) {
@@ -198,6 +247,17 @@ int main() {
   run("v2 const far unroll4", 4, 256, 3, reps, dout, [&](int g, int r) { k_const<4, 256, false, 4, 1><<<g, 256>>>(dtgt, dout, r, C); });
   run("v2 const far unroll4 T2", 2, 256, 3, reps, dout, [&](int g, int r) { k_const<2, 256, false, 4, 1><<<g, 256>>>(dtgt, dout, r, C); });
   run("v2 smem NEAR unroll4", 4, 256, 2, reps, dout, [&](int g, int r) { k_smem<4, 256, true, 4, 1><<<g, 256>>>(dsrc, dtgt, dout, r, C); });
+  float* draw; cudaMalloc(&draw, 3 * NSRC * sizeof(float)); cudaMemset(draw, 0, 3 * NSRC * sizeof(float));
+#define SYM(T, NT, OCC, U) run("SYM far unroll" #U " (cyc per UNORDERED pair)", T, NT, OCC, reps, dout, [&](int g, int r) { k_sym<T, NT, false, U><<<g, NT>>>(dsrc, dsrc, dout, draw, r, C); })
+  SYM(4, 256, 2, 2);
+  SYM(4, 256, 1, 2);
+  SYM(2, 256, 2, 2);
+  SYM(2, 256, 3, 2);
+  SYM(2, 256, 3, 4);
+  SYM(2, 128, 4, 2);
+  SYM(1, 256, 3, 4);
+  SYM(4, 128, 3, 2);
+  SYM(4, 128, 4, 1);
   run("smem NEAR unroll4", 4, 256, 2, reps, dout, [&](int g, int r) { k_smem<4, 256, true, 4><<<g, 256>>>(dsrc, dtgt, dout, r, C); });
   run("const NEAR unroll4", 4, 256, 2, reps, dout, [&](int g, int r) { k_const<4, 256, true, 4><<<g, 256>>>(dtgt, dout, r, C); });
   return 0;
