@@ -9,12 +9,13 @@ of shell_N_162 above a wall = 162 000 blobs; one STEP = one application of the s
 operator [M lam - K U ; K^T lam], i.e. one wall-corrected RPY mobility product B M B lam over
 N^2 = 2.6244e10 ordered blob pairs plus the K / K^T products.  Metric: ordered blob-pair
 interactions per second (whole job).  Strong scaling: bodies are partitioned over the ranks,
-lambda is all-gathered over NCCL each step.
+lambda is all-gathered over NCCL each step, the pair work is split in equal shares and the
+partial products are all-reduced.
 
 `value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
 `e2e`     : the same step through the host-buffer C ABI (rbl_apply_saddle at N=1; pinned
             host -> device -> sharded step -> host at N>1), copies inside the timed region.
-`roofline`: the matvec kernel alone (events recorded around every launch inside the timed
+`roofline`: the product kernel alone (events recorded around every launch inside the timed
             region) against the FMA-pipe peak measured live by a microbenchmark.  The bound
             is FP32 (FP64) CUDA-core issue, not HBM and not tensor cores.
 `cpu_baseline` / --impl reference: the reference ALGORITHM (dense 3N x 3N assembly + GEMV,
@@ -233,11 +234,13 @@ def run_ours(args):
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
             host_out = ho.numpy().copy()
         dev_out = out_local.cpu().numpy()
-        if not np.array_equal(dev_out, host_out):
-            dd = np.abs(dev_out.astype(np.float64) - host_out.astype(np.float64))
-            raise AssertionError(f"host-buffer and device-resident paths disagree ({precision}): {int((dd > 0).sum())} of "
-                                 f"{dd.size} entries, max |diff| {dd.max():.3e} at {int(dd.argmax())} (3N = {3 * (hi - lo) * n_blb}); "
-                                 f"dev {dev_out[int(dd.argmax())]!r} host {host_out[int(dd.argmax())]!r}")
+        # the symmetric kernel accumulates with floating-point atomics: the two paths agree to
+        # rounding, not bit for bit
+        dd = np.abs(dev_out.astype(np.float64) - host_out.astype(np.float64))
+        agree = float(np.linalg.norm(dd) / np.linalg.norm(host_out.astype(np.float64)))
+        if not agree < (2e-6 if precision == "single" else 1e-13):
+            raise AssertionError(f"host-buffer and device-resident paths disagree ({precision}): relative L2 {agree:.3e}, "
+                                 f"max |diff| {dd.max():.3e} at {int(dd.argmax())}")
         ctx.call("rbl_sync")
 
         traffic = None
@@ -252,12 +255,16 @@ def run_ours(args):
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(nbytes) * world, "d2h_bytes_per_step": int(nbytes) * world},
             "roofline": {"bound": "fp32_cuda_core" if precision == "single" else "fp64_cuda_core",
-                         "kernel": "rbl::rpy_matvec_kernel", "achieved": alg_tflops, "peak": peak,
+                         "kernel": "rbl::rpy_matvec_sym_kernel", "achieved": alg_tflops, "peak": peak,
                          "unit": "TFLOP/s", "frac": alg_tflops / peak, "traffic": traffic,
                          "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); "
                                          "algorithmic bytes = packed records, 162000 x 32 B (fp32) / 64 B (fp64)",
                          "kernel_ms": kern_ms, "kernel_launches_timed": int(kern_n),
                          "algorithmic_flops_per_pair": FLOPS_PER_PAIR[wall],
+                         "convention": "SURVEY.md 8d: N^2 ordered pairs x 127 flop (35 free space) / kernel time. The "
+                                       "kernel evaluates each UNORDERED pair once (like the reference's i<=j loop) and "
+                                       "applies the block in both directions, so it executes ~28% fewer instructions "
+                                       "than the convention assumes; issue-slot utilisation is in profiles/",
                          "peak_source": "FMA-chain microbenchmark run live on this GPU (rbl_fma_peak); nominal "
                                         + ("74.4" if precision == "single" else "37.2") + " TFLOP/s at 148 SM x 1.965 GHz"},
             "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()),
@@ -280,7 +287,8 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {nb} spheres of shell_N_{n_blb} "
                                    f"{'above a wall' if wall else 'in free space'} = {n_all} blobs; step = apply_saddle "
                                    f"(wall-corrected RPY matvec + K + K^T)",
-                       "pairs_per_step": pairs, "parallelism": f"body-range shards x{world}, NCCL all-gather of lambda",
+                       "pairs_per_step": pairs, "parallelism": f"x{world}: bodies in contiguous ranges; NCCL all-gather of lambda, equal shares of the "
+                                      f"unordered-pair tile triangle per rank, all-reduce of the partial products",
                        "l2": "256 MiB memset between steps inside the timed region (inputs < L2)",
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],

@@ -735,8 +735,8 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
   A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
 }
 
-#define RBL_F32_SYM_VARIANTS(X) X(4, 256) X(8, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
-#define RBL_F64_SYM_VARIANTS(X) X(2, 256) X(2, 128) X(4, 128) X(1, 256)
+#define RBL_F32_SYM_VARIANTS(X) X(8, 128) X(4, 256) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F64_SYM_VARIANTS(X) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
 
 template <>
 int matvec_sym_num_variants<float>() { return 6; }
