@@ -234,7 +234,8 @@ template <bool WALL, bool NEAR, int T>
 __device__ __forceinline__ void tile_compute(const float* __restrict__ sb,
                                              const PairConsts<float>& C, const float (&xi)[T],
                                              const float (&yi)[T], const float (&zi)[T],
-                                             float (&ux)[T], float (&uy)[T], float (&uz)[T]) {
+                                             float (&ux)[T], float (&uy)[T], float (&uz)[T],
+                                             int jb = 0, int je = kSrcTile) {
   const float4* __restrict__ s4 = reinterpret_cast<const float4*>(sb);
   // two-level summation: a fresh accumulator per 256-source tile, added to the running sum
   // once per tile.  Keeps the fp32 rounding error at ~sqrt(256)+sqrt(N/256) ulps instead of
@@ -243,7 +244,7 @@ __device__ __forceinline__ void tile_compute(const float* __restrict__ sb,
 #pragma unroll
   for (int t = 0; t < T; ++t) lx[t] = ly[t] = lz[t] = 0.0f;
 #pragma unroll 2
-  for (int j = 0; j < kSrcTile; ++j) {
+  for (int j = jb; j < je; ++j) {
     const float4 p = s4[2 * j];      // x y z fx
     const float4 q = s4[2 * j + 1];  // fy fz 2z 4z^2
 #pragma unroll
@@ -264,10 +265,11 @@ __device__ __forceinline__ void tile_compute(const double* __restrict__ sb,
                                              const PairConsts<double>& C,
                                              const double (&xi)[T], const double (&yi)[T],
                                              const double (&zi)[T], double (&ux)[T],
-                                             double (&uy)[T], double (&uz)[T]) {
+                                             double (&uy)[T], double (&uz)[T], int jb = 0,
+                                             int je = kSrcTile) {
   const double2* __restrict__ s2 = reinterpret_cast<const double2*>(sb);
 #pragma unroll 2
-  for (int j = 0; j < kSrcTile; ++j) {
+  for (int j = jb; j < je; ++j) {
     const double2 p0 = s2[4 * j];      // x y
     const double2 p1 = s2[4 * j + 1];  // z fx
     const double2 p2 = s2[4 * j + 2];  // fy fz
@@ -557,15 +559,15 @@ cudaError_t matvec_launch<double>(int variant, const MatvecArgs<double>& a, cuda
 // symmetric kernel: one evaluation per unordered pair
 // ----------------------------------------------------------------------------------
 __device__ __forceinline__ void load_full_rec(const float* p, float& x, float& y, float& z, float& fx,
-                                              float& fy, float& fz, float& z2, float& nz4) {
+                                              float& fy, float& fz, float& nz4) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  x = a.x; y = a.y; z = a.z; fx = a.w; fy = b.x; fz = b.y; z2 = b.z; nz4 = -b.w;
+  x = a.x; y = a.y; z = a.z; fx = a.w; fy = b.x; fz = b.y; nz4 = -b.w;
 }
 __device__ __forceinline__ void load_full_rec(const double* p, double& x, double& y, double& z, double& fx,
-                                              double& fy, double& fz, double& z2, double& nz4) {
+                                              double& fy, double& fz, double& nz4) {
   const double2* q = reinterpret_cast<const double2*>(p);
   const double2 a = q[0], b = q[1], c = q[2], d = q[3];
-  x = a.x; y = a.y; z = b.x; fx = b.y; fy = c.x; fz = c.y; z2 = d.x; nz4 = -d.y;
+  x = a.x; y = a.y; z = b.x; fx = b.y; fy = c.x; fz = c.y; nz4 = -d.y;
 }
 
 template <typename real>
@@ -575,34 +577,56 @@ __device__ __forceinline__ real warp_sum(real v) {
   return v;
 }
 
-// one staged source tile against the thread's T targets, both directions.  Every 32 sources
-// each lane ends up holding the warp-total reaction of source (j0 + lane) and adds it to the
-// global accumulators (coalesced RED.ADD).
+// one staged source tile against the thread's T targets, both directions.  Sources are taken
+// two at a time (jj and jj + 16): the first butterfly stage exchanges the two sources'
+// partial sums between the half-warps (transposed reduction), the remaining four stages run
+// on 3 values instead of 6, and the totals land in lane jj (first source) and lane jj + 16
+// (second source).  After 32 sources every lane holds the warp-total reaction of source
+// (j0 + lane) and adds it to the global accumulators (coalesced RED.ADD).
 template <typename real, bool WALL, bool NEAR, int T>
 __device__ __forceinline__ void tile_compute_sym(const real* __restrict__ sb, const PairConsts<real>& C,
                                                  const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
                                                  const real (&fxi)[T], const real (&fyi)[T], const real (&fzi)[T],
-                                                 const real (&z2i)[T], const real (&nz4i)[T], real (&ux)[T],
-                                                 real (&uy)[T], real (&uz)[T], real* __restrict__ raw_tile) {
+                                                 const real (&nz4i)[T], real (&ux)[T], real (&uy)[T],
+                                                 real (&uz)[T], real* __restrict__ raw_tile, int jb, int je) {
+  constexpr bool kTwoLevel = sizeof(real) == 4;  // fp32: per-tile accumulators (see tile_compute)
   const int lane = threadIdx.x & 31;
-  real lx[T], ly[T], lz[T];  // per-tile accumulators (two-level summation, see tile_compute)
+  const bool upper = (lane & 16) != 0;
+  real lx[T], ly[T], lz[T];
 #pragma unroll
-  for (int t = 0; t < T; ++t) lx[t] = ly[t] = lz[t] = (real)0;
-  for (int j0 = 0; j0 < kSrcTile; j0 += 32) {
+  for (int t = 0; t < T; ++t) {
+    lx[t] = kTwoLevel ? (real)0 : ux[t];
+    ly[t] = kTwoLevel ? (real)0 : uy[t];
+    lz[t] = kTwoLevel ? (real)0 : uz[t];
+  }
+  for (int j0 = jb; j0 < je; j0 += 32) {
     real rx = 0, ry = 0, rz = 0;
-#pragma unroll 2
-    for (int jj = 0; jj < 32; ++jj) {
-      real xj, yj, zj, fxj, fyj, fzj, z2j, nz4j;
-      load_full_rec(sb + (size_t)(j0 + jj) * kRecReals, xj, yj, zj, fxj, fyj, fzj, z2j, nz4j);
-      real ax = 0, ay = 0, az = 0;
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      real xa, ya, za, fxa, fya, fza, nz4a, xb, yb, zb, fxb, fyb, fzb, nz4b;
+      load_full_rec(sb + (size_t)(j0 + jj) * kRecReals, xa, ya, za, fxa, fya, fza, nz4a);
+      load_full_rec(sb + (size_t)(j0 + jj + 16) * kRecReals, xb, yb, zb, fxb, fyb, fzb, nz4b);
+      real ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
 #pragma unroll
-      for (int t = 0; t < T; ++t)
-        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], z2i[t], nz4i[t], xj, yj, zj,
-                                   fxj, fyj, fzj, z2j, nz4j, lx[t], ly[t], lz[t], ax, ay, az);
-      ax = warp_sum(ax);
-      ay = warp_sum(ay);
-      az = warp_sum(az);
-      if (lane == jj) { rx = ax; ry = ay; rz = az; }
+      for (int t = 0; t < T; ++t) {
+        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xa, ya, za, fxa, fya,
+                                   fza, nz4a, lx[t], ly[t], lz[t], ax, ay, az);
+        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xb, yb, zb, fxb, fyb,
+                                   fzb, nz4b, lx[t], ly[t], lz[t], bx, by, bz);
+      }
+      // stage 1: lower half-warp keeps source a, upper keeps source b
+      real kx = upper ? bx : ax, ky = upper ? by : ay, kz = upper ? bz : az;
+      const real sx = upper ? ax : bx, sy = upper ? ay : by, sz = upper ? az : bz;
+      kx += __shfl_xor_sync(0xffffffffu, sx, 16);
+      ky += __shfl_xor_sync(0xffffffffu, sy, 16);
+      kz += __shfl_xor_sync(0xffffffffu, sz, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        kx += __shfl_xor_sync(0xffffffffu, kx, o);
+        ky += __shfl_xor_sync(0xffffffffu, ky, o);
+        kz += __shfl_xor_sync(0xffffffffu, kz, o);
+      }
+      if ((lane & 15) == jj) { rx = kx; ry = ky; rz = kz; }
     }
     real* o = raw_tile + 3 * (size_t)(j0 + lane);
     atomicAdd(o, rx);
@@ -611,11 +635,13 @@ __device__ __forceinline__ void tile_compute_sym(const real* __restrict__ sb, co
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    ux[t] += lx[t];
-    uy[t] += ly[t];
-    uz[t] += lz[t];
+    ux[t] = kTwoLevel ? ux[t] + lx[t] : lx[t];
+    uy[t] = kTwoLevel ? uy[t] + ly[t] : ly[t];
+    uz[t] = kTwoLevel ? uz[t] + lz[t] : lz[t];
   }
 }
+
+constexpr int kSymChunks = kSrcTile / 32;  // 32-source chunks per tile unit
 
 // first unit index of row I of the triangle: rows have n_src_tiles - I*diag units
 __device__ __host__ __forceinline__ long long sym_row_offset(long long I, int ns, int diag) {
@@ -631,10 +657,15 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
 
   const int tid = threadIdx.x;
   const int ns = A.plan.n_src_tiles, D = A.plan.diag, ntt = A.plan.n_tgt_tiles;
+  // work is cut at the granularity of 32-source chunks (kSymChunks per tile unit) so that the
+  // shares of different CTAs -- and of different GPUs -- differ by at most one chunk
   const long long span = A.plan.u1 - A.plan.u0;
-  const long long g0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
-  const long long g1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
-  if (g0 >= g1) return;
+  const long long f0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
+  const long long f1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
+  if (f0 >= f1) return;
+  const long long g0 = f0 / kSymChunks, g_last = (f1 - 1) / kSymChunks, g1 = g_last + 1;
+  const int jb_first = (int)(f0 - g0 * kSymChunks) * 32;
+  const int je_last = (int)(f1 - 1 - g_last * kSymChunks + 1) * 32;
 
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
@@ -659,7 +690,7 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     tma_load_1d(sbuf[0], A.rec + (size_t)J * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
   }
 
-  real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], z2i[T], nz4i[T], ux[T], uy[T], uz[T];
+  real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], nz4i[T], ux[T], uy[T], uz[T];
   bool fresh = true;
   const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
 
@@ -668,6 +699,8 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     const int buf = it & 1;
     const uint32_t parity = (uint32_t)(it >> 1) & 1u;
     const bool row_end = (J + 1 == ns);
+    const int jb = (g == g0) ? jb_first : 0;
+    const int je = (g == g_last) ? je_last : kSrcTile;
 
     if (tid == 0 && g + 1 < g1) {
       const int nJ = row_end ? (I + 1) * D : J + 1;
@@ -681,7 +714,7 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
         int li = I * TT + tid + t * NT;
         const bool pad = li >= A.plan.n;
         if (pad) li = A.plan.n - 1;
-        load_full_rec(A.rec + (size_t)li * kRecReals, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], z2i[t], nz4i[t]);
+        load_full_rec(A.rec + (size_t)li * kRecReals, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t]);
         if (pad) fxi[t] = fyi[t] = fzi[t] = (real)0;  // padding lanes exert nothing
         ux[t] = uy[t] = uz[t] = (real)0;
       }
@@ -693,13 +726,13 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
 
     mbar_wait(&mbar[buf], parity);
     if (diagonal) {
-      tile_compute<WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz);
+      tile_compute<WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz, jb, je);
     } else {
       real* raw_tile = A.raw + 3 * (size_t)J * kSrcTile;
       if (far)
-        tile_compute_sym<real, WALL, false, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, z2i, nz4i, ux, uy, uz, raw_tile);
+        tile_compute_sym<real, WALL, false, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
       else
-        tile_compute_sym<real, WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, z2i, nz4i, ux, uy, uz, raw_tile);
+        tile_compute_sym<real, WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
     }
     __syncthreads();
 
@@ -735,13 +768,13 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
   A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
 }
 
-#define RBL_F32_SYM_VARIANTS(X) X(8, 128) X(4, 256) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
-#define RBL_F64_SYM_VARIANTS(X) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F32_SYM_VARIANTS(X) X(8, 128) X(4, 256) X(6, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F64_SYM_VARIANTS(X) X(4, 128) X(2, 256) X(3, 256) X(2, 128) X(1, 256)
 
 template <>
-int matvec_sym_num_variants<float>() { return 6; }
+int matvec_sym_num_variants<float>() { return 7; }
 template <>
-int matvec_sym_num_variants<double>() { return 4; }
+int matvec_sym_num_variants<double>() { return 5; }
 template <>
 MatvecVariant matvec_sym_variant<float>(int idx) {
   static const MatvecVariant v[] = {
@@ -801,8 +834,9 @@ cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts
   plan->diag = plan->tgt_tile / kSrcTile;
   plan->n_tgt_tiles = (n + plan->tgt_tile - 1) / plan->tgt_tile;
   plan->units = sym_row_offset(plan->n_tgt_tiles, plan->n_src_tiles, plan->diag);
-  plan->u0 = plan->units * part / n_parts;
-  plan->u1 = plan->units * (part + 1) / n_parts;
+  const long long fine = plan->units * kSymChunks;  // shares are cut at 32-source granularity
+  plan->u0 = fine * part / n_parts;
+  plan->u1 = fine * (part + 1) / n_parts;
   plan->grid = sm_count * bps;
   return cudaSuccess;
 }

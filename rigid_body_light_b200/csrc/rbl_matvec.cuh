@@ -101,7 +101,7 @@ struct SymPlan {
   int tgt_tile;     // T * threads, a multiple of kSrcTile
   int diag;         // tgt_tile / kSrcTile: source tiles per row that overlap the target tile
   long long units;  // units of the whole triangle
-  long long u0, u1; // this launch's share
+  long long u0, u1; // this launch's share, in 32-source chunks (8 per tile unit)
   int grid;
 };
 

@@ -198,12 +198,14 @@ RBL_HD void pair(const PairConsts<real>& C, real xi, real yi, real zi, real xj, 
 // in (W, E); per direction: the dot products with the force, a3/a4/a5 (which carry the
 // SOURCE height) and the accumulation.  ~92 issue slots per unordered pair instead of
 // 2 x 65 for two ordered evaluations.
-//   fi*, fj* are already multiplied by the blob's wall damping B; z2 = 2z, nzz4 = -4 z^2.
+//   fi*, fj* are already multiplied by the blob's wall damping B; nzz4 = -4 z^2.  (2 z_src, which
+//   the ordered kernel reads from the record, is folded into b2 = 2 - 12 z_tgt Z W here so a thread
+//   need not keep it per target.)
 template <typename real, bool WALL, bool NEAR>
 RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real fxi, real fyi,
-                     real fzi, real z2i, real nzz4i, real xj, real yj, real zj, real fxj,
-                     real fyj, real fzj, real z2j, real nzz4j, real& uxi, real& uyi, real& uzi,
-                     real& uxj, real& uyj, real& uzj) {
+                     real fzi, real nzz4i, real xj, real yj, real zj, real fxj, real fyj,
+                     real fzj, real nzz4j, real& uxi, real& uyi, real& uzi, real& uxj,
+                     real& uyj, real& uzj) {
   const real dx = xi - xj, dy = yi - yj, dz = zi - zj;
   const real q = fma_(dy, dy, fma_(dx, dx, C.tiny));
   const real r2 = fma_(dz, dz, q);
@@ -260,9 +262,9 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     const real cF = fma_(w, a1n, c1);
     // direction i <- j (source height z_j)
     {
-      const real b = fma_(zi * ZW, (real)-6, (real)1);
-      const real a3 = fma_(z2j, b, nZWh3);
-      const real a4 = z2j + cZW2;
+      const real b2 = fma_(zi * ZW, (real)-12, (real)2);
+      const real a3 = fma_(zj, b2, nZWh3);
+      const real a4 = fma_(zj, (real)2, cZW2);
       const real a5n = nzz4j + nS5;
       const real A = wW * fma_(a3, fzj, a2n * gj);
       const real Bz = wW * fma_(a5n, fzj, a4 * gj);
@@ -273,9 +275,9 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     }
     // direction j <- i (source height z_i, in-plane separation -d)
     {
-      const real b = fma_(zj * ZW, (real)-6, (real)1);
-      const real a3 = fma_(z2i, b, nZWh3);
-      const real a4 = z2i + cZW2;
+      const real b2 = fma_(zj * ZW, (real)-12, (real)2);
+      const real a3 = fma_(zi, b2, nZWh3);
+      const real a4 = fma_(zi, (real)2, cZW2);
       const real a5n = nzz4i + nS5;
       const real A = wW * fma_(a3, fzi, a2n * gi);
       const real Bz = wW * fma_(a5n, fzi, a4 * gi);

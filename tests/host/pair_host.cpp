@@ -79,7 +79,7 @@ static void matvec_sym(const real* F, const real* r, int n, double a, double eta
     else      rbl::pair<real, false, true>(C, r[3*i], r[3*i+1], zi, r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], 2*zi, 4*zi*zi, acc[3*i], acc[3*i+1], acc[3*i+2]);
     for (int j = i + 1; j < n; ++j) {
       real zj = r[3 * j + 2];
-#define ARGS r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], 2*zi, -4*zi*zi, r[3*j], r[3*j+1], zj, f[3*j], f[3*j+1], f[3*j+2], 2*zj, -4*zj*zj, acc[3*i], acc[3*i+1], acc[3*i+2], acc[3*j], acc[3*j+1], acc[3*j+2]
+#define ARGS r[3*i], r[3*i+1], zi, f[3*i], f[3*i+1], f[3*i+2], -4*zi*zi, r[3*j], r[3*j+1], zj, f[3*j], f[3*j+1], f[3*j+2], -4*zj*zj, acc[3*i], acc[3*i+1], acc[3*i+2], acc[3*j], acc[3*j+1], acc[3*j+2]
       if (wall) { if (near) rbl::pair_sym<real, true, true>(C, ARGS); else rbl::pair_sym<real, true, false>(C, ARGS); }
       else      { if (near) rbl::pair_sym<real, false, true>(C, ARGS); else rbl::pair_sym<real, false, false>(C, ARGS); }
 #undef ARGS
