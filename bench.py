@@ -366,7 +366,8 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     precision = "single" if args.dtype in ("both", "single") else "double"
     nb, n_blb, wall = WORKLOADS[args.workload]
-    cpu = cpu_reference_sample(args.workload, precision, budget_s=100.0, steps=args.steps, warmup=args.warmup)
+    budget = float(os.environ.get("RBL_BENCH_CPU_BUDGET_S", "100"))  # whole-run CPU budget (tests shrink it)
+    cpu = cpu_reference_sample(args.workload, precision, budget_s=budget, steps=args.steps, warmup=args.warmup)
     n_all = nb * n_blb
     line = {
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,

@@ -368,7 +368,7 @@ struct Ctx final : rbl_ctx {
 
   int pick_sym_variant(int n) const {
     if (sym_variant >= 0) return sym_variant;
-    return n >= 16384 ? 0 : rbl::matvec_sym_num_variants<real>() - 1;
+    return rbl::matvec_sym_default_variant<real>(wall, n);
   }
 
   // symmetric kernel: share `part` of `n_parts` of the unordered-pair work; out = partial product

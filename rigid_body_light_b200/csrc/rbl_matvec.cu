@@ -768,8 +768,8 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
   A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
 }
 
-#define RBL_F32_SYM_VARIANTS(X) X(8, 128) X(4, 256) X(6, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
-#define RBL_F64_SYM_VARIANTS(X) X(4, 128) X(2, 256) X(3, 256) X(2, 128) X(1, 256)
+#define RBL_F32_SYM_VARIANTS(X) X(4, 256) X(6, 128) X(8, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F64_SYM_VARIANTS(X) X(3, 256) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
 
 template <>
 int matvec_sym_num_variants<float>() { return 7; }
@@ -793,6 +793,14 @@ MatvecVariant matvec_sym_variant<double>(int idx) {
   };
   return v[idx];
 }
+
+// measured on B200 at 162 000 blobs (profiles/): wall fp32 (4,256), fp64 (3,256); free space
+// fp32 (6,128), fp64 (4,128); small problems take the smallest target tile so that the unit
+// triangle still covers the SMs
+template <>
+int matvec_sym_default_variant<float>(bool wall, int n) { return n < 16384 ? 6 : (wall ? 0 : 1); }
+template <>
+int matvec_sym_default_variant<double>(bool wall, int n) { return n < 16384 ? 4 : (wall ? 0 : 1); }
 
 template <typename real, bool WALL, int T, int NT>
 static cudaError_t sym_occupancy_of(int* bps) {

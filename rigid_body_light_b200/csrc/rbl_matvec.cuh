@@ -122,6 +122,8 @@ int matvec_sym_num_variants();
 template <typename real>
 MatvecVariant matvec_sym_variant(int idx);
 template <typename real>
+int matvec_sym_default_variant(bool wall, int n);
+template <typename real>
 cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts, int sm_count,
                             SymPlan* plan);
 // memset(raw) + symmetric kernel + scale kernel (out = raw * B_i / (8 pi eta))

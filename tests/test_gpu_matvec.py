@@ -297,3 +297,38 @@ def test_blob_below_wall_raises(precision):
     # the context stays usable afterwards
     cb.set_config(np.array([[0.0, 0.0, 2.0]]), np.array([[1.0, 0, 0, 0]]))
     assert np.linalg.norm(cb.apply_M(vec[:36], cb.get_blob_positions())) > 0
+
+
+def test_config4_scale_free_space_sampled_rows(orc):
+    """BASELINE.json configs[3] geometry: 1000 spheres of shell_N_2562 = 2 562 000 blobs in free
+    space (6.6e12 ordered pairs), float: 64 sampled rows against the oracle + symmetry of the
+    whole product.  Exercises the 64-bit index paths of the tile triangle at full size."""
+    from rigid_body_light_b200._lib import Context
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    import torch
+
+    s = sphere_suspension(1000, 2562, False)
+    ref = s["cfg"] - s["cfg"].mean(axis=0)
+    ctx = Context("single")
+    ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
+    ctx.set_flags(0, 0)
+    ctx.set_config(s["X"], s["Q"])
+    n = 2562000
+    r = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    ctx.call("rbl_dev_blob_positions", r.data_ptr())
+    rng = np.random.default_rng(2)
+    F1 = torch.from_numpy(rng.standard_normal(3 * n).astype(np.float32)).cuda()
+    F2 = torch.from_numpy(rng.standard_normal(3 * n).astype(np.float32)).cuda()
+    u1, u2 = torch.empty_like(F1), torch.empty_like(F1)
+    ctx.call("rbl_dev_apply_M", F1.data_ptr(), r.data_ptr(), n, 0, n, u1.data_ptr())
+    ctx.call("rbl_dev_apply_M", F2.data_ptr(), r.data_ptr(), n, 0, n, u2.data_ptr())
+    ctx.call("rbl_sync")
+    rows = np.random.default_rng(5).choice(n, 64, replace=False)
+    rows[:2] = [0, n - 1]
+    want = _oracle_for(orc, F1.cpu().numpy(), r.cpu().numpy(), s["a"], 1.0, False, "single", rows=rows)
+    got = u1.cpu().numpy().reshape(-1, 3)[rows].reshape(-1)
+    assert rel_err(got, want) < TOL["single"]
+    sym = abs(float(torch.dot(F2.double(), u1.double()) - torch.dot(F1.double(), u2.double())))
+    assert sym / float(F2.double().norm() * u1.double().norm()) < 2e-6
+    ctx.close()
