@@ -119,7 +119,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from rigid_body_light_b200._lib import Context
-    from rigid_body_light_b200.sharding import CudaShard, ShardedSaddle, body_ranges, slice_system
+    from rigid_body_light_b200.sharding import CudaShard, ShardedSaddle, body_ranges, comm_breakdown, slice_system
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,11 +186,16 @@ def run_ours(args):
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        op.timing = [] if world > 1 else None
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
+        comm = comm_breakdown(op.timing) if world > 1 else None
+        op.timing = None
+        if comm is not None:
+            comm = [max_over_ranks(c) for c in comm]
         clocks = sampler.stop() if rank == 0 else None
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = ctx.launch_count() - launches0
@@ -268,6 +273,10 @@ def run_ours(args):
                          "peak_source": "FMA-chain microbenchmark run live on this GPU (rbl_fma_peak); nominal "
                                         + ("74.4" if precision == "single" else "37.2") + " TFLOP/s at 148 SM x 1.965 GHz"},
             "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()),
+            "comm_ms_per_step": None if comm is None else {"allgather_lambda": comm[0], "product_incl_pack": comm[1],
+                                                            "allreduce_partials": comm[2],
+                                                            "note": "CUDA events per step, max over ranks; a rank that "
+                                                                    "finishes its share early waits inside the collective"},
         }
         ctx.close()
         del op, shard, x_local, out_local
@@ -292,11 +301,11 @@ def run_ours(args):
                        "l2": "256 MiB memset between steps inside the timed region (inputs < L2)",
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
-            "clocks": head["clocks"], "cpu_baseline": cpu,
+            "clocks": head["clocks"], "cpu_baseline": cpu, "comm_ms_per_step": head["comm_ms_per_step"],
         }
         if "double" in results and head_p == "single":
             d = results["double"]
-            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks")}
+            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

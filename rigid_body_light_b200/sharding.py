@@ -57,6 +57,7 @@ class ShardedSaddle:
         self.r_all = None
         self._gather_buf = None
         self._pad = None
+        self.timing = None  # set to [] to record (allgather, product, allreduce) CUDA-event triples per apply
 
     def _allgather(self, local, out_all):
         """out_all (3*n_all) <- concatenation of every rank's 3*n_local slice."""
@@ -90,17 +91,38 @@ class ShardedSaddle:
         if self.r_all is None:
             self.refresh_positions()
         n3 = 3 * self.n_local
+        ev = None
+        if self.timing is not None and self.world > 1:
+            ev = [self.torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         self._allgather(x_local[:n3], self.lam_all)
+        if ev:
+            ev[1].record()
         if self.world == 1:
             self.backend.saddle_shard(self.lam_all, self.r_all, self.n_all, self.t0, x_local[n3:], out_local)
             return out_local
         if getattr(self, "_mbuf", None) is None:
             self._mbuf = self.torch.empty_like(self.lam_all)
         self.backend.apply_M_part(self.lam_all, self.r_all, self.n_all, self.rank, self.world, self._mbuf)
+        if ev:
+            ev[2].record()
         self.dist.all_reduce(self._mbuf)  # sum of the partial products
+        if ev:
+            ev[3].record()
+            self.timing.append(ev)
         lo = 3 * self.t0
         self.backend.saddle_finish(self._mbuf[lo:lo + n3], x_local[:n3], x_local[n3:], out_local)
         return out_local
+
+
+def comm_breakdown(timing):
+    """(allgather_ms, product_ms, allreduce_ms) averaged over the recorded applies."""
+    if not timing:
+        return None
+    ag = sum(e[0].elapsed_time(e[1]) for e in timing) / len(timing)
+    pr = sum(e[1].elapsed_time(e[2]) for e in timing) / len(timing)
+    ar = sum(e[2].elapsed_time(e[3]) for e in timing) / len(timing)
+    return ag, pr, ar
 
 
 class CudaShard:
