@@ -281,6 +281,11 @@ def run_ours(args):
         ctx.close()
         del op, shard, x_local, out_local
 
+    bd = None
+    if args.bd_steps > 0:
+        bd = bd_step_leg(args, rank, world, dist if world > 1 else None, local_rank,
+                         ["single", "double"] if args.dtype == "both" else [args.dtype])
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args.workload, "single" if args.dtype != "double" else "double", budget_s=12.0)
@@ -302,6 +307,7 @@ def run_ours(args):
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "clocks": head["clocks"], "cpu_baseline": cpu, "comm_ms_per_step": head["comm_ms_per_step"],
+            "bd_step": bd,
         }
         if "double" in results and head_p == "single":
             d = results["double"]
@@ -311,6 +317,61 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
 
+
+
+def bd_step_leg(args, rank, world, dist, local_rank, precisions):
+    """BASELINE.json's second metric: wall time of one full fluctuating rigid BD step (2 Lanczos
+    M^{1/2}W, RFD drift, midpoint K/PC, preconditioned GMRES, evolve) through the host-buffer C ABI
+    (rbl_bd_step: host arrays in, rigid velocities out), on configs[2]'s suspension partitioned
+    over the ranks.  One untimed warm-up step (allocations, module load), then --bd-steps timed
+    steps, max over ranks; every step draws fresh noise and moves the bodies."""
+    import ctypes
+
+    import torch
+
+    from rigid_body_light_b200.sharding import PartitionedRigidBody
+
+    s = build_suspension(args.bd_workload)
+    nb, n_blb, wall = s["n_bodies"], s["n_blb"], s["wall"]
+    n3 = 3 * nb * n_blb
+    F_ext = np.tile(np.array([0, 0, -1.0, 0, 0, 0]), nb)
+    out = {"workload": f"{args.bd_workload}: {nb} spheres of shell_N_{n_blb} {'above a wall' if wall else 'in free space'} "
+                       f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC",
+           "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps}
+    for precision in precisions:
+        tol, ltol = (1e-4, 1e-4) if precision == "single" else (1e-8, 1e-6)
+        pb = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=wall, block_PC=True,
+                                  precision=precision, rank=rank, world=world, dist=dist, device=local_rank)
+        rng = np.random.default_rng(3)
+        times, iters, lz, rel = [], [], [], []
+        prod0 = 0
+        for k in range(1 + args.bd_steps):
+            noise = tuple(pb.slice_blobs(rng.standard_normal(n3)) for _ in range(3))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            if k == 1:
+                prod0 = int(pb.ctx.L.rbl_product_count(pb.ctx.h))
+            t0 = time.perf_counter()
+            U, it, rr = pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60, max_iter=200,
+                                   lanczos_tol=ltol, lanczos_max_iter=80)
+            dt = time.perf_counter() - t0
+            if k == 0:
+                continue
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            l1, l2 = ctypes.c_int(), ctypes.c_int()
+            pb.ctx.L.rbl_bd_stats(pb.ctx.h, ctypes.byref(l1), ctypes.byref(l2))
+            times.append(dt); iters.append(int(it)); lz.append([l1.value, l2.value]); rel.append(float(rr))
+        products = (int(pb.ctx.L.rbl_product_count(pb.ctx.h)) - prod0) / max(1, args.bd_steps)
+        X, _ = pb.get_config()
+        out[precision] = {"seconds_per_step": float(np.mean(times)), "gmres_iterations": iters, "lanczos_iterations": lz,
+                          "gmres_tol": tol, "lanczos_tol": ltol, "relres": rel, "mobility_products_per_step": products,
+                          "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U))}
+        pb.close()
+    return out
 
 # --------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port), bounded sample
@@ -403,6 +464,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="both", choices=["both", "single", "double"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bd-steps", type=int, default=1, help="timed full BD steps after the matvec bench (0 = skip)")
+    ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

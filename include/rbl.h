@@ -148,6 +148,26 @@ int rbl_dev_apply_M_part(rbl_ctx* ctx, const void* dF, const void* dr, int n_blo
 int rbl_dev_saddle_finish(rbl_ctx* ctx, const void* dMlambda_local, const void* dlambda_local,
                           const void* dU_local, void* dout_local);
 int rbl_sync(rbl_ctx* ctx);
+
+/* ---- partitioned suspensions: one context per GPU, NCCL inside the library ---------------
+ * The reference is single process / single thread; this is the multi-GPU path of SURVEY.md
+ * section 8e.  Each rank creates a context, sets ITS bodies (a contiguous range of the global
+ * body list) with rbl_set_config, then all ranks call rbl_comm_init together.  From then on the
+ * SAME entry points work on rank-local slices -- vectors are [lambda_local (3 N_local) ;
+ * U_local (6 n_bod_local)] -- and are collective: rbl_apply_saddle, rbl_dev_apply_saddle,
+ * rbl_gmres, rbl_lanczos_sqrt, rbl_bd_step.  Per mobility product: ncclAllGather of the forces
+ * (positions once per configuration), this rank's share of the unordered-pair work over all
+ * blobs, ncclReduceScatter of the partial products; dot products of the Krylov drivers are
+ * batched and all-reduced; status codes are max-reduced so every rank returns the same one.
+ * K, K^T, the preconditioner and the integrator are rank-local (whole bodies per rank).
+ * rbl_apply_M / rbl_dev_apply_M stay local, non-collective pure functions of their arguments.
+ * NCCL is bound with dlopen("libnccl.so.2") at rbl_comm_init time; a single-GPU host never needs it. */
+/* rank 0: 128 bytes of ncclUniqueId for the host to broadcast (any transport) */
+int rbl_comm_unique_id(void* out128);
+/* blobs_per_rank: `world` entries (blobs, not bodies); entry `rank` must equal this context's N */
+int rbl_comm_init(rbl_ctx* ctx, const void* uid128, int rank, int world, const int* blobs_per_rank);
+int rbl_comm_world(const rbl_ctx* ctx); /* 1 without a communicator */
+int rbl_comm_rank(const rbl_ctx* ctx);
 /* the context's cudaStream_t (as void*); set_stream lets a host share its own stream */
 void* rbl_stream(rbl_ctx* ctx);
 int rbl_set_stream(rbl_ctx* ctx, void* cuda_stream);
@@ -179,6 +199,10 @@ int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, i
 int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t rbl_launch_count(const rbl_ctx* ctx);
+/* mobility products (whole, or one rank's share) launched since creation */
+int64_t rbl_product_count(const rbl_ctx* ctx);
+/* Lanczos iterations of the two M^{1/2}W solves of the last rbl_bd_step */
+int rbl_bd_stats(const rbl_ctx* ctx, int* lanczos_iters_1, int* lanczos_iters_2);
 /* average duration (ms, CUDA events around the kernel alone) of the matvec kernel over
  * the launches since the last reset; enable/disable with rbl_profile_matvec */
 int rbl_profile_matvec(rbl_ctx* ctx, int enable);

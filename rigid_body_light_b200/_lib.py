@@ -60,6 +60,10 @@ SYMBOLS = {
     "rbl_dev_apply_M_part": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rbl_dev_saddle_finish": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rbl_sync": (_i, [_vp]),
+    "rbl_comm_unique_id": (_i, [_vp]),
+    "rbl_comm_init": (_i, [_vp, _vp, _i, _i, _pi]),
+    "rbl_comm_world": (_i, [_vp]),
+    "rbl_comm_rank": (_i, [_vp]),
     "rbl_stream": (_vp, [_vp]),
     "rbl_set_stream": (_i, [_vp, _vp]),
     "rbl_dev_alloc": (_i, [_vp, _sz, _pvp]),
@@ -79,6 +83,8 @@ SYMBOLS = {
     "rbl_sym_variant_info": (_i, [_vp, _i, _pi, _pi]),
     "rbl_set_sym_variant": (_i, [_vp, _i]),
     "rbl_launch_count": (_i64, [_vp]),
+    "rbl_product_count": (_i64, [_vp]),
+    "rbl_bd_stats": (_i, [_vp, _pi, _pi]),
     "rbl_profile_matvec": (_i, [_vp, _i]),
     "rbl_matvec_profile": (_i, [_vp, _pd, _pi64, _i]),
     "rbl_fma_peak": (_i, [_vp, _i, _pd]),

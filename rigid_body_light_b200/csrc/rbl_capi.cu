@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/rbl.h"
+#include "rbl_comm.h"
 #include "rbl_krylov.cuh"
 #include "rbl_matvec.cuh"
 #include "rbl_rigid.cuh"
@@ -54,7 +55,7 @@ struct rbl_ctx {
   int device = 0;
   int sm_count = 0;
   std::string err;
-  virtual ~rbl_ctx() {}
+  virtual ~rbl_ctx() { delete comm; }
   int fail(int code, const std::string& msg) {
     err = msg;
     return code;
@@ -93,12 +94,16 @@ struct rbl_ctx {
   virtual int sym_variant_info(int idx, int* T, int* threads) const = 0;
   virtual int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) = 0;
   virtual int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) = 0;
+  virtual int comm_init(const void* uid128, int rank, int world, const int* blobs_per_rank) = 0;
 
   // shared plumbing
+  rbl::Comm* comm = nullptr;  // non-null: this context holds one rank's bodies of a partitioned suspension
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   int64_t launches = 0;
+  int64_t products = 0;        // mobility products (full or one rank's share) since creation
+  int last_lanczos[2] = {0, 0};  // Lanczos iterations of the last rbl_bd_step
   int variant = -1;
   int sym_variant = -1;
   int mode = 0;  // 0: symmetric kernel when targets == sources; 1: ordered kernel always
@@ -148,6 +153,9 @@ struct Ctx final : rbl_ctx {
   DevBuf d_V, d_w, d_z, d_tmp, d_partial, d_coef, d_dots;
   // BD step
   DevBuf d_rhs, d_sol, d_mh1, d_mh2, d_rfd, d_noise, d_uom, d_Xs, d_Qs, d_Xp, d_Qp, d_rp, d_t1, d_t2;
+  // partitioned mode (comm != nullptr): all-gathered positions / forces, partial product, agreed status
+  DevBuf d_r_all, d_lam_all, d_mbuf, d_status;
+  bool r_all_valid = false;
 
   enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, N_FLAGS = 4 };
 
@@ -268,6 +276,7 @@ struct Ctx final : rbl_ctx {
     LAUNCH(1, rbl::ktk_inv_blocks<real>(d_Q.as<real>(), d_ref.as<real>(), n_bod, n_blb, d_S.as<real>(),
                                         d_flags.as<int>() + FLAG_SINGULAR, stream));
     r_valid = true;
+    r_all_valid = false;
     return RBL_OK;
   }
   int need_K() {
@@ -402,6 +411,7 @@ struct Ctx final : rbl_ctx {
       prof_events.emplace_back(e0, e1);
     }
     LAUNCH(2, rbl::matvec_sym_launch<real>(v, A, stream, e0, e1));
+    ++products;
     return RBL_OK;
   }
 
@@ -446,6 +456,87 @@ struct Ctx final : rbl_ctx {
       prof_events.emplace_back(e0, e1);
     }
     LAUNCH(2, rbl::matvec_launch<real>(v, A, stream, e0, e1));
+    ++products;
+    return RBL_OK;
+  }
+
+
+  // ---- partitioned mode ------------------------------------------------
+  // The context holds this rank's bodies; vectors are rank-local slices [lambda_local ; U_local].
+  int comm_init(const void* uid128, int rank, int world, const int* blobs_per_rank) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "rbl_comm_init: set this rank's configuration first");
+    if (!uid128 || !blobs_per_rank || world < 1 || rank < 0 || rank >= world)
+      return fail(RBL_ERR_INVALID, "rbl_comm_init: bad rank / world / arguments");
+    if ((long long)blobs_per_rank[rank] != N())
+      return fail(RBL_ERR_INVALID, "rbl_comm_init: blobs_per_rank[rank] differs from this context's blob count");
+    long long tot = 0;
+    for (int r = 0; r < world; ++r) tot += blobs_per_rank[r];
+    if (tot > 0x7fffffffLL) return fail(RBL_ERR_INVALID, "rbl_comm_init: more than 2^31-1 blobs");
+    delete comm;
+    comm = nullptr;
+    CK(cudaStreamSynchronize(stream));
+    auto* c = new rbl::Comm();
+    if (!c->init(uid128, rank, world, blobs_per_rank)) {
+      std::string m = c->err;
+      delete c;
+      return fail(RBL_ERR_CUDA, "rbl_comm_init: " + m);
+    }
+    comm = c;
+    r_all_valid = false;
+    CK(d_status.ensure(4 * sizeof(int)));
+    return RBL_OK;
+  }
+#define NK(call)                                                        \
+  do {                                                                  \
+    if (!(call)) return this->fail(RBL_ERR_CUDA, "NCCL: " + comm->err); \
+  } while (0)
+
+  // every rank returns the same status: the largest one seen anywhere (a rank that failed alone
+  // would otherwise leave the others waiting inside the next collective)
+  int agree(int st) {
+    if (!comm) return st;
+    int h = st;
+    CK(cudaMemcpyAsync(d_status.p, &h, sizeof(int), cudaMemcpyHostToDevice, stream));
+    NK(comm->allreduce_max_int(d_status.as<int>(), 1, stream));
+    CK(cudaMemcpyAsync(&h, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (h != RBL_OK && st == RBL_OK) return fail(h, "another rank of the partitioned suspension reported an error");
+    return st != RBL_OK ? st : h;
+  }
+  int csync() { return agree(sync()); }
+
+  // out_local = rows of this rank of  B M B F  where F_local / r_local are this rank's slices.
+  // Single context: the plain product.  Partitioned: all-gather F (and the positions, unless they
+  // are the cached configuration), this rank's share of the unordered-pair work over ALL blobs,
+  // reduce-scatter of the partial products (each rank keeps the sum of its own rows).
+  int prod_M(const real* F_local, const real* r_local, bool r_is_config, real* out_local) {
+    const int nl = (int)N();
+    if (!comm) return dev_apply_M(F_local, r_local, nl, 0, nl, out_local);
+    const size_t n3_all = 3 * (size_t)comm->n_all;
+    const void* before = d_r_all.p;
+    CK(d_r_all.ensure(2 * n3_all * sizeof(real)));  // [configuration ; scratch positions (RFD)]
+    if (d_r_all.p != before) r_all_valid = false;
+    CK(d_lam_all.ensure(n3_all * sizeof(real)));
+    CK(d_mbuf.ensure(n3_all * sizeof(real)));
+    real* r_all = d_r_all.as<real>();
+    if (r_is_config) {
+      if (!r_all_valid) {
+        NK(comm->allgatherv<real>(r_local, r_all, 3, stream));
+        r_all_valid = true;
+      }
+    } else {
+      r_all += n3_all;
+      NK(comm->allgatherv<real>(r_local, r_all, 3, stream));
+    }
+    NK(comm->allgatherv<real>(F_local, d_lam_all.as<real>(), 3, stream));
+    RET(dev_apply_M_part(d_lam_all.p, r_all, (int)comm->n_all, comm->rank, comm->world, d_mbuf.p));
+    NK(comm->reduce_scatterv<real>(d_mbuf.as<real>(), out_local, 3, stream));
+    return RBL_OK;
+  }
+  // d_dots[0..m) = <V_i, w> summed over the ranks
+  int gdots(const real* V, size_t ld, int m, const real* w, size_t n) {
+    LAUNCH(2, rbl::multi_dot<real>(V, ld, m, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+    if (comm) NK(comm->allreduce_sum<real>(d_dots.as<real>(), (size_t)m, stream));
     return RBL_OK;
   }
 
@@ -467,7 +558,7 @@ struct Ctx final : rbl_ctx {
     RET(need_K());
     const int n = (int)N();
     // slip = M lam - K U ; F = K^T lam   (Rigid.py:73-80)
-    RET(dev_apply_M(dx, d_r.p, n, 0, n, dout));
+    RET(prod_M(dx, d_r.as<real>(), true, dout));
     LAUNCH(1, rbl::k_dot<real>(dx + 3 * (size_t)n, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, (real)-1, dout, dout, stream));
     LAUNCH(1, rbl::kt_dot<real>(dx, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, dout + 3 * (size_t)n, stream));
     return RBL_OK;
@@ -492,7 +583,7 @@ struct Ctx final : rbl_ctx {
     RET(h2d(d_in0.p, x, bytes));
     RET(dev_saddle(d_in0.as<real>(), d_out0.as<real>()));
     RET(d2h(out, d_out0.p, bytes));
-    return sync();
+    return csync();
   }
 
   // ---- preconditioner -----------------------------------------------------------------------
@@ -658,7 +749,7 @@ struct Ctx final : rbl_ctx {
     return RBL_OK;
   }
   int dev_norm(const real* v, size_t n, double* out) {
-    LAUNCH(2, rbl::multi_dot<real>(v, n, 1, v, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+    RET(gdots(v, n, 1, v, n));
     std::vector<double> s;
     RET(read_scalars(d_dots.as<real>(), 1, s));
     *out = std::sqrt(std::max(s[0], 0.0));
@@ -673,7 +764,7 @@ struct Ctx final : rbl_ctx {
     RET(h2d(d_in1.p, rhs, n * sizeof(real)));
     RET(dev_gmres(d_in1.as<real>(), d_out0.as<real>(), tol, restart, max_iter, iters, relres));
     RET(d2h(x, d_out0.p, n * sizeof(real)));
-    return sync();
+    return csync();
   }
 
   // device-resident core: b and xs are device vectors of sys_size() reals (distinct from the
@@ -681,6 +772,10 @@ struct Ctx final : rbl_ctx {
   int dev_gmres(const real* b, real* xs, double tol, int restart, int max_iter, int* iters, double* relres) {
     if (restart < 1 || max_iter < 1) return fail(RBL_ERR_INVALID, "gmres: restart and max_iter must be >= 1");
     RET(need_K());
+    if (!pc_set || comm) {  // lazily built like the reference (:591-596); every rank must agree it exists
+      const int st = agree(pc_set ? (int)RBL_OK : build_pc());
+      if (st != RBL_OK) return st;
+    }
     const size_t n = sys_size(), n_head = 3 * (size_t)N();
     const int m = restart;
     CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
@@ -733,7 +828,7 @@ struct Ctx final : rbl_ctx {
         // classical Gram-Schmidt, twice (one device->host read per pass)
         std::fill(H.begin() + (size_t)j * (m + 1), H.begin() + (size_t)(j + 1) * (m + 1), 0.0);
         for (int pass = 0; pass < 2; ++pass) {
-          LAUNCH(2, rbl::multi_dot<real>(V, n, j + 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+          RET(gdots(V, n, j + 1, w, n));
           LAUNCH(1, rbl::multi_axpy<real>(V, n, j + 1, d_dots.as<real>(), (real)-1, w, n, stream));
           RET(read_scalars(d_dots.as<real>(), j + 1, hcol));
           for (int i = 0; i <= j; ++i) H[(size_t)j * (m + 1) + i] += hcol[i];
@@ -828,7 +923,7 @@ struct Ctx final : rbl_ctx {
     RET(h2d(d_in1.p, W, n * sizeof(real)));
     RET(dev_lanczos(d_in1.as<real>(), d_out0.as<real>(), tol, max_iter, iters));
     RET(d2h(out, d_out0.p, n * sizeof(real)));
-    return sync();
+    return csync();
   }
 
   // device-resident core: dout = (B M B)^{1/2} dW at the CURRENT configuration (d_r)
@@ -858,14 +953,14 @@ struct Ctx final : rbl_ctx {
     int k = 0;
     for (; k < m;) {
       // w = M v_k - beta_{k-1} v_{k-1}
-      RET(dev_apply_M(V + (size_t)k * n, d_r.p, nb, 0, nb, w));
+      RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
       if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-beta[k - 1]), w, n, true, stream));
-      LAUNCH(2, rbl::multi_dot<real>(V + (size_t)k * n, n, 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+      RET(gdots(V + (size_t)k * n, n, 1, w, n));
       RET(read_scalars(d_dots.as<real>(), 1, s));
       alpha.push_back(s[0]);
       LAUNCH(1, rbl::scale_copy<real>(V + (size_t)k * n, (real)(-s[0]), w, n, true, stream));
       // full reorthogonalisation (keeps the basis orthonormal in fp32 too)
-      LAUNCH(2, rbl::multi_dot<real>(V, n, k + 1, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
+      RET(gdots(V, n, k + 1, w, n));
       LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>(), (real)-1, w, n, stream));
       double bn = 0;
       RET(dev_norm(w, n, &bn));
@@ -940,8 +1035,10 @@ struct Ctx final : rbl_ctx {
       // Brownian increments at q^n  (M_half_W, :661-675, via Lanczos)
       RET(h2d(noise, W1, n3 * sizeof(real)));
       RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it));
+      last_lanczos[0] = it;
       RET(h2d(noise, W2, n3 * sizeof(real)));
       RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it));
+      last_lanczos[1] = it;
       // random finite difference  (M_RFD, :769-796)
       const double delta = sizeof(real) == 8 ? 1.0e-4 : 4.0e-3;
       RET(h2d(noise, Wr, n3 * sizeof(real)));
@@ -952,7 +1049,7 @@ struct Ctx final : rbl_ctx {
                                        d_Q.as<real>(), d_Xp.as<real>(), d_Qp.as<real>(), stream));
         LAUNCH(1, rbl::place_blobs<real>(d_Xp.as<real>(), d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb,
                                          d_rp.as<real>(), stream));
-        RET(dev_apply_M(noise, d_rp.p, nb, 0, nb, Mpm[sgn]));
+        RET(prod_M(noise, d_rp.as<real>(), false, Mpm[sgn]));
       }
       LAUNCH(1, rbl::scale_copy<real>(d_t1.as<real>(), (real)(1.0 / delta), d_rfd.as<real>(), n3, false, stream));
       LAUNCH(1, rbl::scale_copy<real>(d_t2.as<real>(), (real)(-1.0 / delta), d_rfd.as<real>(), n3, true, stream));
@@ -984,7 +1081,7 @@ struct Ctx final : rbl_ctx {
     RET(set_K_mats());
     pc_set = false;
     RET(d2h(U_out, sol + n3, n6 * sizeof(real)));
-    return sync();
+    return csync();
   }
 
   // ---- measurement ----------------------------------------------------------------------------
@@ -1168,6 +1265,21 @@ int rbl_dev_saddle_finish(rbl_ctx* ctx, const void* dM, const void* dl, const vo
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
   return ctx->saddle_finish(dM, dl, dU, dout);
 }
+int rbl_comm_unique_id(void* out128) {
+  if (!out128) return RBL_ERR_INVALID;
+  std::string why;
+  if (!rbl::Comm::unique_id(out128, &why)) {
+    g_create_error = "rbl_comm_unique_id: " + why;
+    return RBL_ERR_CUDA;
+  }
+  return RBL_OK;
+}
+int rbl_comm_init(rbl_ctx* ctx, const void* uid128, int rank, int world, const int* blobs_per_rank) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->comm_init(uid128, rank, world, blobs_per_rank);
+}
+int rbl_comm_world(const rbl_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->world : 1; }
+int rbl_comm_rank(const rbl_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }
 int rbl_sync(rbl_ctx* ctx) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->sync(); }
 void* rbl_stream(rbl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int rbl_set_stream(rbl_ctx* ctx, void* s) {
@@ -1245,6 +1357,13 @@ int rbl_set_sym_variant(rbl_ctx* ctx, int idx) {
   return RBL_OK;
 }
 int64_t rbl_launch_count(const rbl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t rbl_product_count(const rbl_ctx* ctx) { return ctx ? ctx->products : 0; }
+int rbl_bd_stats(const rbl_ctx* ctx, int* lanczos_iters_1, int* lanczos_iters_2) {
+  if (!ctx) return RBL_ERR_INVALID;
+  if (lanczos_iters_1) *lanczos_iters_1 = ctx->last_lanczos[0];
+  if (lanczos_iters_2) *lanczos_iters_2 = ctx->last_lanczos[1];
+  return RBL_OK;
+}
 int rbl_profile_matvec(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->profile = enable != 0; return RBL_OK; }
 int rbl_matvec_profile(rbl_ctx* ctx, double* avg_ms, int64_t* launches, int reset) {
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);

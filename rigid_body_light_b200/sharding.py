@@ -162,3 +162,152 @@ def slice_system(vec, ranges, n_blb, rank):
     n3 = 3 * n_bod * n_blb
     lo, hi = ranges[rank]
     return np.concatenate([vec[3 * lo * n_blb: 3 * hi * n_blb], vec[n3 + 6 * lo: n3 + 6 * hi]])
+
+
+class PartitionedRigidBody:
+    """One rank's handle on a suspension partitioned over the GPUs of a node, with NCCL inside
+    the library (``rbl_comm_init``, include/rbl.h): the same operators as ``Rigid.RigidBody`` but
+    on rank-local slices, and collective -- every rank calls them together.
+
+    Every rank passes the GLOBAL ``X`` / ``Q``; the rank keeps the bodies ``ranges[rank]``.
+    System vectors are ``[lambda_local (3 N_local) ; U_local (6 n_bod_local)]``
+    (``slice_system`` cuts them out of a global vector, ``gather_system`` puts them back).
+
+    ``dist`` is ``torch.distributed`` (any backend) and is used ONLY to hand rank 0's
+    ncclUniqueId to the other ranks and by ``gather_system``; pass ``uid=`` to use another
+    transport.  world_size 1 needs no communicator (``force_comm=True`` still creates one: the
+    NCCL path with a single rank)."""
+
+    def __init__(self, rigid_config, X, Q, a, eta, dt, wall_PC=False, block_PC=False, precision="single",
+                 rank=0, world=1, dist=None, device=None, uid=None, force_comm=False):
+        import ctypes
+
+        from ._lib import Context
+
+        rigid_config = np.asarray(rigid_config, dtype=np.float64).reshape(-1, 3)
+        X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+        Q = np.asarray(Q, dtype=np.float64).reshape(-1, 4)
+        if X.shape[0] != Q.shape[0]:
+            raise RuntimeError("X and Q must have the same number of bodies")
+        self.rank, self.world, self.dist = rank, world, dist
+        self.n_blb = rigid_config.shape[0]
+        self.N_bodies_global = X.shape[0]
+        self.ranges = body_ranges(self.N_bodies_global, world)
+        if min(hi - lo for lo, hi in self.ranges) < 1:
+            raise RuntimeError("every rank needs at least one body")
+        self.b0, self.b1 = self.ranges[rank]
+        self.N_bodies = self.b1 - self.b0
+        self.total_blobs = self.N_bodies * self.n_blb
+        self.ctx = Context(precision, device=-1 if device is None else device)
+        self.real = self.ctx.real
+        self.ctx.set_parameters(a, dt, 1.0, eta, rigid_config)
+        self.ctx.set_flags(int(block_PC), int(wall_PC))
+        self.ctx.set_config(X[self.b0:self.b1], Q[self.b0:self.b1])
+        if world == 1 and not force_comm:
+            return  # a single context needs no communicator (force_comm: NCCL path with one rank, for tests)
+        if uid is None:
+            box = [None]
+            if rank == 0:
+                buf = ctypes.create_string_buffer(128)
+                st = self.ctx.L.rbl_comm_unique_id(buf)
+                if st != 0:
+                    raise RuntimeError(self.ctx.L.rbl_last_error(None).decode())
+                box[0] = buf.raw
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            uid = box[0]
+        counts = (ctypes.c_int * world)(*[(hi - lo) * self.n_blb for lo, hi in self.ranges])
+        self.ctx.call("rbl_comm_init", ctypes.c_char_p(uid), rank, world, counts)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _in(self, v, n, what):
+        v = np.ascontiguousarray(np.asarray(v, dtype=self.real).reshape(-1))
+        if v.size != n:
+            raise RuntimeError(f"{what} must have total size {n} on this rank, got {v.size}")
+        return v
+
+    @property
+    def sys_size(self):
+        return 3 * self.total_blobs + 6 * self.N_bodies
+
+    def slice_system(self, vec_global):
+        return slice_system(np.asarray(vec_global).reshape(-1), self.ranges, self.n_blb, self.rank)
+
+    def slice_blobs(self, vec_global):
+        v = np.asarray(vec_global).reshape(-1)
+        return v[3 * self.b0 * self.n_blb: 3 * self.b1 * self.n_blb]
+
+    def slice_bodies(self, vec_global, per=6):
+        v = np.asarray(vec_global).reshape(-1)
+        return v[per * self.b0: per * self.b1]
+
+    def gather_system(self, x_local):
+        """Global [lambda ; U] vector on every rank (host side, for checks and output)."""
+        if self.world == 1:
+            return np.asarray(x_local).copy()
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, np.asarray(x_local))
+        lam = [p[: p.size - 6 * (hi - lo)] for p, (lo, hi) in zip(parts, self.ranges)]
+        U = [p[p.size - 6 * (hi - lo):] for p, (lo, hi) in zip(parts, self.ranges)]
+        return np.concatenate(lam + U)
+
+    # -- collective operators (rank-local slices in and out) ---------------------------------
+    def apply_saddle(self, x_local):
+        x = self._in(x_local, self.sys_size, "x")
+        out = np.empty_like(x)
+        self.ctx.call("rbl_apply_saddle", x.ctypes.data, out.ctypes.data)
+        return out
+
+    def apply_PC(self, b_local):  # rank-local: whole bodies per rank
+        b = self._in(b_local, self.sys_size, "b")
+        out = np.empty_like(b)
+        self.ctx.call("rbl_apply_PC", b.ctypes.data, out.ctypes.data)
+        return out
+
+    def gmres(self, rhs_local, tol=1e-8, restart=60, max_iter=300):
+        import ctypes
+
+        rhs = self._in(rhs_local, self.sys_size, "rhs")
+        x = np.empty_like(rhs)
+        it, rr = ctypes.c_int(), ctypes.c_double()
+        self.ctx.call("rbl_gmres", rhs.ctypes.data, x.ctypes.data, tol, restart, max_iter, ctypes.byref(it), ctypes.byref(rr))
+        return x, it.value, rr.value
+
+    def brownian_sqrt(self, W_local, tol=1e-6, max_iter=100):
+        import ctypes
+
+        W = self._in(W_local, 3 * self.total_blobs, "W")
+        out = np.empty_like(W)
+        it = ctypes.c_int()
+        self.ctx.call("rbl_lanczos_sqrt", W.ctypes.data, out.ctypes.data, tol, max_iter, ctypes.byref(it))
+        return out, it.value
+
+    def bd_step(self, F_ext_local, slip_local=None, kBT=0.0, noise_local=None, tol=1e-8, restart=60, max_iter=300,
+                lanczos_tol=1e-6, lanczos_max_iter=100):
+        """One BD step of the whole suspension (``rbl_bd_step``); the rank's bodies move.
+        ``noise_local`` = (W1, W2, Wr) slices of three GLOBAL standard-normal vectors."""
+        import ctypes
+
+        n3 = 3 * self.total_blobs
+        F = self._in(F_ext_local, 6 * self.N_bodies, "F_ext")
+        slip = None if slip_local is None else self._in(slip_local, n3, "slip")
+        W = [None, None, None]
+        if kBT > 0:
+            if noise_local is None:
+                raise RuntimeError("kBT > 0 needs noise_local = (W1, W2, Wr)")
+            W = [self._in(w, n3, "noise") for w in noise_local]
+        U = np.empty(6 * self.N_bodies, dtype=self.real)
+        it, rr = ctypes.c_int(), ctypes.c_double()
+        ptr = lambda v: None if v is None else v.ctypes.data  # noqa: E731
+        self.ctx.call("rbl_bd_step", F.ctypes.data, ptr(slip), ptr(W[0]), ptr(W[1]), ptr(W[2]), float(kBT), tol, restart,
+                      max_iter, lanczos_tol, lanczos_max_iter, U.ctypes.data, ctypes.byref(it), ctypes.byref(rr))
+        return U, it.value, rr.value
+
+    def get_config(self):
+        X = np.empty(3 * self.N_bodies, dtype=self.real)
+        Q = np.empty(4 * self.N_bodies, dtype=self.real)
+        self.ctx.call("rbl_get_config", X.ctypes.data, Q.ctypes.data)
+        return X.reshape(-1, 3), Q.reshape(-1, 4)
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,99 @@
+"""torchrun worker for tests/test_gpu_partitioned.py: every rank holds its body range of a small
+suspension (NCCL inside librbl, rbl_comm_init) and checks the collective operators against the
+same suspension on ONE context built on the rank's own GPU.  Prints PARTITIONED-OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from Rigid import RigidBody
+    from rigid_body_light_b200.sharding import PartitionedRigidBody
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count())
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # plumbing only: hands the NCCL id round
+    n_bodies = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    s = sphere_suspension(n_bodies, 42, True)
+    n_blb = 42
+    n3, n6 = 3 * n_bodies * n_blb, 6 * n_bodies
+    rng = np.random.default_rng(11)
+    vec = rng.standard_normal(n3 + n6)
+    rhs = np.concatenate([np.zeros(n3), rng.standard_normal(n6)])
+    W = [rng.standard_normal(n3) for _ in range(3)]
+    F_ext = np.tile(np.array([0, 0, -1.0, 0, 0, 0]), n_bodies)
+    for precision, tol in (("double", 1e-11), ("single", 2e-5)):
+        for block in (False, True):
+            one = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=block, precision=precision)
+            part = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=block,
+                                        precision=precision, rank=rank, world=world, dist=dist, force_comm=True)
+            # saddle operator
+            got = part.gather_system(part.apply_saddle(part.slice_system(vec)))
+            e = rel(got, one.apply_saddle(vec))
+            assert e < tol, ("saddle", precision, block, e)
+            # preconditioner (rank-local)
+            got = part.gather_system(part.apply_PC(part.slice_system(vec)))
+            e = rel(got, one.apply_PC(vec))
+            assert e < 50 * tol, ("pc", precision, block, e)
+            # GMRES
+            gt = 1e-10 if precision == "double" else 1e-5
+            x, it, rr = part.gmres(part.slice_system(rhs), tol=gt, restart=40, max_iter=120)
+            x1, it1, rr1 = one.gmres(rhs, tol=gt, restart=40, max_iter=120)
+            assert rr <= gt and abs(it - it1) <= 2, ("gmres", precision, block, it, it1, rr)
+            e = rel(part.gather_system(x), x1)
+            assert e < (1e-7 if precision == "double" else 5e-3), ("gmres x", precision, block, e)
+            # Lanczos square root
+            lt = 1e-9 if precision == "double" else 1e-5
+            y, k = part.brownian_sqrt(part.slice_blobs(W[0]), tol=lt, max_iter=80)
+            y1, k1 = one.brownian_sqrt(W[0], tol=lt, max_iter=80)
+            parts = [None] * world
+            dist.all_gather_object(parts, y)
+            e = rel(np.concatenate(parts), y1)
+            assert e < (1e-8 if precision == "double" else 1e-4), ("lanczos", precision, e, k, k1)
+            # full Brownian step: same noise, same step
+            noise_l = tuple(part.slice_blobs(w) for w in W)
+            U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, noise_local=noise_l, tol=gt, restart=40,
+                                     max_iter=120, lanczos_tol=lt, lanczos_max_iter=80)
+            U1, it1, rr1 = one.bd_step(F_ext, kBT=0.0041, noise=tuple(W), tol=gt, restart=40, max_iter=120,
+                                       lanczos_tol=lt, lanczos_max_iter=80)
+            parts = [None] * world
+            dist.all_gather_object(parts, U)
+            e = rel(np.concatenate(parts), U1)
+            assert e < (1e-6 if precision == "double" else 2e-2), ("bd_step U", precision, block, e)
+            Xp, Qp = part.get_config()
+            X1, Q1 = one.get_config()
+            assert rel(Xp, X1[part.b0:part.b1]) < (1e-9 if precision == "double" else 1e-5)
+            assert rel(Qp, Q1[part.b0:part.b1]) < (1e-8 if precision == "double" else 1e-4)
+            part.close()
+    # a blob below the wall on ONE rank must surface as the same error on EVERY rank
+    Xb = s["X"].copy()
+    Xb[0, 2] = 0.0
+    part = PartitionedRigidBody(s["cfg"], Xb, s["Q"], s["a"], 1.0, 0.01, wall_PC=True, precision="double",
+                                rank=rank, world=world, dist=dist, force_comm=True)
+    try:
+        part.apply_saddle(part.slice_system(vec))
+        raise AssertionError("no error for a blob below the wall")
+    except RuntimeError as exc:
+        assert "BELOW_WALL" in str(exc) or "another rank" in str(exc), str(exc)
+    part.close()
+    dist.barrier()
+    if rank == 0:
+        print("PARTITIONED-OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
