@@ -114,7 +114,18 @@ def build_suspension(workload):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout, but native libraries write there too (NCCL prints
+    its version banner on the first communicator).  Point fd 1 at stderr for the run and return a
+    file on the ORIGINAL stdout for the result line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def run_ours(args):
+    result_out = _protect_stdout()
     import torch
     import torch.distributed as dist
 
@@ -312,7 +323,7 @@ def run_ours(args):
         if "double" in results and head_p == "single":
             d = results["double"]
             line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step")}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

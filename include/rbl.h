@@ -109,6 +109,17 @@ int rbl_gmres(rbl_ctx* ctx, const void* rhs, void* x, double tol, int restart, i
 int rbl_lanczos_sqrt(rbl_ctx* ctx, const void* W, void* out, double tol, int max_iter,
                      int* iters);
 
+/* Two right-hand sides per pass: out1 = M F1 (or B M B F1), out2 = M F2, same semantics as
+ * rbl_apply_M.  The geometry of every blob pair is evaluated once for both vectors
+ * (rpy_matvec_sym2_kernel); this is the product behind rbl_lanczos_sqrt2 and the BD step. */
+int rbl_apply_M2(rbl_ctx* ctx, const void* F1, const void* F2, const void* r, int n_blobs, void* out1, void* out2);
+/* (B M B)^{1/2} W1 and (B M B)^{1/2} W2 by two Lanczos recurrences in lockstep that share every
+ * mobility product (the two M_half_W calls of one step, :930-935).  iters2: two ints. */
+int rbl_lanczos_sqrt2(rbl_ctx* ctx, const void* W1, const void* W2, void* out1, void* out2, double tol,
+                      int max_iter, int* iters2);
+/* 1 (default): rbl_bd_step uses the paired Lanczos; 0: two separate single-vector runs */
+int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable);
+
 /* One rigid-body Brownian-dynamics step: the trapezoidal-slip midpoint scheme
  * that RHS_and_Midpoint (:917-976) sets up but never finishes, composed on the device:
  *   M^{1/2}W_1, M^{1/2}W_2 by Lanczos;  RFD drift (M(q+) - M(q-)) W_r / delta with
@@ -128,6 +139,9 @@ int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W
  * This is the entry a multi-GPU host shards by body range. */
 int rbl_dev_apply_M(rbl_ctx* ctx, const void* dF, const void* dr, int n_blobs, int tgt_first,
                     int n_tgt, void* dout);
+/* device-pointer form of rbl_apply_M2 (all n_blobs blobs are targets and sources) */
+int rbl_dev_apply_M2(rbl_ctx* ctx, const void* dF1, const void* dF2, const void* dr, int n_blobs, void* dout1,
+                     void* dout2);
 int rbl_dev_blob_positions(rbl_ctx* ctx, void* dout);
 int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout);
 int rbl_dev_KT_dot(rbl_ctx* ctx, const void* dlambda, void* dout);
@@ -197,6 +211,9 @@ int rbl_set_matvec_mode(rbl_ctx* ctx, int mode);
 int rbl_num_sym_variants(const rbl_ctx* ctx);
 int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
+int rbl_num_sym2_variants(const rbl_ctx* ctx);
+int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
+int rbl_set_sym2_variant(rbl_ctx* ctx, int idx); /* two-right-hand-side kernel; -1 = automatic */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t rbl_launch_count(const rbl_ctx* ctx);
 /* mobility products (whole, or one rank's share) launched since creation */

@@ -136,6 +136,23 @@ class RigidBody:
         self._need(W, 3 * self.total_blobs, "W", "3*N_blobs")
         return self.cb.lanczos_sqrt(W.reshape(-1), tol, max_iter)
 
+    def apply_M2(self, forces1, forces2, positions):
+        """(M F1, M F2) in one pass over the blob pairs (two-right-hand-side kernel)."""
+        f1, f2, r = np.asarray(forces1), np.asarray(forces2), np.asarray(positions)
+        if f1.size != r.size or f2.size != r.size:
+            raise RuntimeError("Positions and forces must be of the same size")
+        if r.size % 3 != 0:
+            raise RuntimeError("Positions and forces must have total length 3N, where N is the number of blobs")
+        return self.cb.apply_M2(f1.reshape(-1), f2.reshape(-1), r.reshape(-1))
+
+    def brownian_sqrt_pair(self, W1, W2, tol=1e-6, max_iter=100):
+        """(B M B)^{1/2} W1 and (B M B)^{1/2} W2 by two Lanczos recurrences that share every
+        mobility product.  Returns (vector1, vector2, iterations1, iterations2)."""
+        W1, W2 = np.asarray(W1), np.asarray(W2)
+        self._need(W1, 3 * self.total_blobs, "W1", "3*N_blobs")
+        self._need(W2, 3 * self.total_blobs, "W2", "3*N_blobs")
+        return self.cb.lanczos_sqrt2(W1.reshape(-1), W2.reshape(-1), tol, max_iter)
+
     def bd_step(self, F_ext, slip=None, kBT=0.0, noise=None, rng=None, tol=1e-8, restart=60, max_iter=300,
                 lanczos_tol=1e-6, lanczos_max_iter=100):
         """Advance the bodies by one (Brownian) step with the trapezoidal-slip midpoint scheme

@@ -49,6 +49,13 @@ SYMBOLS = {
     "rbl_export_Kinv_csc": (_i, [_vp, _vp, _vp, _vp]),
     "rbl_gmres": (_i, [_vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     "rbl_lanczos_sqrt": (_i, [_vp, _vp, _vp, _d, _i, _pi]),
+    "rbl_apply_M2": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "rbl_dev_apply_M2": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "rbl_lanczos_sqrt2": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _pi]),
+    "rbl_set_lanczos_pairing": (_i, [_vp, _i]),
+    "rbl_num_sym2_variants": (_i, [_vp]),
+    "rbl_sym2_variant_info": (_i, [_vp, _i, _pi, _pi]),
+    "rbl_set_sym2_variant": (_i, [_vp, _i]),
     "rbl_bd_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _d, _i, _vp, _pi, _pd]),
     "rbl_dev_apply_M": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rbl_dev_blob_positions": (_i, [_vp, _vp]),

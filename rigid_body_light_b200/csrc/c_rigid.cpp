@@ -165,6 +165,21 @@ class CManyBodies {
     check(rbl_lanczos_sqrt(ctx_, W.data(), out.mutable_data(), tol, max_iter, &iters));
     return py::make_tuple(out, iters);
   }
+  py::tuple apply_M2(Arr F1, Arr F2, Arr r_vecs) {  // two right-hand sides in one pass over the pairs
+    if (F1.size() != r_vecs.size() || F2.size() != r_vecs.size() || F1.size() % 3 != 0)
+      throw std::runtime_error("apply_M2: F1, F2 and r_vecs must all have 3*N_blobs entries");
+    py::array_t<real> o1(F1.size()), o2(F1.size());
+    check(rbl_apply_M2(ctx_, F1.data(), F2.data(), r_vecs.data(), (int)(F1.size() / 3), o1.mutable_data(), o2.mutable_data()));
+    return py::make_tuple(o1, o2);
+  }
+  py::tuple lanczos_sqrt2(Arr W1, Arr W2, double tol, int max_iter) {
+    want(W1, n3(), "lanczos_sqrt2 W1");
+    want(W2, n3(), "lanczos_sqrt2 W2");
+    py::array_t<real> o1(n3()), o2(n3());
+    int iters[2] = {0, 0};
+    check(rbl_lanczos_sqrt2(ctx_, W1.data(), W2.data(), o1.mutable_data(), o2.mutable_data(), tol, max_iter, iters));
+    return py::make_tuple(o1, o2, iters[0], iters[1]);
+  }
   // one Brownian-dynamics step (noise supplied by the caller; None -> deterministic)
   py::tuple bd_step(Arr F_ext, py::object slip, py::object W1, py::object W2, py::object Wr, double kBT, double tol,
                     int restart, int max_iter, double ltol, int lmax) {
@@ -220,6 +235,9 @@ PYBIND11_MODULE(RBL_MODULE_NAME, m) {
       .def("gmres", &CManyBodies::gmres, py::arg("rhs"), py::arg("tol") = 1e-8, py::arg("restart") = 60,
            py::arg("max_iter") = 300)
       .def("lanczos_sqrt", &CManyBodies::lanczos_sqrt, py::arg("W"), py::arg("tol") = 1e-6,
+           py::arg("max_iter") = 100)
+      .def("apply_M2", &CManyBodies::apply_M2, py::arg("F1"), py::arg("F2"), py::arg("r_vecs"))
+      .def("lanczos_sqrt2", &CManyBodies::lanczos_sqrt2, py::arg("W1"), py::arg("W2"), py::arg("tol") = 1e-6,
            py::arg("max_iter") = 100)
       .def("bd_step", &CManyBodies::bd_step, py::arg("F_ext"), py::arg("slip") = py::none(), py::arg("W1") = py::none(),
            py::arg("W2") = py::none(), py::arg("Wr") = py::none(), py::arg("kBT") = 0.0, py::arg("tol") = 1e-8,

@@ -95,6 +95,11 @@ struct rbl_ctx {
   virtual int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) = 0;
   virtual int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) = 0;
   virtual int comm_init(const void* uid128, int rank, int world, const int* blobs_per_rank) = 0;
+  virtual int dev_apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
+  virtual int apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
+  virtual int lanczos2(const void* W1, const void* W2, void* out1, void* out2, double tol, int max_iter, int* iters2) = 0;
+  virtual int num_sym2_variants() const = 0;
+  virtual int sym2_variant_info(int idx, int* T, int* threads) const = 0;
 
   // shared plumbing
   rbl::Comm* comm = nullptr;  // non-null: this context holds one rank's bodies of a partitioned suspension
@@ -106,6 +111,8 @@ struct rbl_ctx {
   int last_lanczos[2] = {0, 0};  // Lanczos iterations of the last rbl_bd_step
   int variant = -1;
   int sym_variant = -1;
+  int sym2_variant = -1;
+  bool pair_lanczos = true;  // BD step: M^{1/2}W_1 and M^{1/2}W_2 in lockstep over the two-right-hand-side product
   int mode = 0;  // 0: symmetric kernel when targets == sources; 1: ordered kernel always
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -155,6 +162,8 @@ struct Ctx final : rbl_ctx {
   DevBuf d_rhs, d_sol, d_mh1, d_mh2, d_rfd, d_noise, d_uom, d_Xs, d_Qs, d_Xp, d_Qp, d_rp, d_t1, d_t2;
   // partitioned mode (comm != nullptr): all-gathered positions / forces, partial product, agreed status
   DevBuf d_r_all, d_lam_all, d_mbuf, d_status;
+  // two-right-hand-side product / paired Lanczos
+  DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2;
   bool r_all_valid = false;
 
   enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, N_FLAGS = 4 };
@@ -537,6 +546,95 @@ struct Ctx final : rbl_ctx {
   int gdots(const real* V, size_t ld, int m, const real* w, size_t n) {
     LAUNCH(2, rbl::multi_dot<real>(V, ld, m, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
     if (comm) NK(comm->allreduce_sum<real>(d_dots.as<real>(), (size_t)m, stream));
+    return RBL_OK;
+  }
+
+
+  // ---- two right-hand sides per pass (rpy_matvec_sym2_kernel) ----------------------------------
+  int dev_apply_M2_part(const void* F1, const void* F2, const void* r, int n, int part, int n_parts, void* out1,
+                        void* out2) {
+    if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
+    if (n < 0 || n_parts < 1 || part < 0 || part >= n_parts) return fail(RBL_ERR_INVALID, "apply_M2_part: bad share");
+    if (n == 0) return RBL_OK;
+    const int v = sym2_variant >= 0 ? sym2_variant : rbl::matvec_sym2_default_variant<real>(wall, n);
+    rbl::Sym2Args<real> A;
+    CK(rbl::matvec_sym2_plan<real>(v, wall, n, part, n_parts, sm_count, &A.plan));
+    const size_t n_pad = (size_t)A.plan.n_src_tiles * rbl::kSrcTile;
+    CK(d_rec2.ensure(n_pad * rbl::kRec2Reals * sizeof(real)));
+    CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
+    CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
+    CK(d_raw2.ensure(2 * 3 * n_pad * sizeof(real)));
+    LAUNCH(1, rbl::pack_records2<real>(static_cast<const real*>(r), static_cast<const real*>(F1), static_cast<const real*>(F2),
+                                       n, (int)n_pad, wall, (real)a, d_rec2.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream, rbl::kRec2Reals));
+    LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream, rbl::kRec2Reals));
+    A.rec = d_rec2.as<real>();
+    A.box_src = d_box_src.as<float>();
+    A.box_tgt = d_box_tgt.as<float>();
+    A.raw = d_raw2.as<real>();
+    A.out1 = static_cast<real*>(out1);
+    A.out2 = static_cast<real*>(out2);
+    A.C = rbl::make_pair_consts<real>(a, eta);
+    A.wall = wall ? 1 : 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      prof_events.emplace_back(e0, e1);
+    }
+    LAUNCH(2, rbl::matvec_sym2_launch<real>(v, A, stream, e0, e1));
+    products += 2;
+    return RBL_OK;
+  }
+  // out_k_local = rows of this rank of B M B F_k (k = 1, 2) at the cached configuration
+  int prod_M2(const real* F1_local, const real* F2_local, real* out1_local, real* out2_local) {
+    const int nl = (int)N();
+    if (!comm) return dev_apply_M2_part(F1_local, F2_local, d_r.p, nl, 0, 1, out1_local, out2_local);
+    const size_t n3_all = 3 * (size_t)comm->n_all;
+    const void* before = d_r_all.p;
+    CK(d_r_all.ensure(2 * n3_all * sizeof(real)));
+    if (d_r_all.p != before) r_all_valid = false;
+    CK(d_lam_all.ensure(2 * n3_all * sizeof(real)));
+    CK(d_mbuf.ensure(2 * n3_all * sizeof(real)));
+    if (!r_all_valid) {
+      NK(comm->allgatherv<real>(d_r.as<real>(), d_r_all.as<real>(), 3, stream));
+      r_all_valid = true;
+    }
+    real* lam = d_lam_all.as<real>();
+    real* mb = d_mbuf.as<real>();
+    NK(comm->allgatherv<real>(F1_local, lam, 3, stream));
+    NK(comm->allgatherv<real>(F2_local, lam + n3_all, 3, stream));
+    RET(dev_apply_M2_part(lam, lam + n3_all, d_r_all.p, (int)comm->n_all, comm->rank, comm->world, mb, mb + n3_all));
+    NK(comm->reduce_scatterv<real>(mb, out1_local, 3, stream));
+    NK(comm->reduce_scatterv<real>(mb + n3_all, out2_local, 3, stream));
+    return RBL_OK;
+  }
+  int dev_apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) override {
+    return dev_apply_M2_part(F1, F2, r, n, 0, 1, out1, out2);
+  }
+  int apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) override {
+    if (n < 0) return fail(RBL_ERR_INVALID, "apply_M2: negative size");
+    if (n == 0) return RBL_OK;
+    const size_t bytes = 3 * (size_t)n * sizeof(real);
+    CK(d_in0.ensure(bytes));
+    CK(d_in1.ensure(bytes));
+    CK(d_in2.ensure(bytes));
+    CK(d_out0.ensure(bytes));
+    CK(d_out2.ensure(bytes));
+    RET(h2d(d_in0.p, F1, bytes));
+    RET(h2d(d_in2.p, F2, bytes));
+    RET(h2d(d_in1.p, r, bytes));
+    RET(dev_apply_M2_part(d_in0.p, d_in2.p, d_in1.p, n, 0, 1, d_out0.p, d_out2.p));
+    RET(d2h(out1, d_out0.p, bytes));
+    RET(d2h(out2, d_out2.p, bytes));
+    return sync();
+  }
+  int num_sym2_variants() const override { return rbl::matvec_sym2_num_variants<real>(); }
+  int sym2_variant_info(int idx, int* T, int* threads) const override {
+    if (idx < 0 || idx >= rbl::matvec_sym2_num_variants<real>()) return RBL_ERR_INVALID;
+    const rbl::MatvecVariant v = rbl::matvec_sym2_variant<real>(idx);
+    *T = v.T;
+    *threads = v.threads;
     return RBL_OK;
   }
 
@@ -1001,6 +1099,124 @@ struct Ctx final : rbl_ctx {
   }
 
 
+
+  // y = ||W|| T_k^{1/2} e_1 for the Lanczos tridiagonal (alpha, beta)
+  static void lanczos_coeffs(const std::vector<double>& alpha, const std::vector<double>& beta, int k, double wnorm,
+                             std::vector<double>& y) {
+    std::vector<double> T((size_t)k * k, 0.0), Z;
+    for (int i = 0; i < k; ++i) {
+      T[(size_t)i * k + i] = alpha[i];
+      if (i + 1 < k) T[(size_t)i * k + i + 1] = T[(size_t)(i + 1) * k + i] = beta[i];
+    }
+    jacobi_eig(T, k, Z);
+    y.assign(k, 0.0);
+    for (int e = 0; e < k; ++e) {
+      const double lam = std::max(T[(size_t)e * k + e], 0.0);
+      const double f = std::sqrt(lam) * Z[(size_t)0 * k + e] * wnorm;
+      for (int i = 0; i < k; ++i) y[i] += Z[(size_t)i * k + e] * f;
+    }
+  }
+
+  int lanczos2(const void* W1, const void* W2, void* out1, void* out2, double tol, int max_iter, int* iters2) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    const size_t n = 3 * (size_t)N();
+    CK(d_in1.ensure(n * sizeof(real)));
+    CK(d_in2.ensure(n * sizeof(real)));
+    CK(d_out0.ensure(n * sizeof(real)));
+    CK(d_out2.ensure(n * sizeof(real)));
+    RET(h2d(d_in1.p, W1, n * sizeof(real)));
+    RET(h2d(d_in2.p, W2, n * sizeof(real)));
+    RET(dev_lanczos2(d_in1.as<real>(), d_in2.as<real>(), d_out0.as<real>(), d_out2.as<real>(), tol, max_iter, iters2));
+    RET(d2h(out1, d_out0.p, n * sizeof(real)));
+    RET(d2h(out2, d_out2.p, n * sizeof(real)));
+    return csync();
+  }
+
+  // Two Lanczos recurrences in lockstep, (B M B)^{1/2} W_1 and (B M B)^{1/2} W_2, sharing every
+  // mobility product through the two-right-hand-side kernel.  Each recurrence is exactly
+  // dev_lanczos (same stopping rule); one that has converged is frozen while the other finishes.
+  int dev_lanczos2(const real* dW1, const real* dW2, real* dout1, real* dout2, double tol, int max_iter, int* iters2) {
+    if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
+    RET(need_K());
+    const size_t n = 3 * (size_t)N();
+    const int m = max_iter;
+    CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
+    CK(d_V2.ensure((size_t)(m + 1) * n * sizeof(real)));
+    CK(d_w.ensure(n * sizeof(real)));
+    CK(d_w2.ensure(n * sizeof(real)));
+    CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
+    CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    struct Rec {
+      real* V; real* w; const real* W; real* out;
+      std::vector<double> alpha, beta, y_prev, y;
+      double wnorm = 0; int k = 0; bool done = false;
+    } R[2];
+    R[0].V = d_V.as<real>();  R[0].w = d_w.as<real>();  R[0].W = dW1; R[0].out = dout1;
+    R[1].V = d_V2.as<real>(); R[1].w = d_w2.as<real>(); R[1].W = dW2; R[1].out = dout2;
+    std::vector<double> s;
+    for (auto& q : R) {
+      LAUNCH(1, rbl::scale_copy<real>(q.W, (real)1, q.w, n, false, stream));
+      RET(dev_norm(q.w, n, &q.wnorm));
+      if (q.wnorm == 0) {
+        CK(cudaMemsetAsync(q.out, 0, n * sizeof(real), stream));
+        CK(cudaMemsetAsync(q.V, 0, n * sizeof(real), stream));  // a harmless input for the shared products
+        q.done = true;
+      } else {
+        LAUNCH(1, rbl::scale_copy<real>(q.w, (real)(1.0 / q.wnorm), q.V, n, false, stream));
+      }
+    }
+    for (int step = 0; step < m && !(R[0].done && R[1].done); ++step) {
+      // a frozen recurrence feeds its last basis vector (the result is ignored)
+      const real* v0 = R[0].V + (size_t)(R[0].done ? std::max(R[0].k - 1, 0) : R[0].k) * n;
+      const real* v1 = R[1].V + (size_t)(R[1].done ? std::max(R[1].k - 1, 0) : R[1].k) * n;
+      RET(prod_M2(v0, v1, R[0].w, R[1].w));
+      for (auto& q : R) {
+        if (q.done) continue;
+        const int k = q.k;
+        real* V = q.V;
+        real* w = q.w;
+        if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-q.beta[k - 1]), w, n, true, stream));
+        RET(gdots(V + (size_t)k * n, n, 1, w, n));
+        RET(read_scalars(d_dots.as<real>(), 1, s));
+        q.alpha.push_back(s[0]);
+        LAUNCH(1, rbl::scale_copy<real>(V + (size_t)k * n, (real)(-s[0]), w, n, true, stream));
+        RET(gdots(V, n, k + 1, w, n));
+        LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>(), (real)-1, w, n, stream));
+        double bn = 0;
+        RET(dev_norm(w, n, &bn));
+        q.k = k + 1;
+        lanczos_coeffs(q.alpha, q.beta, q.k, q.wnorm, q.y);
+        double diff = 0, nrm = 0;
+        for (int i = 0; i < q.k; ++i) {
+          const double d = q.y[i] - (i < (int)q.y_prev.size() ? q.y_prev[i] : 0.0);
+          diff += d * d;
+          nrm += q.y[i] * q.y[i];
+        }
+        q.y_prev = q.y;
+        const bool converged = q.k > 1 && std::sqrt(diff) <= tol * std::sqrt(nrm);
+        if (converged || bn <= 1e-14 * q.wnorm || q.k == m) {
+          q.done = true;
+          continue;
+        }
+        q.beta.push_back(bn);
+        LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / bn), V + (size_t)q.k * n, n, false, stream));
+      }
+    }
+    for (int r = 0; r < 2; ++r) {
+      auto& q = R[r];
+      iters2[r] = q.k;
+      if (q.wnorm == 0) continue;
+      std::vector<real> coef(q.k);
+      for (int i = 0; i < q.k; ++i) coef[i] = (real)q.y[i];
+      RET(h2d(d_coef.p, coef.data(), q.k * sizeof(real)));
+      CK(cudaMemsetAsync(q.out, 0, n * sizeof(real), stream));
+      LAUNCH(1, rbl::multi_axpy<real>(q.V, n, q.k, d_coef.as<real>(), (real)1, q.out, n, stream));
+      CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
+    }
+    return RBL_OK;
+  }
+
   // ---- Brownian-dynamics step (see rbl_bd_step in include/rbl.h) -------------------------------
   int kinv_dev(const real* v3n, real* out6) {  // out = (K^T K)^-1 K^T v   (:390,406)
     LAUNCH(1, rbl::kt_dot<real>(v3n, d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, out6, stream));
@@ -1033,12 +1249,18 @@ struct Ctx final : rbl_ctx {
       real* noise = d_noise.as<real>();
       int it = 0;
       // Brownian increments at q^n  (M_half_W, :661-675, via Lanczos)
-      RET(h2d(noise, W1, n3 * sizeof(real)));
-      RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it));
-      last_lanczos[0] = it;
-      RET(h2d(noise, W2, n3 * sizeof(real)));
-      RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it));
-      last_lanczos[1] = it;
+      if (pair_lanczos) {
+        RET(h2d(noise, W1, n3 * sizeof(real)));
+        RET(h2d(d_rfd.p, W2, n3 * sizeof(real)));  // d_rfd is free until the RFD below
+        RET(dev_lanczos2(noise, d_rfd.as<real>(), d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos));
+      } else {
+        RET(h2d(noise, W1, n3 * sizeof(real)));
+        RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it));
+        last_lanczos[0] = it;
+        RET(h2d(noise, W2, n3 * sizeof(real)));
+        RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it));
+        last_lanczos[1] = it;
+      }
       // random finite difference  (M_RFD, :769-796)
       const double delta = sizeof(real) == 8 ? 1.0e-4 : 4.0e-3;
       RET(h2d(noise, Wr, n3 * sizeof(real)));
@@ -1247,6 +1469,34 @@ int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W
   return s;
 }
 
+int rbl_apply_M2(rbl_ctx* ctx, const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->apply_M2(F1, F2, r, n, out1, out2);
+}
+int rbl_dev_apply_M2(rbl_ctx* ctx, const void* dF1, const void* dF2, const void* dr, int n, void* dout1, void* dout2) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->dev_apply_M2(dF1, dF2, dr, n, dout1, dout2);
+}
+int rbl_lanczos_sqrt2(rbl_ctx* ctx, const void* W1, const void* W2, void* out1, void* out2, double tol, int max_iter,
+                      int* iters2) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int it[2] = {0, 0};
+  int s = ctx->lanczos2(W1, W2, out1, out2, tol, max_iter, it);
+  if (iters2) { iters2[0] = it[0]; iters2[1] = it[1]; }
+  return s;
+}
+int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
+int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }
+int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {
+  if (!ctx || !T || !threads) return RBL_ERR_INVALID;
+  return ctx->sym2_variant_info(idx, T, threads);
+}
+int rbl_set_sym2_variant(rbl_ctx* ctx, int idx) {
+  CTX_OR_FAIL(ctx);
+  if (idx >= ctx->num_sym2_variants()) return ctx->fail(RBL_ERR_INVALID, "no such two-right-hand-side variant");
+  ctx->sym2_variant = idx < 0 ? -1 : idx;
+  return RBL_OK;
+}
 int rbl_dev_apply_M(rbl_ctx* ctx, const void* dF, const void* dr, int n, int t0, int nt, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->dev_apply_M(dF, dr, n, t0, nt, dout); }
 int rbl_dev_blob_positions(rbl_ctx* ctx, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->blob_positions(dout, true); }
 int rbl_dev_K_dot(rbl_ctx* ctx, const void* dU, void* dout) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->K_dot(dU, dout, true); }

@@ -163,13 +163,13 @@ __device__ __forceinline__ float to_float_up(double v) { return __double2float_r
 
 template <typename real>
 __global__ void tile_boxes_kernel(const real* __restrict__ rec, int first, int count,
-                                  int tile, float* __restrict__ boxes) {
+                                  int tile, float* __restrict__ boxes, int stride) {
   const int t = blockIdx.x;
   const int lo = t * tile;
   const int hi = min(lo + tile, count);
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) {
-    const real* p = rec + (size_t)(first + k) * kRecReals;
+    const real* p = rec + (size_t)(first + k) * stride;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       real v = p[c];
@@ -206,10 +206,10 @@ __global__ void tile_boxes_kernel(const real* __restrict__ rec, int first, int c
 
 template <typename real>
 cudaError_t tile_boxes(const real* rec, int first, int count, int tile, float* boxes,
-                       cudaStream_t s) {
+                       cudaStream_t s, int stride) {
   if (count <= 0) return cudaSuccess;
   int tiles = (count + tile - 1) / tile;
-  tile_boxes_kernel<real><<<tiles, 128, 0, s>>>(rec, first, count, tile, boxes);
+  tile_boxes_kernel<real><<<tiles, 128, 0, s>>>(rec, first, count, tile, boxes, stride);
   return cudaGetLastError();
 }
 
@@ -886,6 +886,403 @@ cudaError_t matvec_sym_launch<double>(int variant, const SymArgs<double>& a, cud
   return cudaErrorInvalidValue;
 }
 
+
+// ----------------------------------------------------------------------------------
+// symmetric kernel, TWO right-hand sides: U1 = B M B F1 and U2 = B M B F2 in one pass.
+// The paired Lanczos of a BD step (M^{1/2}W_1 and M^{1/2}W_2, c_rigid_obj.cpp:930-935) applies
+// M to two vectors per iteration; the geometry of a pair -- distances, both rsqrt, every wall
+// polynomial -- is evaluated once for both (pair_symR).  Same organisation as
+// rpy_matvec_sym_kernel: stream-K over the unordered tile triangle, TMA-staged source tiles,
+// warp-transposed reaction sums, RED.ADD into zeroed accumulators.
+//   record (12 reals): x y z f1x | f1y f1z f2x f2y | f2z -4z^2 0 0
+// ----------------------------------------------------------------------------------
+template <typename real>
+struct Rec2 {
+  real x, y, z, nz4;
+  real f[2][3];
+};
+__device__ __forceinline__ void load_rec2(const float* p, Rec2<float>& r) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  const float4 a = q[0], b = q[1], c = q[2];
+  r.x = a.x; r.y = a.y; r.z = a.z; r.f[0][0] = a.w;
+  r.f[0][1] = b.x; r.f[0][2] = b.y; r.f[1][0] = b.z; r.f[1][1] = b.w;
+  r.f[1][2] = c.x; r.nz4 = c.y;
+}
+__device__ __forceinline__ void load_rec2(const double* p, Rec2<double>& r) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+  r.x = a.x; r.y = a.y; r.z = b.x; r.f[0][0] = b.y;
+  r.f[0][1] = c.x; r.f[0][2] = c.y; r.f[1][0] = d.x; r.f[1][1] = d.y;
+  r.f[1][2] = e.x; r.nz4 = e.y;
+}
+
+template <typename real>
+__global__ void pack_records2_kernel(const real* __restrict__ r, const real* __restrict__ F1,
+                                     const real* __restrict__ F2, int n, int n_padded, int wall, real a,
+                                     real inv_a, real* __restrict__ rec, int* __restrict__ below) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_padded) return;
+  int src = k < n ? k : n - 1;
+  real x = r[3 * (size_t)src], y = r[3 * (size_t)src + 1], z = r[3 * (size_t)src + 2];
+  real f[6] = {0, 0, 0, 0, 0, 0};
+  if (k < n) {
+    real b = wall ? damp(z, a, inv_a) : (real)1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f[c] = b * F1[3 * (size_t)k + c];
+      f[3 + c] = b * F2[3 * (size_t)k + c];
+    }
+    if (wall && z < (real)0) *below = 1;
+  }
+  real* p = rec + (size_t)k * kRec2Reals;
+  p[0] = x; p[1] = y; p[2] = z;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) p[3 + c] = f[c];
+  p[9] = (real)-4 * z * z;
+  p[10] = p[11] = (real)0;
+}
+template <typename real>
+cudaError_t pack_records2(const real* r, const real* F1, const real* F2, int n, int n_padded, bool wall, real a,
+                          real* rec, int* below, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int threads = 256, blocks = (n_padded + threads - 1) / threads;
+  pack_records2_kernel<real><<<blocks, threads, 0, s>>>(r, F1, F2, n, n_padded, wall ? 1 : 0, a, (real)1 / a, rec, below);
+  return cudaGetLastError();
+}
+
+// diagonal tiles (they hold the self pairs): ordered general path, one right-hand side at a time
+template <typename real, bool WALL, int T>
+__device__ __forceinline__ void tile_compute2_ordered(const real* __restrict__ sb, const PairConsts<real>& C,
+                                                      const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
+                                                      real (&u)[T][2][3], int jb, int je) {
+#pragma unroll 1
+  for (int j = jb; j < je; ++j) {
+    Rec2<real> s;
+    load_rec2(sb + (size_t)j * kRec2Reals, s);
+    const real z2 = (real)2 * s.z, zz4 = -s.nz4;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        pair<real, WALL, true>(C, xi[t], yi[t], zi[t], s.x, s.y, s.z, s.f[k][0], s.f[k][1], s.f[k][2], z2, zz4,
+                               u[t][k][0], u[t][k][1], u[t][k][2]);
+    }
+  }
+}
+
+template <typename real, bool WALL, bool NEAR, int T>
+__device__ __forceinline__ void tile_compute_sym2(const real* __restrict__ sb, const PairConsts<real>& C,
+                                                  const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
+                                                  const real (&nz4i)[T], const real (&fi)[T][2][3],
+                                                  real (&u)[T][2][3], real* __restrict__ raw1,
+                                                  real* __restrict__ raw2, int jb, int je) {
+  constexpr bool kTwoLevel = sizeof(real) == 4;
+  const int lane = threadIdx.x & 31;
+  const bool upper = (lane & 16) != 0;
+  real l[T][2][3];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) l[t][k][c] = kTwoLevel ? (real)0 : u[t][k][c];
+  for (int j0 = jb; j0 < je; j0 += 32) {
+    real keep[2][3] = {{0, 0, 0}, {0, 0, 0}};
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      Rec2<real> sa, sb2;
+      load_rec2(sb + (size_t)(j0 + jj) * kRec2Reals, sa);
+      load_rec2(sb + (size_t)(j0 + jj + 16) * kRec2Reals, sb2);
+      real ra[2][3] = {{0, 0, 0}, {0, 0, 0}}, rb[2][3] = {{0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sa.x, sa.y, sa.z, sa.f, sa.nz4, l[t], ra);
+        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sb2.x, sb2.y, sb2.z, sb2.f, sb2.nz4, l[t], rb);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          real kv = upper ? rb[k][c] : ra[k][c];
+          const real sv = upper ? ra[k][c] : rb[k][c];
+          kv += __shfl_xor_sync(0xffffffffu, sv, 16);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) kv += __shfl_xor_sync(0xffffffffu, kv, o);
+          if ((lane & 15) == jj) keep[k][c] = kv;
+        }
+    }
+    real* o1 = raw1 + 3 * (size_t)(j0 + lane);
+    real* o2 = raw2 + 3 * (size_t)(j0 + lane);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(o1 + c, keep[0][c]);
+      atomicAdd(o2 + c, keep[1][c]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u[t][k][c] = kTwoLevel ? u[t][k][c] + l[t][k][c] : l[t][k][c];
+}
+
+template <typename real, bool WALL, int T, int NT>
+__global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real> A) {
+  constexpr int TT = T * NT;
+  constexpr uint32_t kTileBytes = kSrcTile * kRec2Reals * sizeof(real);
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  real* sbuf0 = reinterpret_cast<real*>(smem_dyn);
+  real* sbuf1 = sbuf0 + kSrcTile * kRec2Reals;
+  __shared__ __align__(8) unsigned long long mbar[2];
+
+  const int tid = threadIdx.x;
+  const int ns = A.plan.n_src_tiles, D = A.plan.diag, ntt = A.plan.n_tgt_tiles;
+  const long long span = A.plan.u1 - A.plan.u0;
+  const long long f0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
+  const long long f1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
+  if (f0 >= f1) return;
+  const long long g0 = f0 / kSymChunks, g_last = (f1 - 1) / kSymChunks, g1 = g_last + 1;
+  const int jb_first = (int)(f0 - g0 * kSymChunks) * 32;
+  const int je_last = (int)(f1 - 1 - g_last * kSymChunks + 1) * 32;
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  int I;
+  {
+    int lo = 0, hi = ntt - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sym_row_offset(mid, ns, D) <= g0) lo = mid; else hi = mid - 1;
+    }
+    I = lo;
+  }
+  int J = I * D + (int)(g0 - sym_row_offset(I, ns, D));
+  if (tid == 0) {
+    mbar_expect_tx(&mbar[0], kTileBytes);
+    tma_load_1d(sbuf0, A.rec + (size_t)J * kSrcTile * kRec2Reals, kTileBytes, &mbar[0]);
+  }
+
+  real xi[T], yi[T], zi[T], nz4i[T], fi[T][2][3], u[T][2][3];
+  bool fresh = true;
+  const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
+  const size_t raw_ld = 3 * (size_t)ns * kSrcTile;
+
+  for (long long g = g0; g < g1; ++g) {
+    const int it = (int)(g - g0);
+    const int buf = it & 1;
+    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+    const bool row_end = (J + 1 == ns);
+    const int jb = (g == g0) ? jb_first : 0;
+    const int je = (g == g_last) ? je_last : kSrcTile;
+    real* cur = buf ? sbuf1 : sbuf0;
+    real* nxt = buf ? sbuf0 : sbuf1;
+
+    if (tid == 0 && g + 1 < g1) {
+      const int nJ = row_end ? (I + 1) * D : J + 1;
+      mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
+      tma_load_1d(nxt, A.rec + (size_t)nJ * kSrcTile * kRec2Reals, kTileBytes, &mbar[buf ^ 1]);
+    }
+
+    if (fresh) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        int li = I * TT + tid + t * NT;
+        const bool pad = li >= A.plan.n;
+        if (pad) li = A.plan.n - 1;
+        Rec2<real> me;
+        load_rec2(A.rec + (size_t)li * kRec2Reals, me);
+        xi[t] = me.x; yi[t] = me.y; zi[t] = me.z; nz4i[t] = me.nz4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            fi[t][k][c] = pad ? (real)0 : me.f[k][c];
+            u[t][k][c] = (real)0;
+          }
+      }
+      fresh = false;
+    }
+
+    const bool far = box_gap2(A.box_tgt + 6 * (size_t)I, A.box_src + 6 * (size_t)J) > near2;
+    const bool diagonal = J < (I + 1) * D;
+
+    mbar_wait(&mbar[buf], parity);
+    if (diagonal) {
+      tile_compute2_ordered<real, WALL, T>(cur, A.C, xi, yi, zi, u, jb, je);
+    } else {
+      real* raw1 = A.raw + 3 * (size_t)J * kSrcTile;
+      real* raw2 = raw1 + raw_ld;
+      if (far)
+        tile_compute_sym2<real, WALL, false, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
+      else
+        tile_compute_sym2<real, WALL, true, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
+    }
+    __syncthreads();
+
+    if (row_end || g + 1 == g1) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int li = I * TT + tid + t * NT;
+        if (li < A.plan.n) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) atomicAdd(A.raw + k * raw_ld + 3 * (size_t)li + c, u[t][k][c]);
+        }
+      }
+      fresh = true;
+    }
+    if (row_end) {
+      ++I;
+      J = I * D;
+    } else {
+      ++J;
+    }
+  }
+}
+
+template <typename real, bool WALL>
+__global__ void rpy_sym2_scale_kernel(const Sym2Args<real> A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.plan.n) return;
+  real sc = A.C.out_scale;
+  if (WALL) sc *= damp(A.rec[(size_t)i * kRec2Reals + 2], A.C.a, A.C.inv_a);
+  const size_t raw_ld = 3 * (size_t)A.plan.n_src_tiles * kSrcTile;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    A.out1[3 * (size_t)i + c] = A.raw[3 * (size_t)i + c] * sc;
+    A.out2[3 * (size_t)i + c] = A.raw[raw_ld + 3 * (size_t)i + c] * sc;
+  }
+}
+
+#define RBL_F32_SYM2_VARIANTS(X) X(4, 256) X(2, 256) X(4, 128) X(1, 256)
+#define RBL_F64_SYM2_VARIANTS(X) X(2, 256) X(2, 128) X(1, 256)
+
+template <>
+int matvec_sym2_num_variants<float>() { return 4; }
+template <>
+int matvec_sym2_num_variants<double>() { return 3; }
+template <>
+MatvecVariant matvec_sym2_variant<float>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F32_SYM2_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+template <>
+MatvecVariant matvec_sym2_variant<double>(int idx) {
+  static const MatvecVariant v[] = {
+#define X(T, NT) {T, NT},
+      RBL_F64_SYM2_VARIANTS(X)
+#undef X
+  };
+  return v[idx];
+}
+template <>
+int matvec_sym2_default_variant<float>(bool, int n) { return n < 16384 ? 3 : 0; }
+template <>
+int matvec_sym2_default_variant<double>(bool, int n) { return n < 16384 ? 2 : 0; }
+
+template <typename real>
+constexpr size_t sym2_smem_bytes() { return 2 * (size_t)kSrcTile * kRec2Reals * sizeof(real); }
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t sym2_occupancy_of(int* bps) {
+  cudaError_t e = cudaFuncSetAttribute(rpy_matvec_sym2_kernel<real, WALL, T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sym2_smem_bytes<real>());
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym2_kernel<real, WALL, T, NT>, NT,
+                                                       sym2_smem_bytes<real>());
+}
+template <typename real>
+static cudaError_t sym2_variant_occupancy(int variant, bool wall, int* bps);
+template <>
+cudaError_t sym2_variant_occupancy<float>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return wall ? sym2_occupancy_of<float, true, T, NT>(bps) : sym2_occupancy_of<float, false, T, NT>(bps);
+  RBL_F32_SYM2_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t sym2_variant_occupancy<double>(int variant, bool wall, int* bps) {
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return wall ? sym2_occupancy_of<double, true, T, NT>(bps) : sym2_occupancy_of<double, false, T, NT>(bps);
+  RBL_F64_SYM2_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+template <typename real>
+cudaError_t matvec_sym2_plan(int variant, bool wall, int n, int part, int n_parts, int sm_count, SymPlan* plan) {
+  if (variant < 0 || variant >= matvec_sym2_num_variants<real>() || n_parts < 1 || part < 0 || part >= n_parts)
+    return cudaErrorInvalidValue;
+  const MatvecVariant v = matvec_sym2_variant<real>(variant);
+  int bps = 0;
+  cudaError_t e = sym2_variant_occupancy<real>(variant, wall, &bps);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) return cudaErrorLaunchOutOfResources;
+  plan->n = n;
+  plan->n_src_tiles = (n + kSrcTile - 1) / kSrcTile;
+  plan->tgt_tile = v.T * v.threads;
+  plan->diag = plan->tgt_tile / kSrcTile;
+  plan->n_tgt_tiles = (n + plan->tgt_tile - 1) / plan->tgt_tile;
+  plan->units = sym_row_offset(plan->n_tgt_tiles, plan->n_src_tiles, plan->diag);
+  const long long fine = plan->units * kSymChunks;
+  plan->u0 = fine * part / n_parts;
+  plan->u1 = fine * (part + 1) / n_parts;
+  plan->grid = sm_count * bps;
+  return cudaSuccess;
+}
+
+template <typename real, bool WALL, int T, int NT>
+static cudaError_t sym2_launch_one(const Sym2Args<real>& a, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
+  static_assert((T * NT) % kSrcTile == 0, "target tile must be a multiple of the source tile");
+  cudaError_t e = cudaMemsetAsync(a.raw, 0, 2 * 3 * (size_t)a.plan.n_src_tiles * kSrcTile * sizeof(real), s);
+  if (e != cudaSuccess) return e;
+  if (ev0) cudaEventRecord(ev0, s);
+  if (a.plan.u1 > a.plan.u0)
+    rpy_matvec_sym2_kernel<real, WALL, T, NT><<<a.plan.grid, NT, sym2_smem_bytes<real>(), s>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (ev1) cudaEventRecord(ev1, s);
+  rpy_sym2_scale_kernel<real, WALL><<<(a.plan.n + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <>
+cudaError_t matvec_sym2_launch<float>(int variant, const Sym2Args<float>& a, cudaStream_t s, cudaEvent_t ev0,
+                                      cudaEvent_t ev1) {
+  if (a.plan.n <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return a.wall ? sym2_launch_one<float, true, T, NT>(a, s, ev0, ev1) : sym2_launch_one<float, false, T, NT>(a, s, ev0, ev1);
+  RBL_F32_SYM2_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t matvec_sym2_launch<double>(int variant, const Sym2Args<double>& a, cudaStream_t s, cudaEvent_t ev0,
+                                       cudaEvent_t ev1) {
+  if (a.plan.n <= 0) return cudaSuccess;
+  int k = 0;
+#define X(T, NT) \
+  if (variant == k++) return a.wall ? sym2_launch_one<double, true, T, NT>(a, s, ev0, ev1) : sym2_launch_one<double, false, T, NT>(a, s, ev0, ev1);
+  RBL_F64_SYM2_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 // ----------------------------------------------------------------------------------
 // FMA-pipe peak microbenchmark: 16 independent FMA chains per thread, register operands
 // ----------------------------------------------------------------------------------
@@ -924,7 +1321,9 @@ cudaError_t fma_peak_launch(int sm_count, int iters, real* sink, double* flops,
                                           real*, int*, cudaStream_t);                      \
   template cudaError_t repack_forces<real>(const real*, int, bool, real, real*,            \
                                            cudaStream_t);                                  \
-  template cudaError_t tile_boxes<real>(const real*, int, int, int, float*, cudaStream_t); \
+  template cudaError_t tile_boxes<real>(const real*, int, int, int, float*, cudaStream_t, int); \
+  template cudaError_t pack_records2<real>(const real*, const real*, const real*, int, int, bool, real, real*, int*, cudaStream_t); \
+  template cudaError_t matvec_sym2_plan<real>(int, bool, int, int, int, int, SymPlan*);      \
   template cudaError_t matvec_sym_plan<real>(int, bool, int, int, int, int, SymPlan*);           \
   template cudaError_t fma_peak_launch<real>(int, int, real*, double*, cudaStream_t);
 INST(float)

@@ -77,7 +77,7 @@ cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec,
 // Axis-aligned boxes of consecutive groups of `tile` records starting at `first`.
 template <typename real>
 cudaError_t tile_boxes(const real* rec, int first, int count, int tile, float* boxes,
-                       cudaStream_t s);
+                       cudaStream_t s, int stride = kRecReals);
 
 // The product itself: matvec kernel + deterministic fix-up of split target tiles.
 // If ev0/ev1 are non-null they are recorded immediately around the main kernel (the
@@ -130,6 +130,40 @@ cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts
 template <typename real>
 cudaError_t matvec_sym_launch(int variant, const SymArgs<real>& args, cudaStream_t s,
                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+
+// ---- symmetric product with TWO right-hand sides ------------------------------------------
+// U1 = B M B F1 and U2 = B M B F2 in one pass over the unordered pairs: the geometry of a pair
+// (the larger half of its cost) is evaluated once for both.  Used by the paired Lanczos of a
+// BD step.  Record: 12 reals  x y z f1x | f1y f1z f2x f2y | f2z -4z^2 0 0.
+constexpr int kRec2Reals = 12;
+
+template <typename real>
+struct Sym2Args {
+  const real* rec;   // (n_src_tiles * kSrcTile) x 12
+  const float* box_src;
+  const float* box_tgt;
+  real* raw;         // 2 x (3 * n_src_tiles * kSrcTile) accumulators, zeroed by the launcher
+  real* out1;        // 3 * n
+  real* out2;        // 3 * n
+  SymPlan plan;
+  PairConsts<real> C;
+  int wall;
+};
+
+template <typename real>
+cudaError_t pack_records2(const real* r, const real* F1, const real* F2, int n, int n_padded, bool wall, real a,
+                          real* rec, int* below_wall_flag, cudaStream_t s);
+template <typename real>
+int matvec_sym2_num_variants();
+template <typename real>
+MatvecVariant matvec_sym2_variant(int idx);
+template <typename real>
+int matvec_sym2_default_variant(bool wall, int n);
+template <typename real>
+cudaError_t matvec_sym2_plan(int variant, bool wall, int n, int part, int n_parts, int sm_count, SymPlan* plan);
+template <typename real>
+cudaError_t matvec_sym2_launch(int variant, const Sym2Args<real>& args, cudaStream_t s,
+                               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 
 // FMA-pipe peak microbenchmark (the roofline denominator SURVEY.md section 8d asks for).
 // Returns flop executed; time it with events around the call.

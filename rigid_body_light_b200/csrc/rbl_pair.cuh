@@ -289,4 +289,103 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
   }
 }
 
+// pair_sym for R right-hand sides at once (block Lanczos: M^{1/2}W_1 and M^{1/2}W_2 of one BD
+// step share every product).  Everything that depends only on the geometry -- ~51 of the ~93
+// issue slots of pair_sym with the wall, including both rsqrt -- is computed once; only the dot
+// products with the forces and the accumulation are repeated per right-hand side.
+//   fi[k], fj[k]: damped forces of right-hand side k;  ui[k], uj[k]: accumulators.
+template <typename real, bool WALL, bool NEAR, int R>
+RBL_HD void pair_symR(const PairConsts<real>& C, real xi, real yi, real zi, const real (&fi)[R][3], real nzz4i,
+                      real xj, real yj, real zj, const real (&fj)[R][3], real nzz4j, real (&ui)[R][3],
+                      real (&uj)[R][3]) {
+  const real dx = xi - xj, dy = yi - yj, dz = zi - zj;
+  const real q = fma_(dy, dy, fma_(dx, dx, C.tiny));
+  const real r2 = fma_(dz, dz, q);
+  const real invr = rsqrt_fast(r2);
+  const real i2 = invr * invr;
+  const real i3 = invr * i2;
+  real c1 = fma_(i3, C.c23a2, invr);
+  real c2 = fma_(i2 * i3, C.m2a2, i3);
+  if (NEAR) {
+    const real r = r2 * invr;
+    const real c1n = fma_(r, C.n1, C.n0);
+    const real c2n = invr * C.n2;
+    const bool nr = r2 < C.four_a2;
+    c1 = nr ? c1n : c1;
+    c2 = nr ? c2n : c2;
+  }
+  if (!WALL) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const real sj = fma_(dy, fj[k][1], dx * fj[k][0]);
+      const real si = fma_(dy, fi[k][1], dx * fi[k][0]);
+      const real tj = c2 * fma_(dz, fj[k][2], sj);
+      const real ti = c2 * fma_(dz, fi[k][2], si);
+      ui[k][0] = fma_(c1, fj[k][0], ui[k][0]); ui[k][0] = fma_(tj, dx, ui[k][0]);
+      ui[k][1] = fma_(c1, fj[k][1], ui[k][1]); ui[k][1] = fma_(tj, dy, ui[k][1]);
+      ui[k][2] = fma_(c1, fj[k][2], ui[k][2]); ui[k][2] = fma_(tj, dz, ui[k][2]);
+      uj[k][0] = fma_(c1, fi[k][0], uj[k][0]); uj[k][0] = fma_(ti, dx, uj[k][0]);
+      uj[k][1] = fma_(c1, fi[k][1], uj[k][1]); uj[k][1] = fma_(ti, dy, uj[k][1]);
+      uj[k][2] = fma_(c1, fi[k][2], uj[k][2]); uj[k][2] = fma_(ti, dz, uj[k][2]);
+    }
+  } else {
+    const real Z = zi + zj;
+    const real Z2 = Z * Z;
+    const real R2 = q + Z2;
+    const real w = rsqrt_fast(R2);
+    const real W = w * w;
+    const real E = Z2 * W;
+    const real p = (zi * zj) * W;
+    const real k1 = fma_(E, C.k1a, C.k1b);
+    const real k2 = fma_(E, C.k2a, C.k2b);
+    const real a1n = fma_(fma_(k2, W, k1), W, fma_(p, (real)-2, (real)-1));
+    const real m1 = fma_(E, C.m1a, C.m1b);
+    const real m2 = fma_(E, C.m2a, C.m2b);
+    const real wW = w * W;
+    const real a2w = wW * fma_(fma_(m2, W, m1), W, fma_(p, (real)6, (real)-1));  // wW a2n
+    const real ZW = Z * W;
+    const real q1 = fma_(E, C.q1a, C.q1b);
+    const real q2 = fma_(E, C.q2a, C.q2b);
+    const real nZWh3 = -ZW * fma_(q2, W, q1);
+    const real cZW2 = (ZW * W) * C.a4c;
+    const real o1 = fma_(E, C.o1a, C.o1b);
+    const real nS5 = fma_(o1, W, -(E * C.fa2));
+    const real cF = fma_(w, a1n, c1);
+    // geometry-only coefficients of the two directions, pre-multiplied by wW
+    const real a3j = wW * fma_(zj, fma_(zi * ZW, (real)-12, (real)2), nZWh3);  // i <- j
+    const real a4j = wW * fma_(zj, (real)2, cZW2);
+    const real a5j = wW * (nzz4j + nS5);
+    const real a3i = wW * fma_(zi, fma_(zj * ZW, (real)-12, (real)2), nZWh3);  // j <- i
+    const real a4i = wW * fma_(zi, (real)2, cZW2);
+    const real a5i = wW * (nzz4i + nS5);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const real sj = fma_(dy, fj[k][1], dx * fj[k][0]);
+      const real si = fma_(dy, fi[k][1], dx * fi[k][0]);
+      const real tj = c2 * fma_(dz, fj[k][2], sj);
+      const real ti = c2 * fma_(dz, fi[k][2], si);
+      const real gj = fma_(Z, fj[k][2], sj);
+      const real gi = fma_(Z, fi[k][2], -si);
+      {
+        const real A = fma_(a3j, fj[k][2], a2w * gj);
+        const real Bz = fma_(a5j, fj[k][2], a4j * gj);
+        const real txy = tj + A;
+        ui[k][0] = fma_(cF, fj[k][0], ui[k][0]); ui[k][0] = fma_(txy, dx, ui[k][0]);
+        ui[k][1] = fma_(cF, fj[k][1], ui[k][1]); ui[k][1] = fma_(txy, dy, ui[k][1]);
+        ui[k][2] = fma_(cF, fj[k][2], ui[k][2]); ui[k][2] = fma_(tj, dz, ui[k][2]);
+        ui[k][2] = fma_(A, Z, ui[k][2]); ui[k][2] += Bz;
+      }
+      {
+        const real A = fma_(a3i, fi[k][2], a2w * gi);
+        const real Bz = fma_(a5i, fi[k][2], a4i * gi);
+        const real txy = ti - A;
+        uj[k][0] = fma_(cF, fi[k][0], uj[k][0]); uj[k][0] = fma_(txy, dx, uj[k][0]);
+        uj[k][1] = fma_(cF, fi[k][1], uj[k][1]); uj[k][1] = fma_(txy, dy, uj[k][1]);
+        uj[k][2] = fma_(cF, fi[k][2], uj[k][2]); uj[k][2] = fma_(ti, dz, uj[k][2]);
+        uj[k][2] = fma_(A, Z, uj[k][2]); uj[k][2] += Bz;
+      }
+    }
+  }
+}
+
 }  // namespace rbl

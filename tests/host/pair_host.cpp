@@ -93,3 +93,48 @@ static void matvec_sym(const real* F, const real* r, int n, double a, double eta
 }
 extern "C" void pair_matvec_sym_host_f64(const double* F, const double* r, int n, double a, double eta, int wall, int near, double* U) { matvec_sym<double>(F, r, n, a, eta, wall, near, U); }
 extern "C" void pair_matvec_sym_host_f32(const float* F, const float* r, int n, double a, double eta, int wall, int near, float* U) { matvec_sym<float>(F, r, n, a, eta, wall, near, U); }
+
+// two right-hand sides per unordered pair through pair_symR<.., 2> (the arithmetic of the
+// two-right-hand-side symmetric kernel): U1 = M F1, U2 = M F2
+template <typename real>
+static void matvec_sym2(const real* F1, const real* F2, const real* r, int n, double a, double eta, int wall, int near,
+                        real* U1, real* U2) {
+  rbl::PairConsts<real> C = rbl::make_pair_consts<real>(a, eta);
+  std::vector<real> f(6 * (size_t)n), acc(6 * (size_t)n, 0);
+  for (int j = 0; j < n; ++j) {
+    real zj = r[3 * j + 2];
+    real bj = wall ? (zj >= (real)a ? (real)1 : zj * C.inv_a) : (real)1;
+    for (int c = 0; c < 3; ++c) { f[6 * j + c] = bj * F1[3 * j + c]; f[6 * j + 3 + c] = bj * F2[3 * j + c]; }
+  }
+  for (int i = 0; i < n; ++i) {
+    real zi = r[3 * i + 2];
+    for (int k = 0; k < 2; ++k) {  // self term: ordered general path, one right-hand side at a time
+      real* u = &acc[6 * i + 3 * k];
+      const real* fk = &f[6 * i + 3 * k];
+      if (wall) rbl::pair<real, true, true>(C, r[3*i], r[3*i+1], zi, r[3*i], r[3*i+1], zi, fk[0], fk[1], fk[2], 2*zi, 4*zi*zi, u[0], u[1], u[2]);
+      else      rbl::pair<real, false, true>(C, r[3*i], r[3*i+1], zi, r[3*i], r[3*i+1], zi, fk[0], fk[1], fk[2], 2*zi, 4*zi*zi, u[0], u[1], u[2]);
+    }
+    for (int j = i + 1; j < n; ++j) {
+      real zj = r[3 * j + 2];
+      real fi[2][3], fj[2][3], ui[2][3], uj[2][3];
+      for (int k = 0; k < 2; ++k)
+        for (int c = 0; c < 3; ++c) {
+          fi[k][c] = f[6 * i + 3 * k + c]; fj[k][c] = f[6 * j + 3 * k + c];
+          ui[k][c] = acc[6 * i + 3 * k + c]; uj[k][c] = acc[6 * j + 3 * k + c];
+        }
+#define ARGS r[3*i], r[3*i+1], zi, fi, -4*zi*zi, r[3*j], r[3*j+1], zj, fj, -4*zj*zj, ui, uj
+      if (wall) { if (near) rbl::pair_symR<real, true, true, 2>(C, ARGS); else rbl::pair_symR<real, true, false, 2>(C, ARGS); }
+      else      { if (near) rbl::pair_symR<real, false, true, 2>(C, ARGS); else rbl::pair_symR<real, false, false, 2>(C, ARGS); }
+#undef ARGS
+      for (int k = 0; k < 2; ++k)
+        for (int c = 0; c < 3; ++c) { acc[6 * i + 3 * k + c] = ui[k][c]; acc[6 * j + 3 * k + c] = uj[k][c]; }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    real zi = r[3 * i + 2];
+    real bi = wall ? (zi >= (real)a ? (real)1 : zi * C.inv_a) : (real)1;
+    for (int c = 0; c < 3; ++c) { U1[3 * i + c] = acc[6 * i + c] * C.out_scale * bi; U2[3 * i + c] = acc[6 * i + 3 + c] * C.out_scale * bi; }
+  }
+}
+extern "C" void pair_matvec_sym2_host_f64(const double* F1, const double* F2, const double* r, int n, double a, double eta, int wall, int near, double* U1, double* U2) { matvec_sym2<double>(F1, F2, r, n, a, eta, wall, near, U1, U2); }
+extern "C" void pair_matvec_sym2_host_f32(const float* F1, const float* F2, const float* r, int n, double a, double eta, int wall, int near, float* U1, float* U2) { matvec_sym2<float>(F1, F2, r, n, a, eta, wall, near, U1, U2); }

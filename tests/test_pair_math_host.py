@@ -100,3 +100,25 @@ def test_symmetric_pair_evaluation_float(host_lib, orc, name):
     want = orc.apply_M(f32.astype(np.float64), r32.astype(np.float64), a, eta, wall)
     u = _host_matvec(host_lib, f32, r32, a, eta, int(wall), 1, np.float32, sym=True)
     assert rel_err(u, want) < TOL["single"]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_two_rhs_symmetric_pair_evaluation(host_lib, orc, name, dt):
+    """pair_symR<2>: the geometry of an unordered pair evaluated once and applied to two force
+    vectors in both directions (the two-right-hand-side kernel behind the paired Lanczos of the
+    BD step) gives the two products."""
+    g = load_golden(name)
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    r = np.ascontiguousarray(g["r"].astype(dt)).reshape(-1)
+    F1 = np.ascontiguousarray(g["lam"].astype(dt)).reshape(-1)
+    F2 = np.ascontiguousarray(np.random.default_rng(7).standard_normal(F1.size).astype(dt))
+    U1, U2 = np.empty_like(F1), np.empty_like(F2)
+    fn = getattr(host_lib, "pair_matvec_sym2_host_" + ("f64" if dt == np.float64 else "f32"))
+    p = lambda v: ctypes.c_void_p(v.ctypes.data)  # noqa: E731
+    fn(p(F1), p(F2), p(r), ctypes.c_int(r.size // 3), ctypes.c_double(a), ctypes.c_double(eta), ctypes.c_int(wall),
+       ctypes.c_int(1), p(U1), p(U2))
+    tol = TOL["double"] if dt == np.float64 else TOL["single"]
+    for F, U in ((F1, U1), (F2, U2)):
+        want = orc.apply_M(F.astype(np.float64), r.astype(np.float64), a, eta, wall)
+        assert rel_err(U, want) < tol
