@@ -10,7 +10,9 @@ operator [M lam - K U ; K^T lam], i.e. one wall-corrected RPY mobility product B
 N^2 = 2.6244e10 ordered blob pairs plus the K / K^T products.  Metric: ordered blob-pair
 interactions per second (whole job).  Strong scaling: bodies are partitioned over the ranks,
 lambda is all-gathered over NCCL each step, the pair work is split in equal shares and the
-partial products are all-reduced.
+partial products are reduce-scattered.  `bd_step`: BASELINE.json's second metric, one full
+fluctuating rigid BD step on configs[2]'s suspension partitioned over the ranks (NCCL inside
+librbl), seconds per step.
 
 `value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
 `e2e`     : the same step through the host-buffer C ABI (rbl_apply_saddle at N=1; pinned
@@ -285,7 +287,7 @@ def run_ours(args):
                                         + ("74.4" if precision == "single" else "37.2") + " TFLOP/s at 148 SM x 1.965 GHz"},
             "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()),
             "comm_ms_per_step": None if comm is None else {"allgather_lambda": comm[0], "product_incl_pack": comm[1],
-                                                            "allreduce_partials": comm[2],
+                                                            "reduce_partials": comm[2],
                                                             "note": "CUDA events per step, max over ranks; a rank that "
                                                                     "finishes its share early waits inside the collective"},
         }
@@ -313,7 +315,7 @@ def run_ours(args):
                                    f"{'above a wall' if wall else 'in free space'} = {n_all} blobs; step = apply_saddle "
                                    f"(wall-corrected RPY matvec + K + K^T)",
                        "pairs_per_step": pairs, "parallelism": f"x{world}: bodies in contiguous ranges; NCCL all-gather of lambda, equal shares of the "
-                                      f"unordered-pair tile triangle per rank, all-reduce of the partial products",
+                                      f"unordered-pair tile triangle per rank, reduce-scatter of the partial products",
                        "l2": "256 MiB memset between steps inside the timed region (inputs < L2)",
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],

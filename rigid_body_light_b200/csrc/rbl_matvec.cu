@@ -1186,8 +1186,10 @@ MatvecVariant matvec_sym2_variant<double>(int idx) {
   };
   return v[idx];
 }
+// measured on B200 at 172 032 blobs with the wall (profiles/r01_sym2_sweep_cfg3.jsonl): fp32 (4,128)
+// 75.96 ms, (4,256) 76.56 ms; fp64 (2,256) 148.7 ms -- against 102.2 / 196.1 ms for two single passes
 template <>
-int matvec_sym2_default_variant<float>(bool, int n) { return n < 16384 ? 3 : 0; }
+int matvec_sym2_default_variant<float>(bool, int n) { return n < 16384 ? 3 : 2; }
 template <>
 int matvec_sym2_default_variant<double>(bool, int n) { return n < 16384 ? 2 : 0; }
 

@@ -6,8 +6,8 @@ rank-local.  The mobility product needs every source, so each application all-ga
 constraint forces lambda (3N reals) over NCCL/NVLink; the O(N^2) work itself is the upper
 triangle of the tile grid of the SYMMETRIC kernel, cut into ``world`` equal contiguous shares
 (``rbl_dev_apply_M_part``): every rank produces a partial product over all blobs, the partial
-products are summed with one all-reduce (3N reals), and each rank finishes its own rows with
-its local K and K^T (``rbl_dev_saddle_finish``).  Blob positions are all-gathered once per
+products are summed with one reduce-scatter (NCCL, equal shards; an all-reduce otherwise) of 3N
+reals, and each rank finishes its own rows with its local K and K^T (``rbl_dev_saddle_finish``).  Blob positions are all-gathered once per
 configuration, not per application.
 
 The collective plumbing is ``torch.distributed`` (backend "nccl" on GPUs; the same code runs
@@ -106,12 +106,21 @@ class ShardedSaddle:
         self.backend.apply_M_part(self.lam_all, self.r_all, self.n_all, self.rank, self.world, self._mbuf)
         if ev:
             ev[2].record()
-        self.dist.all_reduce(self._mbuf)  # sum of the partial products
+        lo = 3 * self.t0
+        if self.even and self.dist.get_backend() == "nccl":
+            # every rank only needs the sum of ITS rows: reduce-scatter moves half of what an
+            # all-reduce does
+            if getattr(self, "_mine", None) is None:
+                self._mine = self.torch.empty(n3, dtype=self._mbuf.dtype, device=self._mbuf.device)
+            mine = self._mine
+            self.dist.reduce_scatter_tensor(mine, self._mbuf)
+        else:
+            self.dist.all_reduce(self._mbuf)  # uneven shards / gloo: sum of the partial products everywhere
+            mine = self._mbuf[lo:lo + n3]
         if ev:
             ev[3].record()
             self.timing.append(ev)
-        lo = 3 * self.t0
-        self.backend.saddle_finish(self._mbuf[lo:lo + n3], x_local[:n3], x_local[n3:], out_local)
+        self.backend.saddle_finish(mine, x_local[:n3], x_local[n3:], out_local)
         return out_local
 
 
