@@ -126,3 +126,30 @@ def test_bd_step_paired_and_unpaired_lanczos_agree():
         out.append((U, cb.get_config()))
     assert rel_err(out[0][0], out[1][0]) < 1e-9
     assert rel_err(out[0][1][0], out[1][1][0]) < 1e-11
+
+
+def test_full_size_krylov_properties_config3():
+    """BASELINE.json configs[2] size (4096 spheres x shell_N_42 = 172 032 blobs, wall), float:
+    size-independent properties of the Krylov drivers where the dense oracle cannot go --
+    the square root applied twice is the mobility product, the paired run equals itself with the
+    vectors swapped, and the GMRES solution satisfies the saddle system (true residual through an
+    independent operator application)."""
+    from Rigid import RigidBody
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(4096, 42, True)
+    cb = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=True, precision="single")
+    n3, n6 = 3 * 4096 * 42, 6 * 4096
+    rng = np.random.default_rng(17)
+    W1, W2 = rng.standard_normal(n3), rng.standard_normal(n3)
+    y1, y2, k1, k2 = cb.brownian_sqrt_pair(W1, W2, tol=1e-5, max_iter=80)
+    z1, z2, _, _ = cb.brownian_sqrt_pair(y1, y2, tol=1e-5, max_iter=80)
+    r = cb.get_blob_positions()
+    m1, m2 = cb.apply_M2(W1, W2, r)
+    assert rel_err(z1, m1) < 2e-3 and rel_err(z2, m2) < 2e-3
+    s2, s1, j2, j1 = cb.brownian_sqrt_pair(W2, W1, tol=1e-5, max_iter=80)
+    assert (j1, j2) == (k1, k2) and rel_err(s1, y1) < 1e-4 and rel_err(s2, y2) < 1e-4
+    rhs = np.concatenate([np.zeros(n3), rng.standard_normal(n6)]).astype(np.float32)
+    x, it, rr = cb.gmres(rhs, tol=1e-4, restart=60, max_iter=120)
+    assert rr <= 1e-4 and it < 60
+    assert rel_err(cb.apply_saddle(x), rhs) < 5e-4
