@@ -103,52 +103,62 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// One thread per OUTPUT ELEMENT (not per blob): consecutive threads write consecutive reals, so
+// every store instruction fills whole 32-byte sectors (a thread per blob writes 4 of every 12
+// bytes per instruction and reached 0.41 of the HBM peak on B200; profiles/r01_on_kernels_bw*).
+// The quaternion row is recomputed by the three threads of a blob: flops are free here.
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, int n_bod, int n_blb,
+                                   const real* __restrict__ ref, long long n3, int n_blb,
                                    real* __restrict__ r) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_bod * n_blb) return;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  const long long i = e / 3;
+  const int c = (int)(e - 3 * i);
   const int b = (int)(i / n_blb), k = (int)(i - (long long)b * n_blb);
-  real R[9];
-  quat_to_rot(Q + 4 * (size_t)b, R);
-  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
-  r[3 * i + 0] = R[0] * cx + R[1] * cy + R[2] * cz + X[3 * (size_t)b + 0];
-  r[3 * i + 1] = R[3] * cx + R[4] * cy + R[5] * cz + X[3 * (size_t)b + 1];
-  r[3 * i + 2] = R[6] * cx + R[7] * cy + R[8] * cz + X[3 * (size_t)b + 2];
+  const real* q = Q + 4 * (size_t)b;
+  const real w = q[0], x = q[1], y = q[2], z = q[3];
+  // row c of the rotation matrix of [w,x,y,z] (Eigen toRotationMatrix, :258)
+  real r0, r1, r2;
+  if (c == 0) { r0 = 1 - 2 * (y * y + z * z); r1 = 2 * (x * y - w * z); r2 = 2 * (x * z + w * y); }
+  else if (c == 1) { r0 = 2 * (x * y + w * z); r1 = 1 - 2 * (x * x + z * z); r2 = 2 * (y * z - w * x); }
+  else { r0 = 2 * (x * z - w * y); r1 = 2 * (y * z + w * x); r2 = 1 - 2 * (x * x + y * y); }
+  r[e] = r0 * ref[3 * k] + r1 * ref[3 * k + 1] + r2 * ref[3 * k + 2] + X[3 * (size_t)b + c];
 }
 template <typename real>
 cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod, int n_blb,
                         real* r, cudaStream_t s) {
-  const long long n = (long long)n_bod * n_blb;
-  if (n <= 0) return cudaSuccess;
-  place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
+  const long long n3 = 3LL * n_bod * n_blb;
+  if (n3 <= 0) return cudaSuccess;
+  place_blobs_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(X, Q, ref, n3, n_blb, r);
   return cudaGetLastError();
 }
 
+// out[e] = sign (u + omega x rho)[c] (+ add[e]); one thread per output element like place_blobs
 template <typename real>
 __global__ void k_dot_kernel(const real* __restrict__ U, const real* __restrict__ r,
-                             const real* __restrict__ X, int n_bod, int n_blb, real sign,
+                             const real* __restrict__ X, long long n3, int n_blb, real sign,
                              const real* add, real* out) {  // add may alias out
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_bod * n_blb) return;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  const long long i = e / 3;
+  const int c = (int)(e - 3 * i);
   const int b = (int)(i / n_blb);
   const real* u = U + 6 * (size_t)b;
-  const real px = r[3 * i] - X[3 * (size_t)b], py = r[3 * i + 1] - X[3 * (size_t)b + 1],
-             pz = r[3 * i + 2] - X[3 * (size_t)b + 2];
-  real vx = u[0] + (u[4] * pz - u[5] * py);
-  real vy = u[1] + (u[5] * px - u[3] * pz);
-  real vz = u[2] + (u[3] * py - u[4] * px);
-  vx *= sign; vy *= sign; vz *= sign;
-  if (add) { vx += add[3 * i]; vy += add[3 * i + 1]; vz += add[3 * i + 2]; }
-  out[3 * i] = vx; out[3 * i + 1] = vy; out[3 * i + 2] = vz;
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;  // cyclic: (omega x rho)_c = om_c1 rho_c2 - om_c2 rho_c1
+  const real p1 = r[3 * i + c1] - X[3 * (size_t)b + c1];
+  const real p2 = r[3 * i + c2] - X[3 * (size_t)b + c2];
+  real v = u[c] + (u[3 + c1] * p2 - u[3 + c2] * p1);
+  v *= sign;
+  if (add) v += add[e];
+  out[e] = v;
 }
 template <typename real>
 cudaError_t k_dot(const real* U, const real* r, const real* X, int n_bod, int n_blb,
                   real sign, const real* add, real* out, cudaStream_t s) {
-  const long long n = (long long)n_bod * n_blb;
-  if (n <= 0) return cudaSuccess;
-  k_dot_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(U, r, X, n_bod, n_blb, sign, add, out);
+  const long long n3 = 3LL * n_bod * n_blb;
+  if (n3 <= 0) return cudaSuccess;
+  k_dot_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(U, r, X, n3, n_blb, sign, add, out);
   return cudaGetLastError();
 }
 
