@@ -109,13 +109,15 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
 // The quaternion row is recomputed by the three threads of a blob: flops are free here.
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, long long n3, int n_blb,
+                                   const real* __restrict__ ref, unsigned n3, unsigned n_blb,
                                    real* __restrict__ r) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // 32-bit index arithmetic on purpose: two 64-bit divisions per element made this kernel
+  // instruction-bound (3x slower than the stores); the context limits 3N to 2^31-1
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  const long long i = e / 3;
-  const int c = (int)(e - 3 * i);
-  const int b = (int)(i / n_blb), k = (int)(i - (long long)b * n_blb);
+  const unsigned i = e / 3u;
+  const int c = (int)(e - 3u * i);
+  const unsigned b = i / n_blb, k = i - b * n_blb;
   const real* q = Q + 4 * (size_t)b;
   const real w = q[0], x = q[1], y = q[2], z = q[3];
   // row c of the rotation matrix of [w,x,y,z] (Eigen toRotationMatrix, :258)
@@ -130,24 +132,25 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
                         real* r, cudaStream_t s) {
   const long long n3 = 3LL * n_bod * n_blb;
   if (n3 <= 0) return cudaSuccess;
-  place_blobs_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(X, Q, ref, n3, n_blb, r);
+  if (n3 > 0x7fffffffLL) return cudaErrorInvalidValue;
+  place_blobs_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(X, Q, ref, (unsigned)n3, (unsigned)n_blb, r);
   return cudaGetLastError();
 }
 
 // out[e] = sign (u + omega x rho)[c] (+ add[e]); one thread per output element like place_blobs
 template <typename real>
 __global__ void k_dot_kernel(const real* __restrict__ U, const real* __restrict__ r,
-                             const real* __restrict__ X, long long n3, int n_blb, real sign,
+                             const real* __restrict__ X, unsigned n3, unsigned n_blb, real sign,
                              const real* add, real* out) {  // add may alias out
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n3) return;
-  const long long i = e / 3;
-  const int c = (int)(e - 3 * i);
-  const int b = (int)(i / n_blb);
+  const unsigned i = e / 3u;
+  const int c = (int)(e - 3u * i);
+  const unsigned b = i / n_blb;
   const real* u = U + 6 * (size_t)b;
   const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;  // cyclic: (omega x rho)_c = om_c1 rho_c2 - om_c2 rho_c1
-  const real p1 = r[3 * i + c1] - X[3 * (size_t)b + c1];
-  const real p2 = r[3 * i + c2] - X[3 * (size_t)b + c2];
+  const real p1 = r[3u * i + c1] - X[3 * (size_t)b + c1];
+  const real p2 = r[3u * i + c2] - X[3 * (size_t)b + c2];
   real v = u[c] + (u[3 + c1] * p2 - u[3 + c2] * p1);
   v *= sign;
   if (add) v += add[e];
@@ -158,7 +161,8 @@ cudaError_t k_dot(const real* U, const real* r, const real* X, int n_bod, int n_
                   real sign, const real* add, real* out, cudaStream_t s) {
   const long long n3 = 3LL * n_bod * n_blb;
   if (n3 <= 0) return cudaSuccess;
-  k_dot_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(U, r, X, n3, n_blb, sign, add, out);
+  if (n3 > 0x7fffffffLL) return cudaErrorInvalidValue;
+  k_dot_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(U, r, X, (unsigned)n3, (unsigned)n_blb, sign, add, out);
   return cudaGetLastError();
 }
 
