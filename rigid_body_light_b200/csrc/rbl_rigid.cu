@@ -103,66 +103,57 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// One thread per OUTPUT ELEMENT (not per blob): consecutive threads write consecutive reals, so
-// every store instruction fills whole 32-byte sectors (a thread per blob writes 4 of every 12
-// bytes per instruction and reached 0.41 of the HBM peak on B200; profiles/r01_on_kernels_bw*).
-// The quaternion row is recomputed by the three threads of a blob: flops are free here.
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, unsigned n3, unsigned n_blb,
+                                   const real* __restrict__ ref, int n_bod, int n_blb,
                                    real* __restrict__ r) {
-  // 32-bit index arithmetic on purpose: two 64-bit divisions per element made this kernel
-  // instruction-bound (3x slower than the stores); the context limits 3N to 2^31-1
-  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n3) return;
-  const unsigned i = e / 3u;
-  const int c = (int)(e - 3u * i);
-  const unsigned b = i / n_blb, k = i - b * n_blb;
-  const real* q = Q + 4 * (size_t)b;
-  const real w = q[0], x = q[1], y = q[2], z = q[3];
-  // row c of the rotation matrix of [w,x,y,z] (Eigen toRotationMatrix, :258)
-  real r0, r1, r2;
-  if (c == 0) { r0 = 1 - 2 * (y * y + z * z); r1 = 2 * (x * y - w * z); r2 = 2 * (x * z + w * y); }
-  else if (c == 1) { r0 = 2 * (x * y + w * z); r1 = 1 - 2 * (x * x + z * z); r2 = 2 * (y * z - w * x); }
-  else { r0 = 2 * (x * z - w * y); r1 = 2 * (y * z + w * x); r2 = 1 - 2 * (x * x + y * y); }
-  r[e] = r0 * ref[3 * k] + r1 * ref[3 * k + 1] + r2 * ref[3 * k + 2] + X[3 * (size_t)b + c];
+  // 32-bit index arithmetic on purpose: a 64-bit division per blob (a ~100-instruction library
+  // routine) made this kernel instruction-bound at 0.41 of the HBM peak; N < 2^31 is checked by the launcher
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)n_bod * (unsigned)n_blb) return;
+  const unsigned b = i / (unsigned)n_blb, k = i - b * (unsigned)n_blb;
+  real R[9];
+  quat_to_rot(Q + 4 * (size_t)b, R);
+  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
+  r[3 * (size_t)i + 0] = R[0] * cx + R[1] * cy + R[2] * cz + X[3 * (size_t)b + 0];
+  r[3 * (size_t)i + 1] = R[3] * cx + R[4] * cy + R[5] * cz + X[3 * (size_t)b + 1];
+  r[3 * (size_t)i + 2] = R[6] * cx + R[7] * cy + R[8] * cz + X[3 * (size_t)b + 2];
 }
 template <typename real>
 cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod, int n_blb,
                         real* r, cudaStream_t s) {
-  const long long n3 = 3LL * n_bod * n_blb;
-  if (n3 <= 0) return cudaSuccess;
-  if (n3 > 0x7fffffffLL) return cudaErrorInvalidValue;
-  place_blobs_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(X, Q, ref, (unsigned)n3, (unsigned)n_blb, r);
+  const long long n = (long long)n_bod * n_blb;
+  if (n <= 0) return cudaSuccess;
+  if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
+  place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
   return cudaGetLastError();
 }
 
-// out[e] = sign (u + omega x rho)[c] (+ add[e]); one thread per output element like place_blobs
 template <typename real>
 __global__ void k_dot_kernel(const real* __restrict__ U, const real* __restrict__ r,
-                             const real* __restrict__ X, unsigned n3, unsigned n_blb, real sign,
+                             const real* __restrict__ X, int n_bod, int n_blb, real sign,
                              const real* add, real* out) {  // add may alias out
-  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n3) return;
-  const unsigned i = e / 3u;
-  const int c = (int)(e - 3u * i);
-  const unsigned b = i / n_blb;
+  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: see place_blobs_kernel
+  if (iu >= (unsigned)n_bod * (unsigned)n_blb) return;
+  const unsigned b = iu / (unsigned)n_blb;
+  const size_t i = iu;
   const real* u = U + 6 * (size_t)b;
-  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;  // cyclic: (omega x rho)_c = om_c1 rho_c2 - om_c2 rho_c1
-  const real p1 = r[3u * i + c1] - X[3 * (size_t)b + c1];
-  const real p2 = r[3u * i + c2] - X[3 * (size_t)b + c2];
-  real v = u[c] + (u[3 + c1] * p2 - u[3 + c2] * p1);
-  v *= sign;
-  if (add) v += add[e];
-  out[e] = v;
+  const real px = r[3 * i] - X[3 * (size_t)b], py = r[3 * i + 1] - X[3 * (size_t)b + 1],
+             pz = r[3 * i + 2] - X[3 * (size_t)b + 2];
+  real vx = u[0] + (u[4] * pz - u[5] * py);
+  real vy = u[1] + (u[5] * px - u[3] * pz);
+  real vz = u[2] + (u[3] * py - u[4] * px);
+  vx *= sign; vy *= sign; vz *= sign;
+  if (add) { vx += add[3 * i]; vy += add[3 * i + 1]; vz += add[3 * i + 2]; }
+  out[3 * i] = vx; out[3 * i + 1] = vy; out[3 * i + 2] = vz;
 }
 template <typename real>
 cudaError_t k_dot(const real* U, const real* r, const real* X, int n_bod, int n_blb,
                   real sign, const real* add, real* out, cudaStream_t s) {
-  const long long n3 = 3LL * n_bod * n_blb;
-  if (n3 <= 0) return cudaSuccess;
-  if (n3 > 0x7fffffffLL) return cudaErrorInvalidValue;
-  k_dot_kernel<real><<<(unsigned)((n3 + 255) / 256), 256, 0, s>>>(U, r, X, (unsigned)n3, (unsigned)n_blb, sign, add, out);
+  const long long n = (long long)n_bod * n_blb;
+  if (n <= 0) return cudaSuccess;
+  if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
+  k_dot_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(U, r, X, n_bod, n_blb, sign, add, out);
   return cudaGetLastError();
 }
 
@@ -285,14 +276,15 @@ cudaError_t pc_diag_build(const real* r, int n, real a, real eta, bool wall, rea
   return cudaGetLastError();
 }
 
-template <typename real>
+// index type: 32-bit whenever the element count allows (64-bit divisions are library calls)
+template <typename real, typename idx_t>
 __global__ void pc_diag_mul_kernel(const real* __restrict__ dinv, const real* __restrict__ in,
-                                   int sz, int ncols, long long total, real* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                   idx_t sz, idx_t ncols, idx_t total, real* __restrict__ out) {
+  const idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const long long per_body = (long long)sz * ncols;
-  const long long b = i / per_body;
-  const int row = (int)((i - b * per_body) % sz);
+  const idx_t per_body = sz * ncols;
+  const idx_t b = i / per_body;
+  const idx_t row = (i - b * per_body) % sz;
   out[i] = dinv[b * sz + row] * in[i];
 }
 template <typename real>
@@ -300,16 +292,22 @@ cudaError_t pc_diag_mul(const real* dinv, const real* in, int n_bod, int n_blb, 
                         real* out, cudaStream_t s) {
   const long long total = (long long)n_bod * 3 * n_blb * ncols;
   if (total <= 0) return cudaSuccess;
-  pc_diag_mul_kernel<real><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dinv, in, 3 * n_blb, ncols, total, out);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (total < 0x7fffffffLL)
+    pc_diag_mul_kernel<real, unsigned><<<blocks, 256, 0, s>>>(dinv, in, 3u * n_blb, (unsigned)ncols, (unsigned)total, out);
+  else
+    pc_diag_mul_kernel<real, unsigned long long><<<blocks, 256, 0, s>>>(dinv, in, 3ull * n_blb, (unsigned long long)ncols,
+                                                                     (unsigned long long)total, out);
   return cudaGetLastError();
 }
 
 template <typename real>
 __global__ void pc_fill_kcols_kernel(const real* __restrict__ r, const real* __restrict__ X,
                                      int n_bod, int n_blb, real* __restrict__ Kc) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_bod * n_blb) return;
-  const int b = (int)(i / n_blb), k = (int)(i - (long long)b * n_blb);
+  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: see place_blobs_kernel
+  if (iu >= (unsigned)n_bod * (unsigned)n_blb) return;
+  const unsigned b = iu / (unsigned)n_blb, k = iu - b * (unsigned)n_blb;
+  const size_t i = iu;
   const int sz = 3 * n_blb;
   const real px = r[3 * i] - X[3 * (size_t)b], py = r[3 * i + 1] - X[3 * (size_t)b + 1],
              pz = r[3 * i + 2] - X[3 * (size_t)b + 2];

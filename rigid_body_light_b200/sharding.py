@@ -165,6 +165,13 @@ class CudaShard:
                       out_local.data_ptr())
 
 
+def join_system(parts, ranges):
+    """Inverse of ``slice_system``: the global [lambda ; U] vector from every rank's local one."""
+    lam = [p[: p.size - 6 * (hi - lo)] for p, (lo, hi) in zip(parts, ranges)]
+    U = [p[p.size - 6 * (hi - lo):] for p, (lo, hi) in zip(parts, ranges)]
+    return np.concatenate(lam + U)
+
+
 def slice_system(vec, ranges, n_blb, rank):
     """Rank-local [lambda ; U] slice of a global [lambda(3N) ; U(6 n_bod)] vector (numpy)."""
     n_bod = ranges[-1][1]
@@ -256,9 +263,7 @@ class PartitionedRigidBody:
             return np.asarray(x_local).copy()
         parts = [None] * self.world
         self.dist.all_gather_object(parts, np.asarray(x_local))
-        lam = [p[: p.size - 6 * (hi - lo)] for p, (lo, hi) in zip(parts, self.ranges)]
-        U = [p[p.size - 6 * (hi - lo):] for p, (lo, hi) in zip(parts, self.ranges)]
-        return np.concatenate(lam + U)
+        return join_system(parts, self.ranges)
 
     # -- collective operators (rank-local slices in and out) ---------------------------------
     def apply_saddle(self, x_local):

@@ -2,7 +2,7 @@
 must keep sampling the Gibbs-Boltzmann height distribution (tools/bd_equilibrium.py).  This is
 the validation the reference cannot give (its step is unfinished and seeds from the wall clock,
 c_rigid_obj.cpp:730-741,917-976): without the stochastic drift terms the spheres pile up at the
-wall (mean height 1.92 instead of 2.01 for these parameters, 8 standard errors of this test)."""
+wall (mean height 2.29 instead of 2.36 for these parameters, about 7 standard errors of this test)."""
 import os
 import sys
 
@@ -22,4 +22,4 @@ def test_sedimented_spheres_sample_the_boltzmann_distribution():
     assert abs(out["mean_h"] - want) < 4 * sem + 0.01, out  # + O(dt) weak error of the scheme
     assert abs(out["mean_h"] - want) < 0.5 * abs(out["no_drift_mean_h"] - want), out  # closer to Boltzmann than to the biased law
     assert 0.75 < out["var_h"] / out["boltzmann_var_h"] < 1.3, out
-    assert out["min_h"] > 0.85  # nobody went through the wall
+    assert out["min_h"] > 1.0  # nobody went through the wall

@@ -116,3 +116,14 @@ def test_body_ranges_are_contiguous_and_balanced():
         assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         sizes = [hi - lo for lo, hi in r]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_slice_and_join_system_are_inverse_for_uneven_ranges():
+    from rigid_body_light_b200.sharding import body_ranges, join_system, slice_system
+
+    for n_bod, world, n_blb in [(7, 3, 12), (1000, 8, 5), (5, 2, 42), (4, 1, 3)]:
+        ranges = body_ranges(n_bod, world)
+        vec = np.arange(3 * n_bod * n_blb + 6 * n_bod, dtype=np.float64)
+        parts = [slice_system(vec, ranges, n_blb, r) for r in range(world)]
+        assert [p.size for p in parts] == [(hi - lo) * (3 * n_blb + 6) for lo, hi in ranges]
+        assert np.array_equal(join_system(parts, ranges), vec)

@@ -31,7 +31,7 @@ def boltzmann(mg, eps, b, R, kBT):
     return g, w / Z, m1, m2 - m1 * m1
 
 
-def run(steps=4000, burn=0, dt=0.05, kBT=1.0, mg=2.0, eps=8.0, b=0.25, R=1.0, side=8, precision="double", seed=5):
+def run(steps=4000, burn=0, dt=0.05, kBT=1.0, mg=2.0, eps=32.0, b=0.25, R=1.0, side=8, precision="double", seed=5):
     from Rigid import RigidBody
     from rigid_body_light_b200.shells import icosphere_shell
 
