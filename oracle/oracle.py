@@ -425,7 +425,23 @@ def Kinv_apply(v, r, X, Q, ref_cfg):
     return np.einsum("bij,bj->bi", G, y).reshape(-1)
 
 
-def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta=1.0e-4):
+def noise_block_cholesky(M_raw, A, n_bod, sz, W):
+    """g = L (G A G^T)^{1/2} W with L = blockdiag(chol(M_raw[b,b])) over the bodies and G = L^-1:
+    a vector of covariance A (= B M B) through the block-Cholesky preconditioned square root
+    (include/rbl.h rbl_set_noise_preconditioner).  Dense float64."""
+    from scipy.linalg import sqrtm
+
+    n = M_raw.shape[0]
+    L = np.zeros((n, n))
+    for b in range(n_bod):
+        sl = slice(b * sz, (b + 1) * sz)
+        L[sl, sl] = np.linalg.cholesky(M_raw[sl, sl])
+    G = np.linalg.inv(L)
+    S = np.real(sqrtm(G @ A @ G.T))
+    return L @ (S @ W)
+
+
+def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta=1.0e-4, noise="symmetric"):
     """The trapezoidal-slip midpoint step RHS_and_Midpoint sets up (c_rigid_obj.cpp:917-976),
     completed as intended (the reference computes the midpoint configuration but never installs
     it) and evaluated with dense float64 linear algebra:
@@ -446,12 +462,17 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
     rhs_slip = np.zeros(n3) if slip is None else np.asarray(slip, dtype=np.float64).reshape(-1).copy()
     Xm, Qm = X, Q
     if kBT > 0:
-        M = np.asarray(dense_mobility(r, a, eta, wall))
+        M_raw = np.asarray(dense_mobility(r, a, eta, wall))
+        M = M_raw
         if wall:
             B = damp_diag(r, a)
-            M = B[:, None] * M * B[None, :]
-        S = np.real(sqrtm(M))
-        mh1, mh2 = S @ W1, S @ W2
+            M = B[:, None] * M_raw * B[None, :]
+        if noise == "block_cholesky":
+            mh1 = noise_block_cholesky(M_raw, M, nb, 3 * n_blb, W1)
+            mh2 = noise_block_cholesky(M_raw, M, nb, 3 * n_blb, W2)
+        else:
+            S = np.real(sqrtm(M))
+            mh1, mh2 = S @ W1, S @ W2
         uom = Kinv_apply(Wr, r, X, Q, ref)
         Xp, Qp = update_X_Q(X, Q, 0.5 * delta * uom)
         Xn, Qn = update_X_Q(X, Q, -0.5 * delta * uom)

@@ -203,6 +203,8 @@ class CManyBodies {
                       &iters, &relres));
     return py::make_tuple(U, iters, relres);
   }
+  void set_noise_preconditioner(int mode) { check(rbl_set_noise_preconditioner(ctx_, mode)); }
+  void set_lanczos_pairing(bool on) { check(rbl_set_lanczos_pairing(ctx_, on ? 1 : 0)); }
   std::uintptr_t handle() const { return reinterpret_cast<std::uintptr_t>(ctx_); }
 };
 
@@ -243,5 +245,8 @@ PYBIND11_MODULE(RBL_MODULE_NAME, m) {
            py::arg("W2") = py::none(), py::arg("Wr") = py::none(), py::arg("kBT") = 0.0, py::arg("tol") = 1e-8,
            py::arg("restart") = 60, py::arg("max_iter") = 300, py::arg("lanczos_tol") = 1e-6,
            py::arg("lanczos_max_iter") = 100)
+      .def("set_noise_preconditioner", &CManyBodies::set_noise_preconditioner, py::arg("mode"),
+           "0: symmetric square root; 1: block-Cholesky preconditioned noise in bd_step (default); 2: also in lanczos_sqrt")
+      .def("set_lanczos_pairing", &CManyBodies::set_lanczos_pairing, py::arg("on"))
       .def("handle", &CManyBodies::handle, "address of the rbl_ctx (for ctypes users of include/rbl.h)");
 }

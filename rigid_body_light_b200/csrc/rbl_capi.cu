@@ -112,6 +112,9 @@ struct rbl_ctx {
   int variant = -1;
   int sym_variant = -1;
   int sym2_variant = -1;
+  // 0: symmetric square root everywhere; 1 (default): block-Cholesky preconditioned noise inside
+  // rbl_bd_step; 2: also in rbl_lanczos_sqrt / rbl_lanczos_sqrt2 (they then return L (G A G^T)^{1/2} W)
+  int noise_mode = 1;
   bool pair_lanczos = true;  // BD step: M^{1/2}W_1 and M^{1/2}W_2 in lockstep over the two-right-hand-side product
   int mode = 0;  // 0: symmetric kernel when targets == sources; 1: ordered kernel always
   bool profile = false;
@@ -164,9 +167,12 @@ struct Ctx final : rbl_ctx {
   DevBuf d_r_all, d_lam_all, d_mbuf, d_status;
   // two-right-hand-side product / paired Lanczos
   DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2, d_ktr;
+  // noise preconditioner: Cholesky factors L of the bodies' own mobility blocks and G = L^-1
+  DevBuf d_NL, d_NG, d_nt1, d_nt2, d_nu1, d_nu2;
+  bool noise_set = false, noise_ok = false, noise_shared = false, noise_shared_ready = false;
   bool r_all_valid = false;
 
-  enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, N_FLAGS = 4 };
+  enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, FLAG_NOISE = 3, N_FLAGS = 4 };
 
   ~Ctx() override {
     for (auto& pr : prof_events) {
@@ -241,12 +247,14 @@ struct Ctx final : rbl_ctx {
     params_set = true;
     r_valid = false;
     pc_set = false;
+    noise_set = false;
+    noise_shared_ready = false;
     return RBL_OK;
   }
 
   int set_flags(int block_pc_, int wall_) override {
     if (block_pc_ >= 0 && (block_pc_ != 0) != block_pc) { block_pc = block_pc_ != 0; pc_set = false; }
-    if (wall_ >= 0 && (wall_ != 0) != wall) { wall = wall_ != 0; pc_set = false; }
+    if (wall_ >= 0 && (wall_ != 0) != wall) { wall = wall_ != 0; pc_set = false; noise_set = false; }
     return RBL_OK;
   }
 
@@ -286,6 +294,7 @@ struct Ctx final : rbl_ctx {
                                         d_flags.as<int>() + FLAG_SINGULAR, stream));
     r_valid = true;
     r_all_valid = false;
+    noise_set = false;  // the per-body factors follow the blob positions
     return RBL_OK;
   }
   int need_K() {
@@ -1019,15 +1028,17 @@ struct Ctx final : rbl_ctx {
     CK(d_in1.ensure(n * sizeof(real)));
     CK(d_out0.ensure(n * sizeof(real)));
     RET(h2d(d_in1.p, W, n * sizeof(real)));
-    RET(dev_lanczos(d_in1.as<real>(), d_out0.as<real>(), tol, max_iter, iters));
+    RET(dev_lanczos(d_in1.as<real>(), d_out0.as<real>(), tol, max_iter, iters, noise_mode == 2));
     RET(d2h(out, d_out0.p, n * sizeof(real)));
     return csync();
   }
 
   // device-resident core: dout = (B M B)^{1/2} dW at the CURRENT configuration (d_r)
-  int dev_lanczos(const real* dW, real* dout, double tol, int max_iter, int* iters) {
+  int dev_lanczos(const real* dW, real* dout, double tol, int max_iter, int* iters, bool precondition = false) {
     if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
     RET(need_K());
+    bool pc = false;
+    RET(want_noise_pc(precondition, &pc));
     const size_t n = 3 * (size_t)N();
     const int nb = (int)N();
     const int m = max_iter;
@@ -1051,7 +1062,13 @@ struct Ctx final : rbl_ctx {
     int k = 0;
     for (; k < m;) {
       // w = M v_k - beta_{k-1} v_{k-1}
-      RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
+      if (pc) {  // w = G A G^T v_k
+        RET(noise_GT(V + (size_t)k * n, d_nt1.as<real>()));
+        RET(prod_M(d_nt1.as<real>(), d_r.as<real>(), true, d_nu1.as<real>()));
+        RET(noise_G(d_nu1.as<real>(), w));
+      } else {
+        RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
+      }
       if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-beta[k - 1]), w, n, true, stream));
       RET(gdots(V + (size_t)k * n, n, 1, w, n));
       RET(read_scalars(d_dots.as<real>(), 1, s));
@@ -1091,14 +1108,107 @@ struct Ctx final : rbl_ctx {
     std::vector<real> coef(k);
     for (int i = 0; i < k; ++i) coef[i] = (real)y[i];
     RET(h2d(d_coef.p, coef.data(), k * sizeof(real)));
-    CK(cudaMemsetAsync(dout, 0, n * sizeof(real), stream));
-    LAUNCH(1, rbl::multi_axpy<real>(V, n, k, d_coef.as<real>(), (real)1, dout, n, stream));
+    real* acc = pc ? d_nt1.as<real>() : dout;
+    CK(cudaMemsetAsync(acc, 0, n * sizeof(real), stream));
+    LAUNCH(1, rbl::multi_axpy<real>(V, n, k, d_coef.as<real>(), (real)1, acc, n, stream));
+    if (pc) RET(noise_L(acc, dout));
     CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
     *iters = k;
     return RBL_OK;
   }
 
 
+
+
+  // ---- noise preconditioner ---------------------------------------------------------------------
+  int reduce_max_int(int v, int* out) {
+    *out = v;
+    if (!comm) return RBL_OK;
+    CK(cudaMemcpyAsync(d_status.p, &v, sizeof(int), cudaMemcpyHostToDevice, stream));
+    NK(comm->allreduce_max_int(d_status.as<int>(), 1, stream));
+    CK(cudaMemcpyAsync(out, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return RBL_OK;
+  }
+  // L_b = chol(Mt_b), G_b = L_b^-1 for the bodies of this context.  Free space: ONE factor of the
+  // reference shape (M_b = R M_ref R^T  =>  L_b = R L_ref), computed once per parameter set.  With the
+  // wall: one factor per body and configuration.  noise_ok = false (plain Lanczos) when a block is not
+  // positive definite (blobs inside the wall-overlap layer) or the factors do not fit in memory.
+  int build_noise_pc() {
+    RET(need_K());
+    const int sz = 3 * n_blb;
+    int* fl = d_flags.as<int>();
+    int bad = 0;
+    if (!wall) {
+      noise_shared = true;
+      if (!noise_shared_ready) {
+        const size_t bytes = (size_t)sz * sz * sizeof(real);
+        if (d_NL.ensure(bytes) != cudaSuccess || d_NG.ensure(bytes) != cudaSuccess) {
+          cudaGetLastError();
+          bad = 1;
+        } else {
+          LAUNCH(1, rbl::pc_block_assemble<real>(d_ref.as<real>(), 1, n_blb, (real)a, (real)eta, false, d_NL.as<real>(), fl + FLAG_NOISE, stream));
+          LAUNCH(1, rbl::chol_lower<real>(d_NL.as<real>(), 1, sz, fl + FLAG_NOISE, stream));
+          LAUNCH(1, rbl::tri_inverse<real>(d_NL.as<real>(), d_NG.as<real>(), 1, sz, stream));
+        }
+      }
+    } else {
+      noise_shared = false;
+      const size_t bytes = (size_t)n_bod * sz * sz * sizeof(real);
+      if (d_NL.ensure(bytes) != cudaSuccess || d_NG.ensure(bytes) != cudaSuccess) {
+        cudaGetLastError();
+        d_NL.release();
+        d_NG.release();
+        bad = 1;
+      } else {
+        LAUNCH(1, rbl::pc_block_assemble<real>(d_r.as<real>(), n_bod, n_blb, (real)a, (real)eta, true, d_NL.as<real>(), fl + FLAG_NOISE, stream));
+        LAUNCH(1, rbl::chol_lower<real>(d_NL.as<real>(), n_bod, sz, fl + FLAG_NOISE, stream));
+        LAUNCH(1, rbl::tri_inverse<real>(d_NL.as<real>(), d_NG.as<real>(), n_bod, sz, stream));
+      }
+    }
+    if (!bad) {
+      int f = 0;
+      CK(cudaMemcpyAsync(&f, fl + FLAG_NOISE, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      if (f) {
+        CK(cudaMemsetAsync(fl + FLAG_NOISE, 0, sizeof(int), stream));
+        bad = 1;
+      }
+    }
+    int any_bad = 0;
+    RET(reduce_max_int(bad, &any_bad));  // all ranks precondition, or none
+    noise_ok = !any_bad;
+    if (noise_ok && !wall) noise_shared_ready = true;
+    noise_set = true;
+    const size_t n3 = 3 * (size_t)N();
+    if (noise_ok)
+      for (DevBuf* b : {&d_nt1, &d_nt2, &d_nu1, &d_nu2}) CK(b->ensure(n3 * sizeof(real)));
+    return RBL_OK;
+  }
+  // out = G^T v, G u, L y for every body of the context
+  int noise_GT(const real* v, real* out) {
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), noise_shared ? 0 : (size_t)9 * n_blb * n_blb, d_Q.as<real>(), false,
+                                      noise_shared, true, v, n_bod, n_blb, out, stream));
+    return RBL_OK;
+  }
+  int noise_G(const real* u, real* out) {
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), noise_shared ? 0 : (size_t)9 * n_blb * n_blb, d_Q.as<real>(), noise_shared,
+                                      false, false, u, n_bod, n_blb, out, stream));
+    return RBL_OK;
+  }
+  int noise_L(const real* y, real* out) {
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NL.as<real>(), noise_shared ? 0 : (size_t)9 * n_blb * n_blb, d_Q.as<real>(), false,
+                                      noise_shared, false, y, n_bod, n_blb, out, stream));
+    return RBL_OK;
+  }
+  // decides whether this Lanczos run is preconditioned (builds the factors if needed)
+  int want_noise_pc(bool requested, bool* use) {
+    *use = false;
+    if (!requested) return RBL_OK;
+    if (!noise_set) RET(build_noise_pc());
+    *use = noise_ok;
+    return RBL_OK;
+  }
 
   // y = ||W|| T_k^{1/2} e_1 for the Lanczos tridiagonal (alpha, beta)
   static void lanczos_coeffs(const std::vector<double>& alpha, const std::vector<double>& beta, int k, double wnorm,
@@ -1126,7 +1236,8 @@ struct Ctx final : rbl_ctx {
     CK(d_out2.ensure(n * sizeof(real)));
     RET(h2d(d_in1.p, W1, n * sizeof(real)));
     RET(h2d(d_in2.p, W2, n * sizeof(real)));
-    RET(dev_lanczos2(d_in1.as<real>(), d_in2.as<real>(), d_out0.as<real>(), d_out2.as<real>(), tol, max_iter, iters2));
+    RET(dev_lanczos2(d_in1.as<real>(), d_in2.as<real>(), d_out0.as<real>(), d_out2.as<real>(), tol, max_iter, iters2,
+                     noise_mode == 2));
     RET(d2h(out1, d_out0.p, n * sizeof(real)));
     RET(d2h(out2, d_out2.p, n * sizeof(real)));
     return csync();
@@ -1135,9 +1246,12 @@ struct Ctx final : rbl_ctx {
   // Two Lanczos recurrences in lockstep, (B M B)^{1/2} W_1 and (B M B)^{1/2} W_2, sharing every
   // mobility product through the two-right-hand-side kernel.  Each recurrence is exactly
   // dev_lanczos (same stopping rule); one that has converged is frozen while the other finishes.
-  int dev_lanczos2(const real* dW1, const real* dW2, real* dout1, real* dout2, double tol, int max_iter, int* iters2) {
+  int dev_lanczos2(const real* dW1, const real* dW2, real* dout1, real* dout2, double tol, int max_iter, int* iters2,
+                   bool precondition) {
     if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
     RET(need_K());
+    bool pc = false;
+    RET(want_noise_pc(precondition, &pc));
     const size_t n = 3 * (size_t)N();
     const int m = max_iter;
     CK(d_V.ensure((size_t)(m + 1) * n * sizeof(real)));
@@ -1170,7 +1284,15 @@ struct Ctx final : rbl_ctx {
       // a frozen recurrence feeds its last basis vector (the result is ignored)
       const real* v0 = R[0].V + (size_t)(R[0].done ? std::max(R[0].k - 1, 0) : R[0].k) * n;
       const real* v1 = R[1].V + (size_t)(R[1].done ? std::max(R[1].k - 1, 0) : R[1].k) * n;
-      RET(prod_M2(v0, v1, R[0].w, R[1].w));
+      if (pc) {  // w = G A G^T v
+        RET(noise_GT(v0, d_nt1.as<real>()));
+        RET(noise_GT(v1, d_nt2.as<real>()));
+        RET(prod_M2(d_nt1.as<real>(), d_nt2.as<real>(), d_nu1.as<real>(), d_nu2.as<real>()));
+        RET(noise_G(d_nu1.as<real>(), R[0].w));
+        RET(noise_G(d_nu2.as<real>(), R[1].w));
+      } else {
+        RET(prod_M2(v0, v1, R[0].w, R[1].w));
+      }
       for (auto& q : R) {
         if (q.done) continue;
         const int k = q.k;
@@ -1210,8 +1332,10 @@ struct Ctx final : rbl_ctx {
       std::vector<real> coef(q.k);
       for (int i = 0; i < q.k; ++i) coef[i] = (real)q.y[i];
       RET(h2d(d_coef.p, coef.data(), q.k * sizeof(real)));
-      CK(cudaMemsetAsync(q.out, 0, n * sizeof(real), stream));
-      LAUNCH(1, rbl::multi_axpy<real>(q.V, n, q.k, d_coef.as<real>(), (real)1, q.out, n, stream));
+      real* acc = pc ? d_nt1.as<real>() : q.out;
+      CK(cudaMemsetAsync(acc, 0, n * sizeof(real), stream));
+      LAUNCH(1, rbl::multi_axpy<real>(q.V, n, q.k, d_coef.as<real>(), (real)1, acc, n, stream));
+      if (pc) RET(noise_L(acc, q.out));  // g = L (G A G^T)^{1/2} W
       CK(cudaStreamSynchronize(stream));  // coef (host) must outlive the copy
     }
     return RBL_OK;
@@ -1252,13 +1376,14 @@ struct Ctx final : rbl_ctx {
       if (pair_lanczos) {
         RET(h2d(noise, W1, n3 * sizeof(real)));
         RET(h2d(d_rfd.p, W2, n3 * sizeof(real)));  // d_rfd is free until the RFD below
-        RET(dev_lanczos2(noise, d_rfd.as<real>(), d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos));
+        RET(dev_lanczos2(noise, d_rfd.as<real>(), d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos,
+                         noise_mode >= 1));
       } else {
         RET(h2d(noise, W1, n3 * sizeof(real)));
-        RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it));
+        RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it, noise_mode >= 1));
         last_lanczos[0] = it;
         RET(h2d(noise, W2, n3 * sizeof(real)));
-        RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it));
+        RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it, noise_mode >= 1));
         last_lanczos[1] = it;
       }
       // random finite difference  (M_RFD, :769-796)
@@ -1491,6 +1616,12 @@ int rbl_lanczos_sqrt2(rbl_ctx* ctx, const void* W1, const void* W2, void* out1, 
   int s = ctx->lanczos2(W1, W2, out1, out2, tol, max_iter, it);
   if (iters2) { iters2[0] = it[0]; iters2[1] = it[1]; }
   return s;
+}
+int rbl_set_noise_preconditioner(rbl_ctx* ctx, int mode) {
+  CTX_OR_FAIL(ctx);
+  if (mode < 0 || mode > 2) return ctx->fail(RBL_ERR_INVALID, "noise preconditioner mode must be 0, 1 or 2");
+  ctx->noise_mode = mode;
+  return RBL_OK;
 }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }

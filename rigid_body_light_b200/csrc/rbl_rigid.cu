@@ -615,6 +615,139 @@ cudaError_t pc_finish(const real* y, const real* F, const real* Y, const real* L
   return cudaGetLastError();
 }
 
+
+// ----------------------------------------------------------------------------------
+// noise preconditioner: per-body Cholesky factor of the body's own mobility block
+// ----------------------------------------------------------------------------------
+// In-place lower Cholesky, one CTA per matrix (right-looking).  The strict upper triangle is
+// zeroed so the factor can be used as a plain dense matrix.  Flags a non-positive pivot.
+template <typename real>
+__global__ void chol_lower_kernel(real* __restrict__ M, int sz, int* __restrict__ not_spd) {
+  real* A = M + (size_t)blockIdx.x * sz * sz;
+  __shared__ real piv_s;
+  for (int k = 0; k < sz; ++k) {
+    if (threadIdx.x == 0) {
+      const real d = A[(size_t)k * sz + k];
+      if (!(d > (real)0) || !isfinite(d)) *not_spd = 1;
+      piv_s = sqrt(d > (real)0 ? d : (real)1);
+    }
+    __syncthreads();
+    const real piv = piv_s, ip = (real)1 / piv;
+    // column k below the diagonal
+    for (int i = k + threadIdx.x; i < sz; i += blockDim.x)
+      A[(size_t)i * sz + k] = (i == k) ? piv : A[(size_t)i * sz + k] * ip;
+    __syncthreads();
+    // trailing update A[i][j] -= L[i][k] L[j][k],  k < j <= i  (row-major: threads along j)
+    const int m = sz - k - 1;
+    for (int i = k + 1 + (threadIdx.x >> 5); i < sz; i += (blockDim.x >> 5)) {
+      const real lik = A[(size_t)i * sz + k];
+      for (int j = k + 1 + (threadIdx.x & 31); j <= i; j += 32) A[(size_t)i * sz + j] -= lik * A[(size_t)j * sz + k];
+    }
+    (void)m;
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < sz * sz; idx += blockDim.x) {
+    const int i = idx / sz, j = idx - i * sz;
+    if (j > i) A[idx] = (real)0;
+  }
+}
+template <typename real>
+cudaError_t chol_lower(real* M, int count, int sz, int* not_spd, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  chol_lower_kernel<real><<<count, sz <= 128 ? 256 : 1024, 0, s>>>(M, sz, not_spd);
+  return cudaGetLastError();
+}
+
+// G = L^-1 for lower-triangular L (row-major), 256 columns per CTA: column j of G solves
+// L g = e_j by forward substitution; threads own columns, so G[k][j] reads coalesce and
+// L[i][k] is a broadcast.  G's strict upper triangle is written as zero.
+template <typename real>
+__global__ void tri_inverse_kernel(const real* __restrict__ Lm, real* __restrict__ Gm, int sz) {
+  const real* L = Lm + (size_t)blockIdx.y * sz * sz;
+  real* G = Gm + (size_t)blockIdx.y * sz * sz;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = 0; i < sz; ++i) {
+    if (j < sz) {
+      real acc = (real)0;
+      if (i >= j) {
+        acc = (i == j) ? (real)1 : (real)0;
+        for (int k = j; k < i; ++k) acc -= L[(size_t)i * sz + k] * G[(size_t)k * sz + j];
+        acc /= L[(size_t)i * sz + i];
+      }
+      G[(size_t)i * sz + j] = acc;  // a thread only ever reads back its OWN column: no barrier needed
+    }
+  }
+}
+template <typename real>
+cudaError_t tri_inverse(const real* L, real* G, int count, int sz, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  dim3 grid((sz + 255) / 256, count);
+  tri_inverse_kernel<real><<<grid, 256, 0, s>>>(L, G, sz);
+  return cudaGetLastError();
+}
+
+// out_b = op(A_b) x_b per body: op = A (trans = 0) or A^T (trans = 1); with ONE shared matrix
+// (stride = 0, Q given) body b uses the rotated factor: rot_in applies R_b^T per blob before the
+// product, rot_out applies R_b after it.  Thread per output row, x staged in shared memory.
+template <typename real>
+__global__ void body_mat_mul_kernel(const real* __restrict__ A0, size_t stride, const real* __restrict__ Q, int rot_in,
+                                    int rot_out, int trans, const real* __restrict__ in, int sz, real* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* x = reinterpret_cast<real*>(smem_raw);  // sz
+  __shared__ real tile[192];
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 192 + threadIdx.x;
+  const real* A = A0 + stride * b;
+  real R[9];
+  if (rot_in || rot_out) quat_to_rot(Q + 4 * (size_t)b, R);
+  const real* xin = in + (size_t)b * sz;
+  if (rot_in) {
+    for (int k = threadIdx.x; k < sz / 3; k += blockDim.x) {
+      const real vx = xin[3 * k], vy = xin[3 * k + 1], vz = xin[3 * k + 2];
+      x[3 * k + 0] = R[0] * vx + R[3] * vy + R[6] * vz;
+      x[3 * k + 1] = R[1] * vx + R[4] * vy + R[7] * vz;
+      x[3 * k + 2] = R[2] * vx + R[5] * vy + R[8] * vz;
+    }
+  } else {
+    for (int j = threadIdx.x; j < sz; j += blockDim.x) x[j] = xin[j];
+  }
+  __syncthreads();
+  real acc = 0;
+  if (row < sz) {
+    if (trans) {
+#pragma unroll 8
+      for (int j = 0; j < sz; ++j) acc += A[(size_t)j * sz + row] * x[j];
+    } else {
+      const real* Ar = A + (size_t)row * sz;
+#pragma unroll 8
+      for (int j = 0; j < sz; ++j) acc += Ar[j] * x[j];
+    }
+  }
+  real* o = out + (size_t)b * sz;
+  if (rot_out) {
+    tile[threadIdx.x] = acc;
+    __syncthreads();
+    if (row < sz) {
+      const int k3 = (threadIdx.x / 3) * 3, p = threadIdx.x - k3;
+      o[row] = R[3 * p] * tile[k3] + R[3 * p + 1] * tile[k3 + 1] + R[3 * p + 2] * tile[k3 + 2];
+    }
+  } else if (row < sz) {
+    o[row] = acc;
+  }
+}
+template <typename real>
+cudaError_t body_mat_mul(const real* A, size_t stride, const real* Q, bool rot_in, bool rot_out, bool trans,
+                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s) {
+  if (n_bod <= 0) return cudaSuccess;
+  const int sz = 3 * n_blb;
+  const size_t smem = (size_t)sz * sizeof(real);
+  cudaError_t e = cudaFuncSetAttribute(body_mat_mul_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((sz + 191) / 192, n_bod);
+  body_mat_mul_kernel<real><<<grid, 192, smem, s>>>(A, stride, Q, rot_in ? 1 : 0, rot_out ? 1 : 0, trans ? 1 : 0, in, sz, out);
+  return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------------
 // integrator (Q_from_Om :679-689, update_X_Q :691-710)
 // ----------------------------------------------------------------------------------
@@ -680,6 +813,10 @@ cudaError_t integrate(const real* U, real scale, int n_bod, const real* X, const
                                           int*, cudaStream_t);                                      \
   template cudaError_t pc_finish<real>(const real*, const real*, const real*, const real*,          \
                                        const real*, const real*, int, int, real*, cudaStream_t);    \
+  template cudaError_t chol_lower<real>(real*, int, int, int*, cudaStream_t);                       \
+  template cudaError_t tri_inverse<real>(const real*, real*, int, int, cudaStream_t);               \
+  template cudaError_t body_mat_mul<real>(const real*, size_t, const real*, bool, bool, bool,       \
+                                          const real*, int, int, real*, cudaStream_t);              \
   template cudaError_t integrate<real>(const real*, real, int, const real*, const real*, real*,     \
                                        real*, cudaStream_t);
 INST(float)

@@ -84,6 +84,24 @@ cudaError_t pc_finish(const real* y, const real* F, const real* Y, const real* L
                       const real* r, const real* X, int n_bod, int n_blb, real* out,
                       cudaStream_t s);
 
+// ---- noise preconditioner (block-Cholesky preconditioned Lanczos) -----------------------
+// The Brownian increment only needs a vector of covariance A = B M B, not the symmetric square
+// root: with L_b the Cholesky factor of body b's own mobility block Mt_b (the matrix
+// Block_diag_invM assembles, :461-487) and G = L^-1,   g = L (G A G^T)^{1/2} W   has covariance A,
+// and G A G^T is ~15x better conditioned than A, so Lanczos needs ~3x fewer products.
+// In-place lower Cholesky of `count` sz x sz matrices (upper triangle zeroed), one CTA each.
+template <typename real>
+cudaError_t chol_lower(real* M, int count, int sz, int* not_spd, cudaStream_t s);
+// G = L^-1 (both lower triangular, row-major, `count` matrices)
+template <typename real>
+cudaError_t tri_inverse(const real* L, real* G, int count, int sz, cudaStream_t s);
+// out_b = A_b x_b (trans = false) or A_b^T x_b (trans = true) for every body; stride = sz*sz, or 0
+// for ONE shared matrix of the reference shape used through the body rotation (rot_in: R_b^T per
+// blob before the product, rot_out: R_b after it)
+template <typename real>
+cudaError_t body_mat_mul(const real* A, size_t stride, const real* Q, bool rot_in, bool rot_out, bool trans,
+                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s);
+
 // ---- integrator ---------------------------------------------------------------------
 // Qo <- exp(omega * scale) Q (normalised), Xo <- X + u * scale  (scale = dt for
 // evolve_X_Q; in-place allowed)

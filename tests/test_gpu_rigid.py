@@ -230,7 +230,7 @@ def test_bd_step_brownian_given_noise(orc, name):
                                   lanczos_tol=1e-12, lanczos_max_iter=200)
     ref = orc.remove_mean(g["cfg"])
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), kBT,
-                             bool(g["wall"]), F, None, *noise)
+                             bool(g["wall"]), F, None, *noise, noise="block_cholesky")  # the default noise of bd_step
     assert rel_err(U, Uo) < 1e-6
     X, Q = cb.get_config()
     assert rel_err(X, Xo) < 1e-8 and rel_err(Q, Qo) < 1e-8
@@ -247,3 +247,58 @@ def test_bd_step_needs_noise_when_brownian():
         cb.cb.bd_step(np.zeros(6 * nb), None, None, None, None, 1.0, 1e-8, 60, 100, 1e-6, 50)
     U, it, rr = cb.bd_step(np.ones(6 * nb), kBT=0.01, rng=np.random.default_rng(0))  # draws its own noise
     assert np.all(np.isfinite(U)) and rr <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_step_symmetric_square_root_noise(orc, name):
+    """noise preconditioner off: the Brownian increments are (B M B)^{1/2} W with the symmetric root"""
+    g = load_golden(name)
+    cb = _solver(g, "double", block=True)
+    cb.set_noise_preconditioner(0)
+    nb, n3 = g["X"].shape[0], g["r"].size
+    rng = np.random.default_rng(31)
+    F = rng.standard_normal(6 * nb)
+    noise = tuple(rng.standard_normal(n3) for _ in range(3))
+    U, iters, relres = cb.bd_step(F, kBT=0.004, noise=noise, tol=1e-11, restart=100, max_iter=400,
+                                  lanczos_tol=1e-12, lanczos_max_iter=200)
+    ref = orc.remove_mean(g["cfg"])
+    Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.004,
+                             bool(g["wall"]), F, None, *noise)
+    assert rel_err(U, Uo) < 1e-6
+    X, Q = cb.get_config()
+    assert rel_err(X, Xo) < 1e-8 and rel_err(Q, Qo) < 1e-8
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free", "case_near_wall"])
+def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, name, precision):
+    """mode 2: brownian_sqrt returns g = L (G A G^T)^{1/2} W (per-body Cholesky L of the body's own
+    mobility block; free space: ONE factor of the reference shape rotated per body).  Checked
+    against the dense formula, and through S S^T = A on the assembled operator S (columns =
+    images of unit vectors) -- the property a Brownian increment needs."""
+    g = load_golden(name)
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    cb = _solver(g, precision)
+    cb.set_noise_preconditioner(2)
+    M_raw = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
+    A = M_raw
+    if wall:
+        B = orc.damp_diag(g["r"], a)
+        A = B[:, None] * M_raw * B[None, :]
+    nb, sz = g["X"].shape[0], 3 * g["cfg"].shape[0]
+    spd = all(np.linalg.eigvalsh(M_raw[b * sz:(b + 1) * sz, b * sz:(b + 1) * sz]).min() > 1e-9 for b in range(nb))
+    W = np.random.default_rng(9).standard_normal(A.shape[0])
+    tol = 1e-11 if precision == "double" else 1e-5
+    out, iters = cb.brownian_sqrt(W, tol=tol, max_iter=150)
+    plain = _solver(g, precision)
+    ref_out, ref_iters = plain.brownian_sqrt(W, tol=tol, max_iter=150)
+    lim = 1e-7 if precision == "double" else 2e-3
+    if spd:
+        want = orc.noise_block_cholesky(M_raw, A, nb, sz, W)
+        assert rel_err(out, want) < lim
+        assert iters < ref_iters  # the point of the exercise
+    else:  # body blocks not positive definite (blobs in the wall-overlap layer): plain recurrence
+        assert rel_err(out, ref_out) < lim
+    if precision == "double" and A.shape[0] <= 400:
+        S = np.stack([cb.brownian_sqrt(e, tol=1e-12, max_iter=200)[0] for e in np.eye(A.shape[0])], axis=1)
+        assert np.linalg.norm(S @ S.T - A) / np.linalg.norm(A) < 1e-8
