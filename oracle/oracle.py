@@ -425,17 +425,41 @@ def Kinv_apply(v, r, X, Q, ref_cfg):
     return np.einsum("bij,bj->bi", G, y).reshape(-1)
 
 
-def noise_block_cholesky(M_raw, A, n_bod, sz, W):
-    """g = L (G A G^T)^{1/2} W with L = blockdiag(chol(M_raw[b,b])) over the bodies and G = L^-1:
-    a vector of covariance A (= B M B) through the block-Cholesky preconditioned square root
-    (include/rbl.h rbl_set_noise_preconditioner).  Dense float64."""
+def noise_factors(r, Q, ref_cfg, a, eta, wall):
+    """Per-body factors L_b with L_b L_b^T = Mt_b, the body's own mobility block (no B damping),
+    as the product path builds them: with the wall, the lower Cholesky factor of each body's block;
+    in free space ONE Cholesky factor of the reference shape, rotated -- M_b = R M_ref R^T with
+    R = blockdiag(R_b) per blob, so L_b = R L_ref (not triangular, equally valid)."""
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    n_blb = ref.shape[0]
+    r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
+    nb = r.shape[0] // n_blb
+    out = []
+    if wall:
+        for b in range(nb):
+            Mb = np.asarray(dense_mobility(r[b * n_blb:(b + 1) * n_blb], a, eta, True))
+            out.append(np.linalg.cholesky(Mb))
+    else:
+        L_ref = np.linalg.cholesky(np.asarray(dense_mobility(ref, a, eta, False)))
+        R = rotation_matrices(normalize_quats(np.asarray(Q, dtype=np.float64).reshape(-1, 4)))
+        for b in range(nb):
+            out.append(np.kron(np.eye(n_blb), R[b]) @ L_ref)
+    return out
+
+
+def noise_block_cholesky(factors, A, W):
+    """g = L (G A G^T)^{1/2} W with L = blockdiag(factors) and G = L^-1: a vector of covariance A
+    (= B M B) through the block preconditioned square root (include/rbl.h
+    rbl_set_noise_preconditioner).  Dense float64."""
     from scipy.linalg import sqrtm
 
-    n = M_raw.shape[0]
+    n = A.shape[0]
     L = np.zeros((n, n))
-    for b in range(n_bod):
-        sl = slice(b * sz, (b + 1) * sz)
-        L[sl, sl] = np.linalg.cholesky(M_raw[sl, sl])
+    o = 0
+    for Lb in factors:
+        sz = Lb.shape[0]
+        L[o:o + sz, o:o + sz] = Lb
+        o += sz
     G = np.linalg.inv(L)
     S = np.real(sqrtm(G @ A @ G.T))
     return L @ (S @ W)
@@ -468,8 +492,9 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
             B = damp_diag(r, a)
             M = B[:, None] * M_raw * B[None, :]
         if noise == "block_cholesky":
-            mh1 = noise_block_cholesky(M_raw, M, nb, 3 * n_blb, W1)
-            mh2 = noise_block_cholesky(M_raw, M, nb, 3 * n_blb, W2)
+            fac = noise_factors(r, Q, ref, a, eta, wall)
+            mh1 = noise_block_cholesky(fac, M, W1)
+            mh2 = noise_block_cholesky(fac, M, W2)
         else:
             S = np.real(sqrtm(M))
             mh1, mh2 = S @ W1, S @ W2

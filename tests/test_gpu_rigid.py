@@ -294,7 +294,7 @@ def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, na
     ref_out, ref_iters = plain.brownian_sqrt(W, tol=tol, max_iter=150)
     lim = 1e-7 if precision == "double" else 2e-3
     if spd:
-        want = orc.noise_block_cholesky(M_raw, A, nb, sz, W)
+        want = orc.noise_block_cholesky(orc.noise_factors(g["r"], g["Qn"], orc.remove_mean(g["cfg"]), a, eta, wall), A, W)
         assert rel_err(out, want) < lim
         assert iters < ref_iters  # the point of the exercise
     else:  # body blocks not positive definite (blobs in the wall-overlap layer): plain recurrence
