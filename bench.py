@@ -349,7 +349,7 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
     n3 = 3 * nb * n_blb
     F_ext = np.tile(np.array([0, 0, -1.0, 0, 0, 0]), nb)
     out = {"workload": f"{args.bd_workload}: {nb} spheres of shell_N_{n_blb} {'above a wall' if wall else 'in free space'} "
-                       f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC",
+                       f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC, block-Cholesky preconditioned paired Lanczos noise",
            "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps}
     for precision in precisions:
         tol, ltol = (1e-4, 1e-4) if precision == "single" else (1e-8, 1e-6)
