@@ -126,6 +126,11 @@ int rbl_lanczos_sqrt2(rbl_ctx* ctx, const void* W1, const void* W2, void* out1, 
  * return the preconditioned vector too.  Falls back to the plain recurrence when a body block is
  * not positive definite (blobs inside the wall-overlap layer) or the factors do not fit. */
 int rbl_set_noise_preconditioner(rbl_ctx* ctx, int mode);
+/* Self-check of the factors at the current configuration, like the reference's unbound test_PC /
+ * Test_Mhalf (:569-587, :895-915): factor_err = |L L^T x - Mt x| / |Mt x| against freshly assembled
+ * body blocks, inverse_err = |G L x - x| / |x| for a fixed pseudo-random x; active = 0 if the
+ * context fell back to the plain recurrence.  Rank-local. */
+int rbl_noise_selfcheck(rbl_ctx* ctx, double* factor_err, double* inverse_err, int* active);
 /* 1 (default): rbl_bd_step uses the paired Lanczos; 0: two separate single-vector runs */
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable);
 

@@ -54,6 +54,7 @@ SYMBOLS = {
     "rbl_lanczos_sqrt2": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _pi]),
     "rbl_set_lanczos_pairing": (_i, [_vp, _i]),
     "rbl_set_noise_preconditioner": (_i, [_vp, _i]),
+    "rbl_noise_selfcheck": (_i, [_vp, _pd, _pd, _pi]),
     "rbl_num_sym2_variants": (_i, [_vp]),
     "rbl_sym2_variant_info": (_i, [_vp, _i, _pi, _pi]),
     "rbl_set_sym2_variant": (_i, [_vp, _i]),

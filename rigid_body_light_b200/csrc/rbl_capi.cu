@@ -98,6 +98,7 @@ struct rbl_ctx {
   virtual int dev_apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
   virtual int apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
   virtual int lanczos2(const void* W1, const void* W2, void* out1, void* out2, double tol, int max_iter, int* iters2) = 0;
+  virtual int noise_selfcheck(double* factor_err, double* inverse_err, int* active) = 0;
   virtual int num_sym2_variants() const = 0;
   virtual int sym2_variant_info(int idx, int* T, int* threads) const = 0;
 
@@ -1210,6 +1211,65 @@ struct Ctx final : rbl_ctx {
     return RBL_OK;
   }
 
+
+  // Self-check of the noise factors in the spirit of the reference's unbound test_PC / Test_Mhalf
+  // (:569-587, :895-915): for a fixed pseudo-random x,  |L L^T x - Mt x| / |Mt x|  with Mt the
+  // freshly assembled body blocks, and  |G L x - x| / |x|.  active = 0 when the context fell back
+  // to the unpreconditioned recurrence (blocks not positive definite / factors do not fit).
+  int noise_selfcheck(double* factor_err, double* inverse_err, int* active) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    RET(build_noise_pc());
+    *active = noise_ok ? 1 : 0;
+    *factor_err = *inverse_err = 0;
+    if (!noise_ok) return RBL_OK;
+    const int sz = 3 * n_blb;
+    const size_t n3 = 3 * (size_t)N();
+    const size_t stride = noise_shared ? 0 : (size_t)sz * sz;
+    std::vector<real> hx(n3);
+    unsigned long long st = 88172645463325252ull;
+    for (auto& v : hx) {  // xorshift: deterministic, no library
+      st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+      v = (real)((double)(st >> 11) / 9007199254740992.0 - 0.5);
+    }
+    for (DevBuf* b : {&d_nt1, &d_nt2, &d_nu1, &d_nu2}) CK(b->ensure(n3 * sizeof(real)));
+    real* x = d_nt1.as<real>();
+    real* t = d_nt2.as<real>();
+    real* y = d_nu1.as<real>();
+    real* z = d_nu2.as<real>();
+    RET(h2d(x, hx.data(), n3 * sizeof(real)));
+    // y = L (L^T x)
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NL.as<real>(), stride, d_Q.as<real>(), noise_shared, false, true, x, n_bod, n_blb, t, stream));
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NL.as<real>(), stride, d_Q.as<real>(), false, noise_shared, false, t, n_bod, n_blb, y, stream));
+    // z = G (L x) - x  -> kept in t after the subtraction below
+    LAUNCH(1, rbl::body_mat_mul<real>(d_NL.as<real>(), stride, d_Q.as<real>(), false, noise_shared, false, x, n_bod, n_blb, t, stream));
+    RET(noise_G(t, z));
+    LAUNCH(1, rbl::scale_copy<real>(x, (real)-1, z, n3, true, stream));
+    CK(d_partial.ensure(4 * rbl::kDotBlocks * sizeof(real)));
+    CK(d_dots.ensure(4 * sizeof(real)));
+    double zn = 0, xn = 0;
+    RET(dev_norm(z, n3, &zn));
+    RET(dev_norm(x, n3, &xn));
+    *inverse_err = zn / xn;
+    // Mt x with freshly assembled blocks (scratch: the G buffer, rebuilt afterwards)
+    int* fl = d_flags.as<int>();
+    if (noise_shared) {
+      LAUNCH(1, rbl::pc_block_assemble<real>(d_ref.as<real>(), 1, n_blb, (real)a, (real)eta, false, d_NG.as<real>(), fl + FLAG_NOISE, stream));
+      // M_b = R M_ref R^T: rotate in, multiply (symmetric), rotate out
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), 0, d_Q.as<real>(), true, true, false, x, n_bod, n_blb, t, stream));
+    } else {
+      LAUNCH(1, rbl::pc_block_assemble<real>(d_r.as<real>(), n_bod, n_blb, (real)a, (real)eta, true, d_NG.as<real>(), fl + FLAG_NOISE, stream));
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), stride, d_Q.as<real>(), false, false, false, x, n_bod, n_blb, t, stream));
+    }
+    LAUNCH(1, rbl::scale_copy<real>(t, (real)-1, y, n3, true, stream));
+    double yn = 0, tn = 0;
+    RET(dev_norm(y, n3, &yn));
+    RET(dev_norm(t, n3, &tn));
+    *factor_err = yn / tn;
+    CK(cudaMemsetAsync(fl + FLAG_NOISE, 0, sizeof(int), stream));
+    LAUNCH(1, rbl::tri_inverse<real>(d_NL.as<real>(), d_NG.as<real>(), noise_shared ? 1 : n_bod, sz, stream));  // restore G
+    return sync();
+  }
+
   // y = ||W|| T_k^{1/2} e_1 for the Lanczos tridiagonal (alpha, beta)
   static void lanczos_coeffs(const std::vector<double>& alpha, const std::vector<double>& beta, int k, double wnorm,
                              std::vector<double>& y) {
@@ -1622,6 +1682,16 @@ int rbl_set_noise_preconditioner(rbl_ctx* ctx, int mode) {
   if (mode < 0 || mode > 2) return ctx->fail(RBL_ERR_INVALID, "noise preconditioner mode must be 0, 1 or 2");
   ctx->noise_mode = mode;
   return RBL_OK;
+}
+int rbl_noise_selfcheck(rbl_ctx* ctx, double* factor_err, double* inverse_err, int* active) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  double f = 0, g = 0;
+  int a = 0;
+  int s = ctx->noise_selfcheck(&f, &g, &a);
+  if (factor_err) *factor_err = f;
+  if (inverse_err) *inverse_err = g;
+  if (active) *active = a;
+  return s;
 }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }

@@ -305,3 +305,26 @@ def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, na
     if precision == "double" and A.shape[0] <= 400 and np.linalg.eigvalsh(A).min() > 0:
         S = np.stack([cb.brownian_sqrt(e, tol=1e-12, max_iter=200)[0] for e in np.eye(A.shape[0])], axis=1)
         assert np.linalg.norm(S @ S.T - A) / np.linalg.norm(A) < 1e-8
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("shell,n_bodies,wall", [(642, 5, True), (162, 40, True), (2562, 3, False), (42, 300, False)])
+def test_noise_factor_selfcheck_at_large_body_sizes(shell, n_bodies, wall, precision):
+    """L L^T = Mt_b and G L = I for body blocks up to 7686 x 7686 (shell_N_2562, one shared factor in
+    free space) and 1926 x 1926 per body with the wall (shell_N_642: BASELINE.json configs[4]'s body)."""
+    import ctypes
+
+    from rigid_body_light_b200._lib import Context
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(n_bodies, shell, wall)
+    ctx = Context(precision)
+    ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, s["cfg"])
+    ctx.set_flags(0, int(wall))
+    ctx.set_config(s["X"], s["Q"])
+    f, g, act = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    ctx.call("rbl_noise_selfcheck", ctypes.byref(f), ctypes.byref(g), ctypes.byref(act))
+    assert act.value == 1
+    lim = 1e-10 if precision == "double" else 2e-3
+    assert f.value < lim and g.value < lim, (f.value, g.value)
+    ctx.close()
