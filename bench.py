@@ -350,7 +350,8 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
     F_ext = np.tile(np.array([0, 0, -1.0, 0, 0, 0]), nb)
     out = {"workload": f"{args.bd_workload}: {nb} spheres of shell_N_{n_blb} {'above a wall' if wall else 'in free space'} "
                        f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC, block-Cholesky preconditioned paired Lanczos noise",
-           "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps}
+           "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps,
+           "warmup_steps": 1 if args.bd_warmup else 0}
     for precision in precisions:
         tol, ltol = (1e-4, 1e-4) if precision == "single" else (1e-8, 1e-6)
         pb = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=wall, block_PC=True,
@@ -358,18 +359,19 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
         rng = np.random.default_rng(3)
         times, iters, lz, rel = [], [], [], []
         prod0 = 0
-        for k in range(1 + args.bd_steps):
+        warm = 1 if args.bd_warmup else 0
+        for k in range(warm + args.bd_steps):
             noise = tuple(pb.slice_blobs(rng.standard_normal(n3)) for _ in range(3))
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            if k == 1:
+            if k == warm:
                 prod0 = int(pb.ctx.L.rbl_product_count(pb.ctx.h))
             t0 = time.perf_counter()
             U, it, rr = pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60, max_iter=200,
                                    lanczos_tol=ltol, lanczos_max_iter=80)
             dt = time.perf_counter() - t0
-            if k == 0:
+            if k < warm:
                 continue
             if world > 1:
                 t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -479,6 +481,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bd-steps", type=int, default=1, help="timed full BD steps after the matvec bench (0 = skip)")
     ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--bd-warmup", type=int, default=1, help="0: time the very first BD step (allocations included)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
