@@ -368,8 +368,8 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
             if k == warm:
                 prod0 = int(pb.ctx.L.rbl_product_count(pb.ctx.h))
             t0 = time.perf_counter()
-            U, it, rr = pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60, max_iter=200,
-                                   lanczos_tol=ltol, lanczos_max_iter=80)
+            U, it, rr = pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60,
+                                   max_iter=args.bd_gmres_max_iter, lanczos_tol=ltol, lanczos_max_iter=args.bd_lanczos_max_iter)
             dt = time.perf_counter() - t0
             if k < warm:
                 continue
@@ -383,7 +383,8 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
         products = (int(pb.ctx.L.rbl_product_count(pb.ctx.h)) - prod0) / max(1, args.bd_steps)
         X, _ = pb.get_config()
         out[precision] = {"seconds_per_step": float(np.mean(times)), "gmres_iterations": iters, "lanczos_iterations": lz,
-                          "gmres_tol": tol, "lanczos_tol": ltol, "relres": rel, "mobility_products_per_step": products,
+                          "gmres_tol": tol, "lanczos_tol": ltol, "gmres_max_iter": args.bd_gmres_max_iter,
+                          "lanczos_max_iter": args.bd_lanczos_max_iter, "relres": rel, "mobility_products_per_step": products,
                           "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U))}
         pb.close()
     return out
@@ -482,6 +483,8 @@ def main():
     ap.add_argument("--bd-steps", type=int, default=1, help="timed full BD steps after the matvec bench (0 = skip)")
     ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--bd-warmup", type=int, default=1, help="0: time the very first BD step (allocations included)")
+    ap.add_argument("--bd-gmres-max-iter", type=int, default=200)
+    ap.add_argument("--bd-lanczos-max-iter", type=int, default=80)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

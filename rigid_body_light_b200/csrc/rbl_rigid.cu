@@ -623,6 +623,8 @@ cudaError_t pc_finish(const real* y, const real* F, const real* Y, const real* L
 // zeroed so the factor can be used as a plain dense matrix.  Flags a non-positive pivot.
 template <typename real>
 __global__ void chol_lower_kernel(real* __restrict__ M, int sz, int* __restrict__ not_spd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* colk = reinterpret_cast<real*>(smem_raw);  // sz: the finished column k (strided in global memory)
   real* A = M + (size_t)blockIdx.x * sz * sz;
   __shared__ real piv_s;
   for (int k = 0; k < sz; ++k) {
@@ -633,17 +635,19 @@ __global__ void chol_lower_kernel(real* __restrict__ M, int sz, int* __restrict_
     }
     __syncthreads();
     const real piv = piv_s, ip = (real)1 / piv;
-    // column k below the diagonal
-    for (int i = k + threadIdx.x; i < sz; i += blockDim.x)
-      A[(size_t)i * sz + k] = (i == k) ? piv : A[(size_t)i * sz + k] * ip;
-    __syncthreads();
-    // trailing update A[i][j] -= L[i][k] L[j][k],  k < j <= i  (row-major: threads along j)
-    const int m = sz - k - 1;
-    for (int i = k + 1 + (threadIdx.x >> 5); i < sz; i += (blockDim.x >> 5)) {
-      const real lik = A[(size_t)i * sz + k];
-      for (int j = k + 1 + (threadIdx.x & 31); j <= i; j += 32) A[(size_t)i * sz + j] -= lik * A[(size_t)j * sz + k];
+    // column k on and below the diagonal
+    for (int i = k + threadIdx.x; i < sz; i += blockDim.x) {
+      const real v = (i == k) ? piv : A[(size_t)i * sz + k] * ip;
+      A[(size_t)i * sz + k] = v;
+      colk[i] = v;
     }
-    (void)m;
+    __syncthreads();
+    // trailing update A[i][j] -= L[i][k] L[j][k],  k < j <= i  (row-major: a warp per row, lanes along j)
+    for (int i = k + 1 + (threadIdx.x >> 5); i < sz; i += (blockDim.x >> 5)) {
+      const real lik = colk[i];
+      real* Ai = A + (size_t)i * sz;
+      for (int j = k + 1 + (threadIdx.x & 31); j <= i; j += 32) Ai[j] -= lik * colk[j];
+    }
     __syncthreads();
   }
   for (int idx = threadIdx.x; idx < sz * sz; idx += blockDim.x) {
@@ -654,7 +658,10 @@ __global__ void chol_lower_kernel(real* __restrict__ M, int sz, int* __restrict_
 template <typename real>
 cudaError_t chol_lower(real* M, int count, int sz, int* not_spd, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  chol_lower_kernel<real><<<count, sz <= 128 ? 256 : 1024, 0, s>>>(M, sz, not_spd);
+  const size_t smem = (size_t)sz * sizeof(real);
+  cudaError_t e = cudaFuncSetAttribute(chol_lower_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  chol_lower_kernel<real><<<count, sz <= 128 ? 256 : 1024, smem, s>>>(M, sz, not_spd);
   return cudaGetLastError();
 }
 
