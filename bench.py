@@ -48,6 +48,7 @@ WORKLOADS = {
     "cfg3": (4096, 42, True),     # configs[2] geometry
     "cfg4": (1000, 2562, False),  # configs[3]
     "cfg5": (10000, 642, True),   # configs[4]
+    "cfg5s": (200, 642, True),    # configs[4]'s body (shell_N_642) at 1/50 of its size
     "small": (64, 42, True),      # CI-sized
 }
 NVSMI_FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
