@@ -28,8 +28,9 @@ def main():
         f64 = d.get("f64") or {}
         comm = d.get("comm_ms_per_step")
         cs = "-" if not comm else f"{1e3 * comm['allgather_lambda']:.0f} / {1e3 * comm.get('reduce_partials', comm.get('allreduce_partials', 0)):.0f}"
-        rows.append((name, d["n_gpus"], wl, d["value"] / 1e9, d["ms_per_step"], d["e2e"]["value"] / 1e9, d["roofline"]["frac"],
-                     f64.get("value", 0) / 1e9, f64.get("ms_per_step"), (f64.get("roofline") or {}).get("frac"), cs))
+        if "bd" not in name:  # *bd* lines exist for their bd_step object (their matvec leg is a 1-step formality)
+            rows.append((name, d["n_gpus"], wl, d["value"] / 1e9, d["ms_per_step"], d["e2e"]["value"] / 1e9, d["roofline"]["frac"],
+                         f64.get("value", 0) / 1e9, f64.get("ms_per_step"), (f64.get("roofline") or {}).get("frac"), cs))
         bd = d.get("bd_step")
         if bd:
             for p in ("single", "double"):
