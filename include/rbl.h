@@ -139,8 +139,7 @@ int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable);
  *   M^{1/2}W_1, M^{1/2}W_2 by Lanczos;  RFD drift (M(q+) - M(q-)) W_r / delta with
  *   q+- = q +- (delta/2) K^-1 W_r (:769-796);  BI = sqrt(kBT/dt) (M^{1/2}W_1 - M^{1/2}W_2) (:945-948);
  *   midpoint q' = q + (dt/2) K^-1 (2 sqrt(kBT/dt) M^{1/2}W_1) (:954-958), K and PC rebuilt THERE;
- *   GMRES solve of  apply_saddle([lambda;U]) = [slip - kBT*RFD - BI ; F_ext - kBT*RFD_KT]  at q', with
- *   RFD_KT = (K^T(q+) - K^T(q-)) W_r / delta (KT_RFD_from_U, :842-863; a torque that vanishes for spheres);
+ *   GMRES solve of  apply_saddle([lambda;U]) = [slip - kBT*RFD - BI ; F_ext]  at q';
  *   q <- q + dt*U from the ORIGINAL configuration (evolve_X_Q, :865-878).
  * F_ext: 6*n_bod.  slip: 3*N or NULL (zero).  W1, W2, Wr: 3*N standard-normal vectors supplied by
  * the caller (the reference seeds its generator from the wall clock, :731); all three NULL or

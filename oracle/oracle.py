@@ -471,8 +471,8 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
     it) and evaluated with dense float64 linear algebra:
       M^{1/2}W by scipy sqrtm of B M B (the reference uses the Cholesky factor, :661-675 -- a
       different square root with the same covariance; Lanczos converges to the symmetric one),
-      RFD of M (:769-796) and of K^T (:842-863), BI (:945-948), midpoint (:954-958), dense solve of
-      [M -K; K^T 0][lam;U] = [slip - kBT RFD_M - BI ; F_ext - kBT RFD_KT] at the midpoint, evolve from q^n.
+      RFD (:769-796), BI (:945-948), midpoint (:954-958), dense solve of
+      [M -K; K^T 0][lam;U] = [slip - kBT RFD - BI ; F_ext] at the midpoint, evolve from q^n.
     Returns (U, X_new, Q_new)."""
     from scipy.linalg import sqrtm
 
@@ -503,8 +503,6 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
         Xn, Qn = update_X_Q(X, Q, -0.5 * delta * uom)
         rp, rn = blob_positions(Xp, Qp, ref), blob_positions(Xn, Qn, ref)
         rfd = (apply_M(Wr, rp, a, eta, wall) - apply_M(Wr, rn, a, eta, wall)) / delta
-        # force-row drift -kBT (d_k K^T) K^-T e_k  (KT_RFD_from_U, :842-863)
-        F_drift = -kBT * (KT_dot(Wr, rp, Xp, n_blb) - KT_dot(Wr, rn, Xn, n_blb)) / delta
         c1, c2 = 2.0 * np.sqrt(kBT / dt), np.sqrt(kBT / dt)
         rhs_slip -= kBT * rfd + c2 * (mh1 - mh2)
         Xm, Qm = update_X_Q(X, Q, 0.5 * dt * Kinv_apply(c1 * mh1, r, X, Q, ref))
@@ -515,10 +513,7 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
         Mm = B[:, None] * Mm * B[None, :]
     K = K_dense(rm, Xm, n_blb)
     A = np.block([[Mm, -K], [K.T, np.zeros((6 * nb, 6 * nb))]])
-    rhs_F = np.asarray(F_ext, dtype=np.float64).reshape(-1).copy()
-    if kBT > 0:
-        rhs_F += F_drift
-    sol = np.linalg.solve(A, np.concatenate([rhs_slip, rhs_F]))
+    sol = np.linalg.solve(A, np.concatenate([rhs_slip, np.asarray(F_ext, dtype=np.float64).reshape(-1)]))
     U = sol[n3:]
     Xn, Qn = evolve(X, Q, U, dt)
     return U, Xn, Qn

@@ -167,7 +167,7 @@ struct Ctx final : rbl_ctx {
   // partitioned mode (comm != nullptr): all-gathered positions / forces, partial product, agreed status
   DevBuf d_r_all, d_lam_all, d_mbuf, d_status;
   // two-right-hand-side product / paired Lanczos
-  DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2, d_ktr;
+  DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2;
   // noise preconditioner: Cholesky factors L of the bodies' own mobility blocks and G = L^-1
   DevBuf d_NL, d_NG, d_nt1, d_nt2, d_nu1, d_nu2;
   bool noise_set = false, noise_ok = false, noise_shared = false, noise_shared_ready = false;
@@ -1451,22 +1451,17 @@ struct Ctx final : rbl_ctx {
       RET(h2d(noise, Wr, n3 * sizeof(real)));
       RET(kinv_dev(noise, d_uom.as<real>()));
       real* Mpm[2] = {d_t1.as<real>(), d_t2.as<real>()};
-      CK(d_ktr.ensure(2 * n6 * sizeof(real)));
       for (int sgn = 0; sgn < 2; ++sgn) {
         LAUNCH(1, rbl::integrate<real>(d_uom.as<real>(), (real)((sgn ? -0.5 : 0.5) * delta), n_bod, d_X.as<real>(),
                                        d_Q.as<real>(), d_Xp.as<real>(), d_Qp.as<real>(), stream));
         LAUNCH(1, rbl::place_blobs<real>(d_Xp.as<real>(), d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb,
                                          d_rp.as<real>(), stream));
         RET(prod_M(noise, d_rp.as<real>(), false, Mpm[sgn]));
-        // K^T(q+-) W_r for the force-row drift (KT_RFD_from_U, :842-863)
-        LAUNCH(1, rbl::kt_dot<real>(noise, d_rp.as<real>(), d_Xp.as<real>(), n_bod, n_blb, d_ktr.as<real>() + sgn * n6, stream));
       }
       LAUNCH(1, rbl::scale_copy<real>(d_t1.as<real>(), (real)(1.0 / delta), d_rfd.as<real>(), n3, false, stream));
       LAUNCH(1, rbl::scale_copy<real>(d_t2.as<real>(), (real)(-1.0 / delta), d_rfd.as<real>(), n3, true, stream));
-      // force row += -kBT (K^T(q+) - K^T(q-)) W_r / delta : with the midpoint evaluation of N K^T M^-1 this
-      // completes kBT div(N) for bodies whose lever-arm moment tensor is not isotropic
-      LAUNCH(1, rbl::scale_copy<real>(d_ktr.as<real>(), (real)(-kBT_ / delta), rhs + n3, n6, true, stream));
-      LAUNCH(1, rbl::scale_copy<real>(d_ktr.as<real>() + n6, (real)(kBT_ / delta), rhs + n3, n6, true, stream));
+      // (no K^T finite difference in the force row: with q+- = q +- (delta/2) K^-1 W_r its expectation
+      // (d_k K^T) K^-T e_k vanishes identically -- tests/test_oracle_bd_drift.py)
       // RHS slip -= kBT * RFD + c2 (M^{1/2}W1 - M^{1/2}W2)   (:945-948,963)
       const double c1 = 2.0 * std::sqrt(kBT_ / dt), c2 = std::sqrt(kBT_ / dt);
       LAUNCH(1, rbl::scale_copy<real>(d_rfd.as<real>(), (real)(-kBT_), rhs, n3, true, stream));
