@@ -160,6 +160,8 @@ struct Ctx final : rbl_ctx {
   // preconditioner
   DevBuf d_dinv, d_Minv, d_Kc, d_Y, d_L, d_y;
   bool pc_shared = false;
+  bool pc_chol = false;  // block PC with the wall: Mt^-1 = G^T G from the bodies' Cholesky factors (d_NG)
+  DevBuf d_pt;           // scratch for the two-stage G^T (G x) products
   // krylov
   DevBuf d_V, d_w, d_z, d_tmp, d_partial, d_coef, d_dots;
   // BD step
@@ -705,6 +707,7 @@ struct Ctx final : rbl_ctx {
     CK(d_y.ensure(n3 * sizeof(real)));
     int* fl = d_flags.as<int>();
     LAUNCH(1, rbl::pc_fill_kcols<real>(d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, d_Kc.as<real>(), stream));
+    pc_chol = false;
     if (!block_pc) {
       CK(d_dinv.ensure(n3 * sizeof(real)));
       LAUNCH(1, rbl::pc_diag_build<real>(d_r.as<real>(), (int)N(), (real)a, (real)eta, wall, d_dinv.as<real>(), fl + FLAG_BELOW, stream));
@@ -718,20 +721,34 @@ struct Ctx final : rbl_ctx {
       LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), 0, d_Q.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
     } else {
       pc_shared = false;
-      const size_t bytes = (size_t)n_bod * sz * sz * sizeof(real);
-      cudaError_t e = d_Minv.ensure(bytes);
-      if (e != cudaSuccess) {
-        cudaGetLastError();
-        char msg[256];
-        snprintf(msg, sizeof(msg),
-                 "block preconditioner with wall needs %.1f GB for %d dense %dx%d body blocks; use the "
-                 "diagonal preconditioner (block_PC=False) at this size",
-                 bytes / 1e9, n_bod, sz, sz);
-        return fail(RBL_ERR_NOMEM, msg);
+      // Mt_b^-1 = G_b^T G_b from the Cholesky factors the noise preconditioner uses (same matrices:
+      // 1/6 of the memory traffic of the Gauss-Jordan inverse below); Gauss-Jordan remains the path
+      // for blocks that are not positive definite (blobs inside the wall-overlap layer).
+      if (!noise_set) RET(build_noise_pc());
+      pc_chol = noise_ok && !noise_shared;
+      if (pc_chol) {
+        CK(d_pt.ensure(6 * n3 * sizeof(real)));
+        const size_t st2 = (size_t)sz * sz;
+        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, false, d_Kc.as<real>(), n_bod, n_blb,
+                                          d_pt.as<real>(), stream, 6));
+        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, true, d_pt.as<real>(), n_bod, n_blb,
+                                          d_Y.as<real>(), stream, 6));
+      } else {
+        const size_t bytes = (size_t)n_bod * sz * sz * sizeof(real);
+        cudaError_t e = d_Minv.ensure(bytes);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          char msg[256];
+          snprintf(msg, sizeof(msg),
+                   "block preconditioner with wall needs %.1f GB for %d dense %dx%d body blocks; use the "
+                   "diagonal preconditioner (block_PC=False) at this size",
+                   bytes / 1e9, n_bod, sz, sz);
+          return fail(RBL_ERR_NOMEM, msg);
+        }
+        LAUNCH(1, rbl::pc_block_assemble<real>(d_r.as<real>(), n_bod, n_blb, (real)a, (real)eta, true, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
+        LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), n_bod, sz, fl + FLAG_NOT_SPD, stream));
+        LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), (size_t)sz * sz, nullptr, d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
       }
-      LAUNCH(1, rbl::pc_block_assemble<real>(d_r.as<real>(), n_bod, n_blb, (real)a, (real)eta, true, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
-      LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), n_bod, sz, fl + FLAG_NOT_SPD, stream));
-      LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), (size_t)sz * sz, nullptr, d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
     }
     LAUNCH(1, rbl::pc_ninv_chol<real>(d_Y.as<real>(), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, d_L.as<real>(), fl + FLAG_NOT_SPD, stream));
     RET(sync());  // below-wall / not-SPD surface here, like the reference's lazy build (:591-596)
@@ -744,9 +761,13 @@ struct Ctx final : rbl_ctx {
     if (!pc_set) RET(build_pc());
     const int sz = 3 * n_blb;
     const size_t n3 = 3 * (size_t)N();
-    if (!block_pc)
+    if (!block_pc) {
       LAUNCH(1, rbl::pc_diag_mul<real>(d_dinv.as<real>(), din, n_bod, n_blb, 1, d_y.as<real>(), stream));
-    else
+    } else if (pc_chol) {
+      const size_t st2 = (size_t)sz * sz;
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, false, din, n_bod, n_blb, d_pt.as<real>(), stream));
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, true, d_pt.as<real>(), n_bod, n_blb, d_y.as<real>(), stream));
+    } else
       LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), pc_shared ? 0 : (size_t)sz * sz, pc_shared ? d_Q.as<real>() : nullptr,
                                         din, n_bod, n_blb, 1, d_y.as<real>(), stream));
     LAUNCH(1, rbl::pc_finish<real>(d_y.as<real>(), din + n3, d_Y.as<real>(), d_L.as<real>(), d_r.as<real>(), d_X.as<real>(),
@@ -1122,21 +1143,14 @@ struct Ctx final : rbl_ctx {
 
 
   // ---- noise preconditioner ---------------------------------------------------------------------
-  int reduce_max_int(int v, int* out) {
-    *out = v;
-    if (!comm) return RBL_OK;
-    CK(cudaMemcpyAsync(d_status.p, &v, sizeof(int), cudaMemcpyHostToDevice, stream));
-    NK(comm->allreduce_max_int(d_status.as<int>(), 1, stream));
-    CK(cudaMemcpyAsync(out, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    return RBL_OK;
-  }
   // L_b = chol(Mt_b), G_b = L_b^-1 for the bodies of this context.  Free space: ONE factor of the
   // reference shape (M_b = R M_ref R^T  =>  L_b = R L_ref), computed once per parameter set.  With the
-  // wall: one factor per body and configuration.  noise_ok = false (plain Lanczos) when a block is not
-  // positive definite (blobs inside the wall-overlap layer) or the factors do not fit in memory.
+  // wall: one factor per body and configuration.  noise_ok = false (L = I for this context's bodies)
+  // when a block is not positive definite (blobs inside the wall-overlap layer) or the factors do not fit.
   int build_noise_pc() {
     RET(need_K());
+    // a block PC built on these factors (pc_chol) goes with them: it is rebuilt at its next use
+    if (pc_set && pc_chol) pc_set = false;
     const int sz = 3 * n_blb;
     int* fl = d_flags.as<int>();
     int bad = 0;
@@ -1176,9 +1190,9 @@ struct Ctx final : rbl_ctx {
         bad = 1;
       }
     }
-    int any_bad = 0;
-    RET(reduce_max_int(bad, &any_bad));  // all ranks precondition, or none
-    noise_ok = !any_bad;
+    // rank-local on purpose (no collective here): a rank that falls back simply uses L = I for ITS
+    // bodies, which is still a valid block-diagonal preconditioner of the global operator
+    noise_ok = !bad;
     if (noise_ok && !wall) noise_shared_ready = true;
     noise_set = true;
     const size_t n3 = 3 * (size_t)N();

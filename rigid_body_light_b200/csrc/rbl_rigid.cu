@@ -698,16 +698,18 @@ cudaError_t tri_inverse(const real* L, real* G, int count, int sz, cudaStream_t 
 // product, rot_out applies R_b after it.  Thread per output row, x staged in shared memory.
 template <typename real>
 __global__ void body_mat_mul_kernel(const real* __restrict__ A0, size_t stride, const real* __restrict__ Q, int rot_in,
-                                    int rot_out, int trans, const real* __restrict__ in, int sz, real* __restrict__ out) {
+                                    int rot_out, int trans, const real* __restrict__ in, int sz, int ncols,
+                                    real* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* x = reinterpret_cast<real*>(smem_raw);  // sz
   __shared__ real tile[192];
-  const int b = blockIdx.y;
+  const int v = blockIdx.y;     // vector index: layout [body][column][sz]
+  const int b = v / ncols;      // its body
   const int row = blockIdx.x * 192 + threadIdx.x;
   const real* A = A0 + stride * b;
   real R[9];
   if (rot_in || rot_out) quat_to_rot(Q + 4 * (size_t)b, R);
-  const real* xin = in + (size_t)b * sz;
+  const real* xin = in + (size_t)v * sz;
   if (rot_in) {
     for (int k = threadIdx.x; k < sz / 3; k += blockDim.x) {
       const real vx = xin[3 * k], vy = xin[3 * k + 1], vz = xin[3 * k + 2];
@@ -730,7 +732,7 @@ __global__ void body_mat_mul_kernel(const real* __restrict__ A0, size_t stride, 
       for (int j = 0; j < sz; ++j) acc += Ar[j] * x[j];
     }
   }
-  real* o = out + (size_t)b * sz;
+  real* o = out + (size_t)v * sz;
   if (rot_out) {
     tile[threadIdx.x] = acc;
     __syncthreads();
@@ -744,14 +746,14 @@ __global__ void body_mat_mul_kernel(const real* __restrict__ A0, size_t stride, 
 }
 template <typename real>
 cudaError_t body_mat_mul(const real* A, size_t stride, const real* Q, bool rot_in, bool rot_out, bool trans,
-                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s) {
-  if (n_bod <= 0) return cudaSuccess;
+                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s, int ncols) {
+  if (n_bod <= 0 || ncols <= 0) return cudaSuccess;
   const int sz = 3 * n_blb;
   const size_t smem = (size_t)sz * sizeof(real);
   cudaError_t e = cudaFuncSetAttribute(body_mat_mul_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((sz + 191) / 192, n_bod);
-  body_mat_mul_kernel<real><<<grid, 192, smem, s>>>(A, stride, Q, rot_in ? 1 : 0, rot_out ? 1 : 0, trans ? 1 : 0, in, sz, out);
+  dim3 grid((sz + 191) / 192, (unsigned)n_bod * ncols);
+  body_mat_mul_kernel<real><<<grid, 192, smem, s>>>(A, stride, Q, rot_in ? 1 : 0, rot_out ? 1 : 0, trans ? 1 : 0, in, sz, ncols, out);
   return cudaGetLastError();
 }
 
@@ -823,7 +825,7 @@ cudaError_t integrate(const real* U, real scale, int n_bod, const real* X, const
   template cudaError_t chol_lower<real>(real*, int, int, int*, cudaStream_t);                       \
   template cudaError_t tri_inverse<real>(const real*, real*, int, int, cudaStream_t);               \
   template cudaError_t body_mat_mul<real>(const real*, size_t, const real*, bool, bool, bool,       \
-                                          const real*, int, int, real*, cudaStream_t);              \
+                                          const real*, int, int, real*, cudaStream_t, int);         \
   template cudaError_t integrate<real>(const real*, real, int, const real*, const real*, real*,     \
                                        real*, cudaStream_t);
 INST(float)

@@ -100,7 +100,7 @@ cudaError_t tri_inverse(const real* L, real* G, int count, int sz, cudaStream_t 
 // blob before the product, rot_out: R_b after it)
 template <typename real>
 cudaError_t body_mat_mul(const real* A, size_t stride, const real* Q, bool rot_in, bool rot_out, bool trans,
-                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s);
+                         const real* in, int n_bod, int n_blb, real* out, cudaStream_t s, int ncols = 1);
 
 // ---- integrator ---------------------------------------------------------------------
 // Qo <- exp(omega * scale) Q (normalised), Xo <- X + u * scale  (scale = dt for
