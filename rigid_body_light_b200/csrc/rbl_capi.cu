@@ -712,27 +712,28 @@ struct Ctx final : rbl_ctx {
       CK(d_dinv.ensure(n3 * sizeof(real)));
       LAUNCH(1, rbl::pc_diag_build<real>(d_r.as<real>(), (int)N(), (real)a, (real)eta, wall, d_dinv.as<real>(), fl + FLAG_BELOW, stream));
       LAUNCH(1, rbl::pc_diag_mul<real>(d_dinv.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
-    } else if (!wall) {
-      // free space: one factorisation of the reference-shape body, rotated per body
-      pc_shared = true;
-      CK(d_Minv.ensure((size_t)sz * sz * sizeof(real)));
-      LAUNCH(1, rbl::pc_block_assemble<real>(d_ref.as<real>(), 1, n_blb, (real)a, (real)eta, false, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
-      LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), 1, sz, fl + FLAG_NOT_SPD, stream));
-      LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), 0, d_Q.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
     } else {
-      pc_shared = false;
-      // Mt_b^-1 = G_b^T G_b from the Cholesky factors the noise preconditioner uses (same matrices:
-      // 1/6 of the memory traffic of the Gauss-Jordan inverse below); Gauss-Jordan remains the path
-      // for blocks that are not positive definite (blobs inside the wall-overlap layer).
+      // Block PC.  Mt_b^-1 = G_b^T G_b from the Cholesky factors the noise preconditioner uses (the same
+      // matrices; 1/6 of the memory traffic of an explicit Gauss-Jordan inverse, and blocked kernels).
+      // Free space: ONE factor of the reference shape, M_b^-1 = R G_ref^T G_ref R^T (rotation covariance),
+      // where the reference inverts one dense matrix per body per configuration (:461-487).
+      // Gauss-Jordan remains the path for blocks that are not positive definite (blobs inside the
+      // wall-overlap layer, overlapping a = 1 test geometries).
+      pc_shared = !wall;
       if (!noise_set) RET(build_noise_pc());
-      pc_chol = noise_ok && !noise_shared;
+      pc_chol = noise_ok;
+      const size_t st2 = pc_shared ? 0 : (size_t)sz * sz;
       if (pc_chol) {
         CK(d_pt.ensure(6 * n3 * sizeof(real)));
-        const size_t st2 = (size_t)sz * sz;
-        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, false, d_Kc.as<real>(), n_bod, n_blb,
+        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, d_Q.as<real>(), pc_shared, false, false, d_Kc.as<real>(), n_bod, n_blb,
                                           d_pt.as<real>(), stream, 6));
-        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, true, d_pt.as<real>(), n_bod, n_blb,
+        LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, d_Q.as<real>(), false, pc_shared, true, d_pt.as<real>(), n_bod, n_blb,
                                           d_Y.as<real>(), stream, 6));
+      } else if (pc_shared) {
+        CK(d_Minv.ensure((size_t)sz * sz * sizeof(real)));
+        LAUNCH(1, rbl::pc_block_assemble<real>(d_ref.as<real>(), 1, n_blb, (real)a, (real)eta, false, d_Minv.as<real>(), fl + FLAG_BELOW, stream));
+        LAUNCH(1, rbl::pc_block_invert<real>(d_Minv.as<real>(), 1, sz, fl + FLAG_NOT_SPD, stream));
+        LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), 0, d_Q.as<real>(), d_Kc.as<real>(), n_bod, n_blb, 6, d_Y.as<real>(), stream));
       } else {
         const size_t bytes = (size_t)n_bod * sz * sz * sizeof(real);
         cudaError_t e = d_Minv.ensure(bytes);
@@ -764,9 +765,9 @@ struct Ctx final : rbl_ctx {
     if (!block_pc) {
       LAUNCH(1, rbl::pc_diag_mul<real>(d_dinv.as<real>(), din, n_bod, n_blb, 1, d_y.as<real>(), stream));
     } else if (pc_chol) {
-      const size_t st2 = (size_t)sz * sz;
-      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, false, din, n_bod, n_blb, d_pt.as<real>(), stream));
-      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, nullptr, false, false, true, d_pt.as<real>(), n_bod, n_blb, d_y.as<real>(), stream));
+      const size_t st2 = pc_shared ? 0 : (size_t)sz * sz;
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, d_Q.as<real>(), pc_shared, false, false, din, n_bod, n_blb, d_pt.as<real>(), stream));
+      LAUNCH(1, rbl::body_mat_mul<real>(d_NG.as<real>(), st2, d_Q.as<real>(), false, pc_shared, true, d_pt.as<real>(), n_bod, n_blb, d_y.as<real>(), stream));
     } else
       LAUNCH(1, rbl::pc_block_mul<real>(d_Minv.as<real>(), pc_shared ? 0 : (size_t)sz * sz, pc_shared ? d_Q.as<real>() : nullptr,
                                         din, n_bod, n_blb, 1, d_y.as<real>(), stream));
@@ -1150,7 +1151,7 @@ struct Ctx final : rbl_ctx {
   int build_noise_pc() {
     RET(need_K());
     // a block PC built on these factors (pc_chol) goes with them: it is rebuilt at its next use
-    if (pc_set && pc_chol) pc_set = false;
+    if (pc_set && pc_chol && wall) pc_set = false;  // (the shared free-space factor never changes)
     const int sz = 3 * n_blb;
     int* fl = d_flags.as<int>();
     int bad = 0;
