@@ -15,6 +15,8 @@ Run HERE (the build container), where /root/reference exists:
 * ``case_*.npz``       -- seeded small suspensions with the float64 oracle's outputs for
   every operator of the hot path (apply_M, K, K^T, Kinv, both PCs, saddle, evolve).
   The reference itself holds no golden values for these.
+* ``bd_golden.npz``    -- one fluctuating BD step per touching-sphere case with fixed noise through
+  the dense oracle (both Brownian-increment routes).  ``--bd-only`` regenerates just this file.
 """
 import ctypes
 import os
@@ -133,8 +135,43 @@ def make_case(name):
     print(name, "N =", r.shape[0], "zmin/a =", r[:, 2].min() / a)
 
 
+def bd_golden():
+    """One fluctuating BD step per touching-sphere case with FIXED noise, through the dense oracle:
+    Brownian increments by both routes (symmetric square root; block-Cholesky preconditioned root)
+    and the resulting rigid velocities / new configuration.  Pins oracle.bd_step and gives the
+    GPU tests a committed target for rbl_bd_step / rbl_lanczos_sqrt."""
+    out = {}
+    for name in ("case_touch_wall", "case_touch_free"):
+        g = dict(np.load(os.path.join(HERE, name + ".npz")))
+        a, eta, wall, dt = float(g["a"]), float(g["eta"]), bool(g["wall"]), float(g["dt"])
+        ref = orc.remove_mean(g["cfg"])
+        nb, n3 = g["X"].shape[0], g["r"].size
+        rng = np.random.default_rng(31)
+        F = rng.standard_normal(6 * nb)
+        W = [rng.standard_normal(n3) for _ in range(3)]
+        kBT = 0.004
+        M_raw = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
+        A = M_raw
+        if wall:
+            B = orc.damp_diag(g["r"], a)
+            A = B[:, None] * M_raw * B[None, :]
+        from scipy.linalg import sqrtm
+        out[f"{name}/F"], out[f"{name}/W"], out[f"{name}/kBT"] = F, np.array(W), np.array(kBT)
+        out[f"{name}/noise_symmetric"] = np.real(sqrtm(A)) @ W[0]
+        out[f"{name}/noise_block_cholesky"] = orc.noise_block_cholesky(orc.noise_factors(g["r"], g["Qn"], ref, a, eta, wall), A, W[0])
+        for mode in ("symmetric", "block_cholesky"):
+            U, Xn, Qn = orc.bd_step(g["X"], g["Qn"], ref, a, eta, dt, kBT, wall, F, None, *W, noise=mode)
+            out[f"{name}/{mode}/U"], out[f"{name}/{mode}/X"], out[f"{name}/{mode}/Q"] = U, Xn, Qn
+        print("bd_golden", name, "|U| =", np.linalg.norm(U))
+    np.savez_compressed(os.path.join(HERE, "bd_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--bd-only" in sys.argv:
+        bd_golden()
+        sys.exit(0)
     pair_golden()
     shells_check()
     for c in CASES:
         make_case(c)
+    bd_golden()

@@ -96,3 +96,21 @@ def test_suspension_builder_matches_survey_recipe():
     assert np.array_equal(s["X"], s2["X"])  # seeded
     f = sphere_suspension(1000, 2562, False)
     assert f["X"][:, 2].max() > 20  # a cube, not a monolayer
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/rbl.h compiled as C99 (-pedantic -Werror) into a host that links librbl.so alone:
+    no C++ or torch types cross the ABI.  Without a GPU the host sees the documented failure."""
+    import subprocess
+
+    from rigid_body_light_b200 import _lib
+
+    exe = str(tmp_path / "capi_c_host")
+    libdir = os.path.dirname(_lib.lib_path())
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "host", "capi_c_host.c"), "-o", exe, "-L", libdir, "-lrbl",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ("DEVICE-OK" in r.stdout) if _cuda_present() else ("NO-DEVICE" in r.stdout and "no CPU fallback" in r.stdout)

@@ -328,3 +328,24 @@ def test_noise_factor_selfcheck_at_large_body_sizes(shell, n_bodies, wall, preci
     lim = 1e-10 if precision == "double" else 2e-3
     assert f.value < lim and g.value < lim, (f.value, g.value)
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_step_matches_the_committed_golden_step(name, mode):
+    """rbl_bd_step against tests/golden/bd_golden.npz (dense-oracle step with fixed noise), for the
+    symmetric-root noise (mode 0) and the default block-Cholesky preconditioned noise (mode 1)."""
+    g, bd = load_golden(name), load_golden("bd_golden")
+    cb = _solver(g, "double", block=True)
+    cb.set_noise_preconditioner(mode)
+    key = f"{name}/{'block_cholesky' if mode else 'symmetric'}"
+    U, iters, relres = cb.bd_step(bd[f"{name}/F"], kBT=float(bd[f"{name}/kBT"]), noise=tuple(bd[f"{name}/W"]), tol=1e-11,
+                                  restart=100, max_iter=400, lanczos_tol=1e-12, lanczos_max_iter=200)
+    assert rel_err(U, bd[key + "/U"]) < 1e-6
+    X, Q = cb.get_config()
+    assert rel_err(X, bd[key + "/X"]) < 1e-8 and rel_err(Q, bd[key + "/Q"]) < 1e-8
+    # and the Brownian increment itself
+    cb2 = _solver(g, "double")
+    cb2.set_noise_preconditioner(2 if mode else 0)
+    y, _ = cb2.brownian_sqrt(bd[f"{name}/W"][0], tol=1e-12, max_iter=200)
+    assert rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]) < 1e-7

@@ -171,3 +171,19 @@ def test_golden_cases_reproduce(orc, name):
     if "pc_diag" in g:
         assert rel_err(orc.PC(g["X"], Qn, ref, a, eta, wall, False).apply(g["vec"]), g["pc_diag"]) < 1e-12
         assert rel_err(orc.PC(g["X"], Qn, ref, a, eta, wall, True).apply(g["vec"]), g["pc_block"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_golden_reproduces(orc, name):
+    """The committed BD-step fixture (tests/golden/bd_golden.npz) is what the dense oracle computes
+    today, for both Brownian-increment routes; the two routes give different vectors of the same
+    covariance, hence different (equally valid) steps."""
+    g, bd = load_golden(name), load_golden("bd_golden")
+    a, eta, wall, dt = float(g["a"]), float(g["eta"]), bool(g["wall"]), float(g["dt"])
+    ref = orc.remove_mean(g["cfg"])
+    W, F, kBT = bd[f"{name}/W"], bd[f"{name}/F"], float(bd[f"{name}/kBT"])
+    for mode in ("symmetric", "block_cholesky"):
+        U, Xn, Qn = orc.bd_step(g["X"], g["Qn"], ref, a, eta, dt, kBT, wall, F, None, *W, noise=mode)
+        assert rel_err(U, bd[f"{name}/{mode}/U"]) < 1e-9
+        assert rel_err(Xn, bd[f"{name}/{mode}/X"]) < 1e-12 and rel_err(Qn, bd[f"{name}/{mode}/Q"]) < 1e-12
+    assert rel_err(bd[f"{name}/symmetric/U"], bd[f"{name}/block_cholesky/U"]) > 1e-3
