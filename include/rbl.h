@@ -148,6 +148,19 @@ int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W
                 const void* Wr, double kBT, double gmres_tol, int restart, int max_iter,
                 double lanczos_tol, int lanczos_max_iter, void* U_out, int* gmres_iters, double* relres);
 
+/* rbl_bd_step with the three noise vectors drawn ON THE DEVICE: element e of (W1, W2, Wr) is a pure
+ * function of (seed, step, GLOBAL element index e) -- one Philox4x32-10 block per element, Box-Muller --
+ * so a trajectory is reproducible from (seed, first step) and does not depend on how the suspension
+ * is partitioned over GPUs (the reference seeds std::normal_distribution from the wall clock,
+ * :730-741).  rbl_normals / rbl_dev_normals expose the generator: n elements starting at global
+ * element `first` (host / device pointers). */
+int rbl_bd_step_seeded(rbl_ctx* ctx, const void* F_ext, const void* slip, uint64_t seed, uint64_t step, double kBT,
+                       double gmres_tol, int restart, int max_iter, double lanczos_tol, int lanczos_max_iter,
+                       void* U_out, int* gmres_iters, double* relres);
+int rbl_normals(rbl_ctx* ctx, uint64_t seed, uint64_t step, uint64_t first, size_t n, void* W1, void* W2, void* Wr);
+int rbl_dev_normals(rbl_ctx* ctx, uint64_t seed, uint64_t step, uint64_t first, size_t n, void* dW1, void* dW2,
+                    void* dWr);
+
 /* ---- device-resident API (device pointers, asynchronous on the context stream) ---- */
 /* Targets [tgt_first, tgt_first+n_tgt) of the n_blobs sources: out has 3*n_tgt reals.
  * This is the entry a multi-GPU host shards by body range. */

@@ -425,6 +425,35 @@ def Kinv_apply(v, r, X, Q, ref_cfg):
     return np.einsum("bij,bj->bi", G, y).reshape(-1)
 
 
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123) on arrays of counters: ``counter`` = four
+    uint32 arrays, ``key`` = two uint32 scalars.  Returns four uint32 arrays.  Checked against the
+    Random123 known-answer vectors in tests/test_oracle_physics.py."""
+    c = [np.asarray(x, dtype=np.uint64) for x in counter]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, mask, s32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF), np.uint64(32)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> s32) ^ c[1] ^ k0, p1 & mask, (p0 >> s32) ^ c[3] ^ k1, p0 & mask]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def philox_normals(seed, step, first, n):
+    """The three standard-normal vectors (W1, W2, Wr) of BD step ``step`` for global elements
+    [first, first + n): element e uses ONE Philox block with counter (e_lo, e_hi, step_lo, step_hi)
+    and key (seed_lo, seed_hi); W1, W2 = Box-Muller pair of words 0,1; Wr = cosine branch of words
+    2,3 (rbl_krylov.cu normal_triplet_kernel; include/rbl.h rbl_bd_step_seeded)."""
+    e = np.uint64(first) + np.arange(n, dtype=np.uint64)
+    m, s32 = np.uint64(0xFFFFFFFF), np.uint64(32)
+    step, seed = np.uint64(step), np.uint64(seed)
+    r = philox4x32_10([e & m, e >> s32, np.full(n, step & m), np.full(n, step >> s32)], [seed & m, seed >> s32])
+    u = [(x.astype(np.float64) + 0.5) * 2.3283064365386963e-10 for x in r]
+    ra, rb = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
+    return ra * np.cos(2 * np.pi * u[1]), ra * np.sin(2 * np.pi * u[1]), rb * np.cos(2 * np.pi * u[3])
+
+
 def noise_factors(r, Q, ref_cfg, a, eta, wall):
     """Per-body factors L_b with L_b L_b^T = Mt_b, the body's own mobility block (no B damping),
     as the product path builds them: with the wall, the lower Cholesky factor of each body's block;

@@ -161,12 +161,14 @@ class RigidBody:
         self.cb.set_noise_preconditioner(int(mode))
 
     def bd_step(self, F_ext, slip=None, kBT=0.0, noise=None, rng=None, tol=1e-8, restart=60, max_iter=300,
-                lanczos_tol=1e-6, lanczos_max_iter=100):
+                lanczos_tol=1e-6, lanczos_max_iter=100, seed=None, step=0):
         """Advance the bodies by one (Brownian) step with the trapezoidal-slip midpoint scheme
         the reference sets up in RHS_and_Midpoint (c_rigid_obj.cpp:917-976), entirely on the
         device.  ``F_ext``: external force/torque per body (6*N_bodies); ``slip``: prescribed
         blob slip (3*N_blobs) or None; ``noise`` = (W1, W2, Wr) standard-normal 3*N_blobs
-        vectors, drawn from ``rng`` (numpy Generator) when kBT > 0 and noise is None.
+        vectors, drawn from ``rng`` (numpy Generator) when kBT > 0 and noise is None; or pass
+        ``seed`` (and the ``step`` number) to draw them on the device with the counter-based generator
+        (a pure function of seed, step and blob index: reproducible, partition invariant).
         Returns (U, gmres_iterations, relative_residual)."""
         F_ext = np.asarray(F_ext)
         self._need(F_ext, 6 * self.N_bodies, "F_ext", "6*N_bodies")
@@ -175,6 +177,9 @@ class RigidBody:
             slip = np.asarray(slip)
             self._need(slip, n3, "slip", "3*N_blobs")
             slip = slip.reshape(-1)
+        if seed is not None and kBT > 0 and noise is None:
+            return self.cb.bd_step_seeded(F_ext.reshape(-1), slip, int(seed), int(step), float(kBT), tol, restart, max_iter,
+                                          lanczos_tol, lanczos_max_iter)
         W1 = W2 = Wr = None
         if kBT > 0:
             if noise is None:

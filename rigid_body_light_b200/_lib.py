@@ -49,6 +49,9 @@ SYMBOLS = {
     "rbl_export_Kinv_csc": (_i, [_vp, _vp, _vp, _vp]),
     "rbl_gmres": (_i, [_vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     "rbl_lanczos_sqrt": (_i, [_vp, _vp, _vp, _d, _i, _pi]),
+    "rbl_bd_step_seeded": (_i, [_vp, _vp, _vp, _c.c_uint64, _c.c_uint64, _d, _d, _i, _i, _d, _i, _vp, _pi, _pd]),
+    "rbl_normals": (_i, [_vp, _c.c_uint64, _c.c_uint64, _c.c_uint64, _sz, _vp, _vp, _vp]),
+    "rbl_dev_normals": (_i, [_vp, _c.c_uint64, _c.c_uint64, _c.c_uint64, _sz, _vp, _vp, _vp]),
     "rbl_apply_M2": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "rbl_dev_apply_M2": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "rbl_lanczos_sqrt2": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _pi]),

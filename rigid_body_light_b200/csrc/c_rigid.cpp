@@ -203,6 +203,29 @@ class CManyBodies {
                       &iters, &relres));
     return py::make_tuple(U, iters, relres);
   }
+  py::tuple bd_step_seeded(Arr F_ext, py::object slip, std::uint64_t seed, std::uint64_t step, double kBT, double tol,
+                           int restart, int max_iter, double ltol, int lmax) {
+    want(F_ext, n6(), "bd_step F_ext");
+    Arr keep;
+    const real* ps = nullptr;
+    if (!slip.is_none()) {
+      keep = Arr::ensure(slip);
+      if (!keep) throw std::runtime_error("bd_step slip: not convertible to a float array");
+      want(keep, n3(), "bd_step slip");
+      ps = keep.data();
+    }
+    py::array_t<real> U(n6());
+    int iters = 0;
+    double relres = 0;
+    check(rbl_bd_step_seeded(ctx_, F_ext.data(), ps, seed, step, kBT, tol, restart, max_iter, ltol, lmax, U.mutable_data(),
+                             &iters, &relres));
+    return py::make_tuple(U, iters, relres);
+  }
+  py::tuple normals(std::uint64_t seed, std::uint64_t step, std::uint64_t first, py::ssize_t n) {
+    py::array_t<real> a(n), b(n), c(n);
+    check(rbl_normals(ctx_, seed, step, first, (size_t)n, a.mutable_data(), b.mutable_data(), c.mutable_data()));
+    return py::make_tuple(a, b, c);
+  }
   void set_noise_preconditioner(int mode) { check(rbl_set_noise_preconditioner(ctx_, mode)); }
   void set_lanczos_pairing(bool on) { check(rbl_set_lanczos_pairing(ctx_, on ? 1 : 0)); }
   std::uintptr_t handle() const { return reinterpret_cast<std::uintptr_t>(ctx_); }
@@ -245,6 +268,10 @@ PYBIND11_MODULE(RBL_MODULE_NAME, m) {
            py::arg("W2") = py::none(), py::arg("Wr") = py::none(), py::arg("kBT") = 0.0, py::arg("tol") = 1e-8,
            py::arg("restart") = 60, py::arg("max_iter") = 300, py::arg("lanczos_tol") = 1e-6,
            py::arg("lanczos_max_iter") = 100)
+      .def("bd_step_seeded", &CManyBodies::bd_step_seeded, py::arg("F_ext"), py::arg("slip") = py::none(), py::arg("seed") = 0,
+           py::arg("step") = 0, py::arg("kBT") = 0.0, py::arg("tol") = 1e-8, py::arg("restart") = 60, py::arg("max_iter") = 300,
+           py::arg("lanczos_tol") = 1e-6, py::arg("lanczos_max_iter") = 100)
+      .def("normals", &CManyBodies::normals, py::arg("seed"), py::arg("step"), py::arg("first"), py::arg("n"))
       .def("set_noise_preconditioner", &CManyBodies::set_noise_preconditioner, py::arg("mode"),
            "0: symmetric square root; 1: block-Cholesky preconditioned noise in bd_step (default); 2: also in lanczos_sqrt")
       .def("set_lanczos_pairing", &CManyBodies::set_lanczos_pairing, py::arg("on"))

@@ -86,6 +86,11 @@ struct rbl_ctx {
   virtual int bd_step(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, double kBT,
                       double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
                       double* relres) = 0;
+  virtual int bd_step_seeded(const void* F_ext, const void* slip, unsigned long long seed, unsigned long long step,
+                             double kBT, double tol, int restart, int max_iter, double ltol, int lmax, void* U_out,
+                             int* iters, double* relres) = 0;
+  virtual int normals(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n, void* W1,
+                      void* W2, void* Wr, bool dev) = 0;
   virtual int sync() = 0;
   virtual int fma_peak(int iters, double* tflops) = 0;
   virtual int num_variants() const = 0;
@@ -169,7 +174,7 @@ struct Ctx final : rbl_ctx {
   // partitioned mode (comm != nullptr): all-gathered positions / forces, partial product, agreed status
   DevBuf d_r_all, d_lam_all, d_mbuf, d_status;
   // two-right-hand-side product / paired Lanczos
-  DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2;
+  DevBuf d_rec2, d_raw2, d_V2, d_w2, d_in2, d_out2, d_wr;
   // noise preconditioner: Cholesky factors L of the bodies' own mobility blocks and G = L^-1
   DevBuf d_NL, d_NG, d_nt1, d_nt2, d_nu1, d_nu2;
   bool noise_set = false, noise_ok = false, noise_shared = false, noise_shared_ready = false;
@@ -1425,10 +1430,39 @@ struct Ctx final : rbl_ctx {
   int bd_step(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, double kBT_,
               double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
               double* relres) override {
-    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
-    if (!F_ext || !U_out) return fail(RBL_ERR_INVALID, "bd_step: F_ext and U_out are required");
     const bool brownian = kBT_ > 0 && W1 && W2 && Wr;
     if (kBT_ > 0 && !brownian) return fail(RBL_ERR_INVALID, "bd_step: kBT > 0 needs the three noise vectors W1, W2, Wr");
+    return bd_step_core(F_ext, slip, W1, W2, Wr, false, 0, 0, kBT_, tol, restart, max_iter, ltol, lmax, U_out, iters, relres);
+  }
+  int bd_step_seeded(const void* F_ext, const void* slip, unsigned long long seed, unsigned long long step, double kBT_,
+                     double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
+                     double* relres) override {
+    return bd_step_core(F_ext, slip, nullptr, nullptr, nullptr, true, seed, step, kBT_, tol, restart, max_iter, ltol, lmax,
+                        U_out, iters, relres);
+  }
+  // global index of this context's first vector element (partitioned: after the lower ranks' blobs)
+  unsigned long long first_element() const { return comm ? 3ull * (unsigned long long)comm->first[comm->rank] : 0ull; }
+  int normals(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n, void* W1, void* W2,
+              void* Wr, bool dev) override {
+    if (!W1 || !W2 || !Wr) return fail(RBL_ERR_INVALID, "normals: three output vectors are required");
+    if (dev) {
+      LAUNCH(1, rbl::normal_triplet<real>(seed, step, first, n, static_cast<real*>(W1), static_cast<real*>(W2),
+                                          static_cast<real*>(Wr), stream));
+      return RBL_OK;
+    }
+    for (DevBuf* b : {&d_in0, &d_in1, &d_in2}) CK(b->ensure(n * sizeof(real)));
+    LAUNCH(1, rbl::normal_triplet<real>(seed, step, first, n, d_in0.as<real>(), d_in1.as<real>(), d_in2.as<real>(), stream));
+    RET(d2h(W1, d_in0.p, n * sizeof(real)));
+    RET(d2h(W2, d_in1.p, n * sizeof(real)));
+    RET(d2h(Wr, d_in2.p, n * sizeof(real)));
+    return sync();
+  }
+  int bd_step_core(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, bool rng,
+                   unsigned long long seed, unsigned long long step, double kBT_, double tol, int restart, int max_iter,
+                   double ltol, int lmax, void* U_out, int* iters, double* relres) {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!F_ext || !U_out) return fail(RBL_ERR_INVALID, "bd_step: F_ext and U_out are required");
+    const bool brownian = kBT_ > 0 && (rng || (W1 && W2 && Wr));
     if (brownian && !(dt > 0)) return fail(RBL_ERR_INVALID, "bd_step: dt must be positive");
     RET(need_K());
     const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod, n = n3 + n6;
@@ -1445,25 +1479,29 @@ struct Ctx final : rbl_ctx {
       CK(d_uom.ensure(n6 * sizeof(real)));
       for (DevBuf* b : {&d_Xs, &d_Xp}) CK(b->ensure(3 * (size_t)n_bod * sizeof(real)));
       for (DevBuf* b : {&d_Qs, &d_Qp}) CK(b->ensure(4 * (size_t)n_bod * sizeof(real)));
-      real* noise = d_noise.as<real>();
+      CK(d_wr.ensure(n3 * sizeof(real)));
+      real* w1 = d_noise.as<real>();
+      real* w2 = d_rfd.as<real>();  // d_rfd is free until the RFD below
+      real* noise = d_wr.as<real>();  // W_r of the random finite difference
+      if (rng) {  // counter-based normals on the device, a pure function of (seed, step, global element)
+        LAUNCH(1, rbl::normal_triplet<real>(seed, step, first_element(), n3, w1, w2, noise, stream));
+      } else {
+        RET(h2d(w1, W1, n3 * sizeof(real)));
+        RET(h2d(w2, W2, n3 * sizeof(real)));
+        RET(h2d(noise, Wr, n3 * sizeof(real)));
+      }
       int it = 0;
       // Brownian increments at q^n  (M_half_W, :661-675, via Lanczos)
       if (pair_lanczos) {
-        RET(h2d(noise, W1, n3 * sizeof(real)));
-        RET(h2d(d_rfd.p, W2, n3 * sizeof(real)));  // d_rfd is free until the RFD below
-        RET(dev_lanczos2(noise, d_rfd.as<real>(), d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos,
-                         noise_mode >= 1));
+        RET(dev_lanczos2(w1, w2, d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos, noise_mode >= 1));
       } else {
-        RET(h2d(noise, W1, n3 * sizeof(real)));
-        RET(dev_lanczos(noise, d_mh1.as<real>(), ltol, lmax, &it, noise_mode >= 1));
+        RET(dev_lanczos(w1, d_mh1.as<real>(), ltol, lmax, &it, noise_mode >= 1));
         last_lanczos[0] = it;
-        RET(h2d(noise, W2, n3 * sizeof(real)));
-        RET(dev_lanczos(noise, d_mh2.as<real>(), ltol, lmax, &it, noise_mode >= 1));
+        RET(dev_lanczos(w2, d_mh2.as<real>(), ltol, lmax, &it, noise_mode >= 1));
         last_lanczos[1] = it;
       }
       // random finite difference  (M_RFD, :769-796)
       const double delta = sizeof(real) == 8 ? 1.0e-4 : 4.0e-3;
-      RET(h2d(noise, Wr, n3 * sizeof(real)));
       RET(kinv_dev(noise, d_uom.as<real>()));
       real* Mpm[2] = {d_t1.as<real>(), d_t2.as<real>()};
       for (int sgn = 0; sgn < 2; ++sgn) {
@@ -1671,6 +1709,24 @@ int rbl_bd_step(rbl_ctx* ctx, const void* F_ext, const void* slip, const void* W
   return s;
 }
 
+int rbl_bd_step_seeded(rbl_ctx* ctx, const void* F_ext, const void* slip, uint64_t seed, uint64_t step, double kBT,
+                       double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
+                       double* relres) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  int it = 0; double rr = 0;
+  int s = ctx->bd_step_seeded(F_ext, slip, seed, step, kBT, tol, restart, max_iter, ltol, lmax, U_out, &it, &rr);
+  if (iters) *iters = it;
+  if (relres) *relres = rr;
+  return s;
+}
+int rbl_normals(rbl_ctx* ctx, uint64_t seed, uint64_t step, uint64_t first, size_t n, void* W1, void* W2, void* Wr) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->normals(seed, step, first, n, W1, W2, Wr, false);
+}
+int rbl_dev_normals(rbl_ctx* ctx, uint64_t seed, uint64_t step, uint64_t first, size_t n, void* dW1, void* dW2, void* dWr) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->normals(seed, step, first, n, dW1, dW2, dWr, true);
+}
 int rbl_apply_M2(rbl_ctx* ctx, const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) {
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
   return ctx->apply_M2(F1, F2, r, n, out1, out2);

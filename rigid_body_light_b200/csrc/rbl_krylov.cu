@@ -1,4 +1,6 @@
 // rbl_krylov.cu -- see rbl_krylov.cuh
+#include <cstdint>
+
 #include "rbl_krylov.cuh"
 
 namespace rbl {
@@ -93,13 +95,68 @@ cudaError_t flip_tail(const real* x, size_t n_head, size_t n, real* y, cudaStrea
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Counter-based normal deviates (Philox4x32-10, Salmon et al. SC'11) for the Brownian step.
+// One Philox block per vector ELEMENT, keyed by (seed) and counted by (global element index,
+// step): element e of the three noise vectors of a step is a pure function of
+// (seed, step, e_global), so the noise -- and with it the trajectory -- does not depend on how the
+// suspension is partitioned over GPUs.  (The reference draws from std::normal_distribution seeded
+// with the wall clock, c_rigid_obj.cpp:730-741.)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <typename real>
+__global__ void normal_triplet_kernel(unsigned long long seed, unsigned long long step, unsigned long long first,
+                                      size_t n, real* __restrict__ w1, real* __restrict__ w2, real* __restrict__ wr) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long e = first + k;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    // Box-Muller in double (the uniforms have 32 bits; (r + 0.5) / 2^32 is never 0 or 1)
+    const double u0 = ((double)r[0] + 0.5) * 2.3283064365386963e-10, u1 = ((double)r[1] + 0.5) * 2.3283064365386963e-10;
+    const double u2 = ((double)r[2] + 0.5) * 2.3283064365386963e-10, u3 = ((double)r[3] + 0.5) * 2.3283064365386963e-10;
+    const double ra = sqrt(-2.0 * log(u0)), rb = sqrt(-2.0 * log(u2));
+    double sa, ca, sb, cb;
+    sincospi(2.0 * u1, &sa, &ca);
+    sincospi(2.0 * u3, &sb, &cb);
+    (void)sb;
+    w1[k] = (real)(ra * ca);
+    w2[k] = (real)(ra * sa);
+    wr[k] = (real)(rb * cb);
+  }
+}
+template <typename real>
+cudaError_t normal_triplet(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n,
+                           real* w1, real* w2, real* wr, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  normal_triplet_kernel<real><<<592, 256, 0, s>>>(seed, step, first, n, w1, w2, wr);
+  return cudaGetLastError();
+}
+
 #define INST(real)                                                                              \
   template cudaError_t multi_dot<real>(const real*, size_t, int, const real*, size_t, real*,    \
                                        real*, cudaStream_t);                                    \
   template cudaError_t multi_axpy<real>(const real*, size_t, int, const real*, real, real*,     \
                                         size_t, cudaStream_t);                                  \
   template cudaError_t scale_copy<real>(const real*, real, real*, size_t, bool, cudaStream_t);  \
-  template cudaError_t flip_tail<real>(const real*, size_t, size_t, real*, cudaStream_t);
+  template cudaError_t flip_tail<real>(const real*, size_t, size_t, real*, cudaStream_t);       \
+  template cudaError_t normal_triplet<real>(unsigned long long, unsigned long long,             \
+                                            unsigned long long, size_t, real*, real*, real*,    \
+                                            cudaStream_t);
 INST(float)
 INST(double)
 #undef INST

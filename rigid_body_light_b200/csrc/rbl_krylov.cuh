@@ -25,4 +25,11 @@ cudaError_t scale_copy(const real* x, real a, real* y, size_t n, bool accumulate
 template <typename real>
 cudaError_t flip_tail(const real* x, size_t n_head, size_t n, real* y, cudaStream_t s);
 
+// w1[k], w2[k], wr[k] = three independent standard normals that are pure functions of
+// (seed, step, first + k): Philox4x32-10 per element + Box-Muller.  `first` is the GLOBAL index of
+// element 0 (partitioned suspensions pass their offset, so the noise is partition invariant).
+template <typename real>
+cudaError_t normal_triplet(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n,
+                           real* w1, real* w2, real* wr, cudaStream_t s);
+
 }  // namespace rbl

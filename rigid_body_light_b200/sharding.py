@@ -297,14 +297,23 @@ class PartitionedRigidBody:
         return out, it.value
 
     def bd_step(self, F_ext_local, slip_local=None, kBT=0.0, noise_local=None, tol=1e-8, restart=60, max_iter=300,
-                lanczos_tol=1e-6, lanczos_max_iter=100):
+                lanczos_tol=1e-6, lanczos_max_iter=100, seed=None, step=0):
         """One BD step of the whole suspension (``rbl_bd_step``); the rank's bodies move.
-        ``noise_local`` = (W1, W2, Wr) slices of three GLOBAL standard-normal vectors."""
+        ``noise_local`` = (W1, W2, Wr) slices of three GLOBAL standard-normal vectors, or ``seed`` /
+        ``step`` for the device generator (``rbl_bd_step_seeded``): every rank passes the same seed
+        and step, each element's noise depends on its GLOBAL index only."""
         import ctypes
 
         n3 = 3 * self.total_blobs
         F = self._in(F_ext_local, 6 * self.N_bodies, "F_ext")
         slip = None if slip_local is None else self._in(slip_local, n3, "slip")
+        if seed is not None and kBT > 0 and noise_local is None:
+            U = np.empty(6 * self.N_bodies, dtype=self.real)
+            it, rr = ctypes.c_int(), ctypes.c_double()
+            self.ctx.call("rbl_bd_step_seeded", F.ctypes.data, None if slip is None else slip.ctypes.data, int(seed), int(step),
+                          float(kBT), tol, restart, max_iter, lanczos_tol, lanczos_max_iter, U.ctypes.data, ctypes.byref(it),
+                          ctypes.byref(rr))
+            return U, it.value, rr.value
         W = [None, None, None]
         if kBT > 0:
             if noise_local is None:

@@ -73,6 +73,15 @@ def main():
             dist.all_gather_object(parts, U)
             e = rel(np.concatenate(parts), U1)
             assert e < (1e-6 if precision == "double" else 2e-2), ("bd_step U", precision, block, e)
+            # device-generated noise: same (seed, step) on every rank = the single-context step
+            U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, seed=1234, step=7, tol=gt, restart=40,
+                                     max_iter=120, lanczos_tol=lt, lanczos_max_iter=80)
+            U1, it1, rr1 = one.bd_step(F_ext, kBT=0.0041, seed=1234, step=7, tol=gt, restart=40, max_iter=120,
+                                       lanczos_tol=lt, lanczos_max_iter=80)
+            parts = [None] * world
+            dist.all_gather_object(parts, U)
+            e = rel(np.concatenate(parts), U1)
+            assert e < (1e-6 if precision == "double" else 2e-2), ("seeded bd_step U", precision, block, e)
             Xp, Qp = part.get_config()
             X1, Q1 = one.get_config()
             assert rel(Xp, X1[part.b0:part.b1]) < (1e-9 if precision == "double" else 1e-5)

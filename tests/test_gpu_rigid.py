@@ -349,3 +349,34 @@ def test_bd_step_matches_the_committed_golden_step(name, mode):
     cb2.set_noise_preconditioner(2 if mode else 0)
     y, _ = cb2.brownian_sqrt(bd[f"{name}/W"][0], tol=1e-12, max_iter=200)
     assert rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]) < 1e-7
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_device_normals_match_the_oracle_generator(orc, precision):
+    """rbl_normals = Philox4x32-10 per element + Box-Muller, against oracle.philox_normals
+    (which is pinned to the Random123 known answers on the CPU)."""
+    g = load_golden("case_touch_free")
+    cb = _solver(g, precision)
+    first, n = 2**33 + 12345, 20001
+    got = cb.cb.normals(987654321, 5, first, n)
+    want = orc.philox_normals(987654321, 5, first, n)
+    tol = 1e-12 if precision == "double" else 2e-6
+    for a, b in zip(got, want):
+        assert np.abs(np.asarray(a, np.float64) - b).max() < tol * 6
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_seeded_bd_step_equals_the_step_with_the_same_noise(orc, name):
+    g = load_golden(name)
+    nb, n3 = g["X"].shape[0], g["r"].size
+    F = np.random.default_rng(21).standard_normal(6 * nb)
+    kw = dict(tol=1e-11, restart=100, max_iter=400, lanczos_tol=1e-12, lanczos_max_iter=200)
+    a = _solver(g, "double", block=True)
+    Ua, _, _ = a.bd_step(F, kBT=0.004, seed=77, step=12, **kw)
+    b = _solver(g, "double", block=True)
+    Ub, _, _ = b.bd_step(F, kBT=0.004, noise=orc.philox_normals(77, 12, 0, n3), **kw)
+    assert rel_err(Ua, Ub) < 1e-9
+    assert rel_err(a.get_config()[0], b.get_config()[0]) < 1e-12
+    c = _solver(g, "double", block=True)
+    Uc, _, _ = c.bd_step(F, kBT=0.004, seed=77, step=13, **kw)  # another step number: other noise
+    assert rel_err(Uc, Ua) > 1e-3

@@ -187,3 +187,28 @@ def test_bd_golden_reproduces(orc, name):
         assert rel_err(U, bd[f"{name}/{mode}/U"]) < 1e-9
         assert rel_err(Xn, bd[f"{name}/{mode}/X"]) < 1e-12 and rel_err(Qn, bd[f"{name}/{mode}/Q"]) < 1e-12
     assert rel_err(bd[f"{name}/symmetric/U"], bd[f"{name}/block_cholesky/U"]) > 1e-3
+
+
+def test_philox_known_answers_and_normal_statistics(orc):
+    """oracle.philox4x32_10 against the Random123 known-answer vectors, and the moments of the
+    Box-Muller triplets built on it (the device generator of rbl_bd_step_seeded is checked against
+    this in tests/test_gpu_rigid.py)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+            (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        got = orc.philox4x32_10([np.array([c]) for c in ctr], key)
+        assert tuple(int(g[0]) for g in got) == want
+    n = 400000
+    W = orc.philox_normals(seed=42, step=3, first=10**10, n=n)  # a 64-bit element offset too
+    for w in W:
+        assert abs(w.mean()) < 4 / np.sqrt(n) and abs(w.var() - 1) < 4 * np.sqrt(2 / n)
+        assert abs((w ** 4).mean() - 3) < 0.1
+    c = np.corrcoef(np.stack(W))
+    assert np.abs(c - np.eye(3)).max() < 4 / np.sqrt(n)
+    # pure function of (seed, step, element): a shifted window reproduces the overlap, other keys do not
+    V = orc.philox_normals(seed=42, step=3, first=10**10 + 1000, n=500)
+    assert all(np.array_equal(v, w[1000:1500]) for v, w in zip(V, W))
+    assert not np.array_equal(orc.philox_normals(42, 4, 10**10, 10)[0], W[0][:10])
+    assert not np.array_equal(orc.philox_normals(43, 3, 10**10, 10)[0], W[0][:10])
