@@ -44,12 +44,13 @@ def _terms(orc, cfg, X, Q, a, eta):
     at, moved = _setup(orc, cfg, X, Q, a, eta)
     base = at(X, Q)
     M, K, Kinv, N, A = (base[k] for k in ("M", "K", "Kinv", "N", "A"))
-    assert np.allclose(Kinv @ K, np.eye(6), atol=1e-12)
+    nd = K.shape[1]  # 6 rigid degrees of freedom per body
+    assert np.allclose(Kinv @ K, np.eye(nd), atol=1e-12)
     n3 = M.shape[0]
-    E = np.eye(6)
-    div_N = sum(_ddir(at, moved, "N", E[k])[:, k] for k in range(6))
+    E = np.eye(nd)
+    div_N = sum(_ddir(at, moved, "N", E[k])[:, k] for k in range(nd))
     # (1) noise through A(q') with q' - q = sqrt(kBT dt) K^-1 g, g ~ N(0, M):  E = d_k(A) M K^-T e_k
-    t_mid = sum(_ddir(at, moved, "A", E[k]) @ (M @ Kinv[k]) for k in range(6))
+    t_mid = sum(_ddir(at, moved, "A", E[k]) @ (M @ Kinv[k]) for k in range(nd))
     # (2) slip-row RFD of M: E[(M(q+) - M(q-)) W / delta], q+- = q +- (delta/2) K^-1 W, summed over W = e_j
     rfd_M = sum(_ddir(at, moved, "M", Kinv[:, j])[:, j] for j in range(n3))
     # (3) force-row RFD of K^T, same displacements
@@ -72,6 +73,20 @@ def test_drift_of_an_anisotropic_body_next_to_the_wall(orc):
     assert np.abs(t_KT).max() < 1e-8 * scale                       # the K^T finite difference has zero mean
     assert np.abs(t_mid - div_N).max() > 1e-3 * scale                # without the RFD of M the drift is wrong
     assert np.abs(t_M - div_N).max() > 1e-3 * scale                  # and so it is without the midpoint
+
+
+def test_drift_of_two_hydrodynamically_coupled_bodies(orc):
+    """two copies of the bent body, one above the other's shoulder: the 12 x 12 body mobility N
+    couples them, and the identity must hold for the whole vector, cross terms included"""
+    cfg = np.array([[0.0, 0, 0], [0.7, 0, 0], [1.4, 0, 0], [0, 0.8, 0], [0.3, 0.2, 0.9]])
+    X = np.array([[0.3, -0.2, 2.1], [1.9, 0.8, 3.0]])
+    Q = np.concatenate([_random_quat(4), _random_quat(9)])
+    div_N, t_mid, t_M, t_KT, N = _terms(orc, cfg, X, Q, a=0.3, eta=1.0)
+    scale = np.abs(N).max()
+    assert np.abs(N[:6, 6:]).max() > 1e-2 * scale                  # the bodies do interact
+    assert np.abs(t_mid + t_M - div_N).max() < 1e-6 * scale
+    assert np.abs(t_KT).max() < 1e-8 * scale
+    assert np.abs(t_mid - div_N).max() > 1e-3 * scale
 
 
 def test_kt_drift_vanishes_for_an_icosahedral_shell(orc):
