@@ -20,10 +20,11 @@ librbl), seconds per step.
 `roofline`: the product kernel alone (events recorded around every launch inside the timed
             region) against the FMA-pipe peak measured live by a microbenchmark.  The bound
             is FP32 (FP64) CUDA-core issue, not HBM and not tensor cores.
-`cpu_baseline` / --impl reference: the reference ALGORITHM (dense 3N x 3N assembly + GEMV,
-            c_rigid_obj.cpp:413-459,641-659, single thread like the reference) restated in
-            oracle/rbl_oracle.c, on a bounded sample of the same suspension.  The only place
-            bench.py touches oracle/.
+`cpu_baseline` / --impl reference: the reference's own dense 3N x 3N assembly + GEMV
+            (rotne_prager_tensor / make_damp_mat / apply_M, c_rigid_obj.cpp:413-459,618-659, compiled
+            from the reference source into oracle/_ref/libref_apply_M.so; the oracle's port where that
+            library is absent), single thread like the reference, on a bounded sample of the same
+            suspension.  The only place bench.py touches oracle/.
 """
 import argparse
 import json
@@ -411,10 +412,19 @@ def cpu_reference_sample(workload, precision, budget_s, steps=1, warmup=0):
 
     ndt = np.float32 if precision == "single" else np.float64
     nb_total, n_blb, wall = WORKLOADS[workload]
+    # the reference's OWN members (rotne_prager_tensor + make_damp_mat + apply_M compiled from its
+    # source into oracle/_ref/libref_apply_M.so) when that library is there, else the oracle's port
+    use_ref = orc.ref_apply_M_lib() is not None
+
+    def dense_apply(F_, r_, a_):
+        if use_ref:
+            return orc.ref_apply_M(F_, r_, a_, 1.0, wall, dtype=ndt)
+        return orc.apply_M_dense(F_, r_, a_, 1.0, wall, dtype=ndt)
+
     # calibrate on a small piece
     s, nb, r, F = _sample_inputs(workload, max(1, 600 // n_blb), ndt)
     t0 = time.perf_counter()
-    orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+    dense_apply(F, r, s["a"])
     rate = (r.shape[0] ** 2) / max(time.perf_counter() - t0, 1e-6)
     per_step = budget_s / max(1, steps + warmup)
     n_target = int(np.sqrt(rate * per_step))
@@ -423,10 +433,10 @@ def cpu_reference_sample(workload, precision, budget_s, steps=1, warmup=0):
     s, nb, r, F = _sample_inputs(workload, nb_s, ndt)
     n = r.shape[0]
     for _ in range(warmup):
-        orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+        dense_apply(F, r, s["a"])
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.apply_M_dense(F, r, s["a"], 1.0, wall, dtype=ndt)
+        dense_apply(F, r, s["a"])
     dt = (time.perf_counter() - t0) / steps
     # best-effort CPU: matrix-free OpenMP oracle on all host cores, sampled target rows of the
     # FULL workload (float64 with long-double row sums; a courtesy number, not the reference)
@@ -436,9 +446,12 @@ def cpu_reference_sample(workload, precision, budget_s, steps=1, warmup=0):
     orc.apply_M(Ff, rf, sf["a"], 1.0, wall, rows=rows)
     dt_mf = time.perf_counter() - t0
     return {
-        "value": n * n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        "value": n * n / dt, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
         "sample": f"first {nb} bodies of {workload} ({n} blobs, {precision}): dense {3*n}x{3*n} assembly + GEMV "
-                  f"like c_rigid_obj.cpp:413-459,641-659, single thread (the reference has no threading); "
+                  + ("by the reference's own rotne_prager_tensor / make_damp_mat / apply_M members compiled from its source "
+                     "(c_rigid_obj.cpp:413-459,618-659; Eigen's dense ops supplied by oracle/eigen_shim.inc), "
+                     if use_ref else "like c_rigid_obj.cpp:413-459,641-659 (oracle port), ")
+                  + f"single thread (the reference has no threading); "
                   f"the full workload would need {9 * (nb_total * n_blb) ** 2 * np.dtype(ndt).itemsize / 1e9:.0f} GB",
         "ms_per_step": dt * 1e3,
         "best_effort_all_cores": {"value": rows.size * rf.shape[0] / dt_mf, "unit": UNIT, "cores": orc.num_threads(),

@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
 # build_ref.sh -- compile the REFERENCE's own two pair kernels (mobilityUFRPY and
 # mobilityUFSingleWallCorrection, /root/reference/src/c_rigid_obj.cpp:31-142) from
-# the reference source WHERE IT LIES into oracle/_ref/libref_pair.so.
+# the reference source WHERE IT LIES into oracle/_ref/libref_pair.so, and its dense
+# assembly + apply_M members (:413-459, 618-659) into oracle/_ref/libref_apply_M.so.
 #
 # The whole reference translation unit cannot be built here (Eigen3 + nanobind are
 # absent); these two free functions depend only on <cmath>/<iostream>/<stdexcept>,
@@ -48,6 +49,52 @@ WRAP
 }
 gen double f64
 gen float f32
+# ---- the reference's own dense assembly + apply_M (c_rigid_obj.cpp:413-459, 618-659) ------------
+# rotne_prager_tensor, make_damp_mat and apply_M are members of CManyBodies; they use only the
+# pair kernels, the members a / eta / PC_wall and a few Eigen dense operations.  Eigen3 is not
+# installed, so oracle/eigen_shim.inc (ours) supplies exactly those operations; the three member
+# functions are streamed from the reference source into a struct that holds the three data
+# members.  Result: libref_apply_M.so = the reference's assembly loop and its B M B F expression,
+# as written, in float and double.
+gen_apply() { # $1 = real type, $2 = suffix
+  {
+    echo '#include <cmath>'
+    echo '#include <iostream>'
+    echo '#include <stdexcept>'
+    echo '#include <cstdlib>'
+    echo '#include <vector>'
+    echo '#include <algorithm>'
+    echo '#include <initializer_list>'
+    echo "namespace refm_$2 {"
+    echo "using real = $1;"
+    cat "$HERE/eigen_shim.inc"
+    awk '/^void mobilityUFRPY\(/{on=1} /^class CManyBodies/{on=0} on{print}' "$REF_SRC"
+    echo 'struct RefBody {'
+    echo '  real a, eta; bool PC_wall;'
+    awk '/template <class AVector> Matrix rotne_prager_tensor\(/{on=1} /^  SparseM Block_diag_invM\(\)/{on=0} on{print}' "$REF_SRC"
+    awk '/^  DiagM make_damp_mat\(/{on=1} /^  Vector M_half_W\(\)/{on=0} on{print}' "$REF_SRC"
+    echo '};'
+    echo '}'
+    cat <<WRAP
+extern "C" int ref_apply_M_$2(const $1 *F, const $1 *r, int n_blobs, double a, double eta, int wall, $1 *U) {
+  refm_$2::RefBody b;
+  b.a = ($1)a; b.eta = ($1)eta; b.PC_wall = wall != 0;
+  refm_$2::Vector f(3L * n_blobs);
+  std::vector<$1> rv(r, r + 3L * n_blobs);
+  for (long i = 0; i < 3L * n_blobs; ++i) f(i) = F[i];
+  try {
+    refm_$2::Vector u = b.apply_M(f, rv);
+    for (long i = 0; i < 3L * n_blobs; ++i) U[i] = u(i);
+  } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+WRAP
+  } > "$TMP/ref_apply_$2.cpp"
+}
+gen_apply double f64
+gen_apply float f32
+${CXX_SYS:-/usr/bin/g++} -O2 -ffp-contract=off -fPIC -shared -o "$OUT/libref_apply_M.so" "$TMP/ref_apply_f64.cpp" "$TMP/ref_apply_f32.cpp"
+echo "built $OUT/libref_apply_M.so from $REF_SRC"
 # same flags for both sides of the bit-for-bit comparison: no FMA contraction
 ${CXX_SYS:-/usr/bin/g++} -O2 -ffp-contract=off -fPIC -shared -o "$OUT/libref_pair.so" "$TMP/ref_pair_f64.cpp" "$TMP/ref_pair_f32.cpp"
 echo "built $OUT/libref_pair.so from $REF_SRC"

@@ -12,12 +12,15 @@ What it restates (citations are into /root/reference/src/):
 * everything O(N) around it is plain numpy float64 below, one function per
   reference member function, each citing the lines it follows.
 
-Pinning status: the two pair kernels are pinned bit-for-bit against the
-reference's own source compiled into ``oracle/_ref`` (tests/test_oracle_vs_ref.py)
-and blob placement against scipy's ``Rotation`` exactly like the reference's
-tests/test_interface.py:55-73.  The reference holds no golden values for M.F, K,
-K^T or the preconditioner: for those, parity is "unpinned by
-the reference" and defended by the physics checks in tests/test_oracle_physics.py.
+Pinning status: the two pair kernels AND the dense assembly + apply_M members
+(rotne_prager_tensor, make_damp_mat, apply_M) are pinned bit-for-bit, in float and
+double, against the reference's own source compiled into ``oracle/_ref`` by
+build_ref.sh (tests/test_oracle_vs_ref.py; committed outputs in tests/golden/), and
+blob placement against scipy's ``Rotation`` exactly like the reference's
+tests/test_interface.py:55-73.  The reference holds no golden values for K, K^T or
+the preconditioner and those members need Eigen's sparse/LLT machinery (absent
+here): for those, parity is "unpinned by the reference" and defended by the checks
+in tests/test_oracle_physics.py and tests/test_oracle_bd_drift.py.
 """
 from __future__ import annotations
 
@@ -39,8 +42,8 @@ def build(force: bool = False) -> None:
     stale = force or not os.path.exists(so) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in src
     )
-    need_ref = os.path.exists("/root/reference/src/c_rigid_obj.cpp") and not os.path.exists(
-        os.path.join(_HERE, "_ref", "libref_pair.so")
+    need_ref = os.path.exists("/root/reference/src/c_rigid_obj.cpp") and not all(
+        os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_pair.so", "libref_apply_M.so")
     )
     if stale or need_ref:
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
@@ -73,6 +76,46 @@ def ref_pair_lib():
             g.argtypes = [ct, ct, ct, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ct]
             g.restype = ctypes.c_int
     return _REF
+
+
+_REF_APPLY = None
+
+
+def ref_apply_M_lib():
+    """The reference's own rotne_prager_tensor + make_damp_mat + apply_M members compiled from the
+    reference source (oracle/_ref/libref_apply_M.so, see build_ref.sh) or None."""
+    global _REF_APPLY
+    if _REF_APPLY is None:
+        p = os.path.join(_HERE, "_ref", "libref_apply_M.so")
+        if not os.path.exists(p):
+            build()
+        if not os.path.exists(p):
+            return None
+        _REF_APPLY = ctypes.CDLL(p)
+        for sfx in ("f64", "f32"):
+            f = getattr(_REF_APPLY, f"ref_apply_M_{sfx}")
+            f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                          ctypes.c_void_p]
+            f.restype = ctypes.c_int
+    return _REF_APPLY
+
+
+def ref_apply_M(F, r, a, eta, wall, dtype=np.float64):
+    """U = apply_M(F, r) computed BY THE REFERENCE'S OWN CODE (c_rigid_obj.cpp:413-459,618-659
+    compiled from /root/reference with oracle/eigen_shim.inc standing in for the absent Eigen3).
+    Raises OracleError for a blob below the wall, like the reference throws.  None if the library
+    is not available."""
+    L = ref_apply_M_lib()
+    if L is None:
+        return None
+    F, r = _prep(F, dtype), _prep(r, dtype)
+    n = r.size // 3
+    sfx, _ = _CT[np.dtype(dtype)]
+    U = np.empty(3 * n, dtype=dtype)
+    st = getattr(L, f"ref_apply_M_{sfx}")(F.ctypes.data, r.ctypes.data, n, float(a), float(eta), int(wall), U.ctypes.data)
+    if st != 0:
+        raise OracleError("reference apply_M threw (blob below the wall, c_rigid_obj.cpp:95-97)")
+    return U
 
 
 _CT = {np.dtype(np.float64): ("f64", ctypes.c_double), np.dtype(np.float32): ("f32", ctypes.c_float)}

@@ -7,15 +7,13 @@
  * reported CPU baseline -- never as the product path.
  *
  * It restates /root/reference/src/c_rigid_obj.cpp:31-142,413-459,618-659 in plain
- * C (no Eigen).  The reference itself cannot be built here (it needs Eigen3 and
- * nanobind, neither present, no network), but its two pair kernels depend only on
- * <cmath>; oracle/build_ref.sh compiles those two functions from the reference
- * source where it lies into oracle/_ref/ and tests/test_oracle_vs_ref.py checks
- * this restatement against them bit for bit.  Parity of everything ABOVE the pair
- * kernels (dense assembly, GEMV, B damping) is pinned only by construction and by
- * the physics checks in tests/test_oracle_physics.py: the reference's own tests
- * hold no golden values for M.F -- "parity unpinned by the
- * reference" for those values.
+ * C (no Eigen).  The reference as a whole cannot be built here (it needs Eigen3 and
+ * nanobind, neither present, no network), but oracle/build_ref.sh compiles, from the
+ * reference source where it lies, (a) its two pair kernels and (b) its
+ * rotne_prager_tensor + make_damp_mat + apply_M members (with oracle/eigen_shim.inc
+ * supplying the few Eigen dense operations they use) into oracle/_ref/, and
+ * tests/test_oracle_vs_ref.py checks this restatement against both BIT FOR BIT in
+ * float and double (live, and against committed outputs under tests/golden/).
  */
 #include <math.h>
 #include <stdlib.h>

@@ -15,6 +15,9 @@ Run HERE (the build container), where /root/reference exists:
 * ``case_*.npz``       -- seeded small suspensions with the float64 oracle's outputs for
   every operator of the hot path (apply_M, K, K^T, Kinv, both PCs, saddle, evolve).
   The reference itself holds no golden values for these.
+* ``apply_M_ref_golden.npz`` -- apply_M of the cases above (and of a ragged cloud) computed by the
+  REFERENCE'S OWN assembly + apply_M members compiled from the reference source
+  (oracle/_ref/libref_apply_M.so); ``--apply-M-ref-only`` regenerates just this file.
 * ``bd_golden.npz``    -- one fluctuating BD step per touching-sphere case with fixed noise through
   the dense oracle (both Brownian-increment routes).  ``--bd-only`` regenerates just this file.
 """
@@ -135,6 +138,33 @@ def make_case(name):
     print(name, "N =", r.shape[0], "zmin/a =", r[:, 2].min() / a)
 
 
+def apply_M_ref_golden():
+    """apply_M of every committed case computed by THE REFERENCE'S OWN CODE (rotne_prager_tensor +
+    make_damp_mat + apply_M, c_rigid_obj.cpp:413-459,618-659, compiled from the reference source by
+    oracle/build_ref.sh with oracle/eigen_shim.inc standing in for Eigen3), in double and in float,
+    plus a ragged random cloud with overlapping and touching pairs.  This is what pins the oracle's
+    M.F -- and through it the CUDA product -- to the reference where /root/reference is absent."""
+    assert orc.ref_apply_M_lib() is not None, "oracle/_ref/libref_apply_M.so missing: run make -C oracle"
+    out = {}
+    for name in CASES:
+        g = dict(np.load(os.path.join(HERE, name + ".npz")))
+        a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+        out[f"{name}/f64"] = orc.ref_apply_M(g["lam"], g["r"], a, eta, wall)
+        out[f"{name}/f32"] = orc.ref_apply_M(g["lam"].astype(np.float32), g["r"].astype(np.float32), a, eta, wall, dtype=np.float32)
+    rng = np.random.default_rng(77)
+    n, a, eta = 257, 0.11, 0.9
+    r = rng.uniform(0.05, 3.0, (n, 3))
+    r[1] = r[0] + [0.7 * a, 0, 0.1 * a]
+    r[3] = r[2] + [0, 2.0 * a, 0]
+    F = rng.standard_normal(3 * n)
+    out["cloud/r"], out["cloud/F"], out["cloud/a"], out["cloud/eta"] = r, F, np.array(a), np.array(eta)
+    for wall in (False, True):
+        out[f"cloud/wall{int(wall)}/f64"] = orc.ref_apply_M(F, r, a, eta, wall)
+        out[f"cloud/wall{int(wall)}/f32"] = orc.ref_apply_M(F.astype(np.float32), r.astype(np.float32), a, eta, wall, dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "apply_M_ref_golden.npz"), **out)
+    print("apply_M_ref_golden.npz:", len(out), "arrays from the reference's own apply_M")
+
+
 def bd_golden():
     """One fluctuating BD step per touching-sphere case with FIXED noise, through the dense oracle:
     Brownian increments by both routes (symmetric square root; block-Cholesky preconditioned root)
@@ -170,8 +200,12 @@ if __name__ == "__main__":
     if "--bd-only" in sys.argv:
         bd_golden()
         sys.exit(0)
+    if "--apply-M-ref-only" in sys.argv:
+        apply_M_ref_golden()
+        sys.exit(0)
     pair_golden()
     shells_check()
     for c in CASES:
         make_case(c)
+    apply_M_ref_golden()
     bd_golden()

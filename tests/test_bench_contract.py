@@ -23,7 +23,10 @@ def test_reference_arm_json_line():
     assert line["vs_baseline"] is None and line["value"] > 0
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and "sample" in cb and cb["value"] == line["value"]
+    from oracle import oracle as orc
+
+    assert cb["kind"] == ("reference" if orc.ref_apply_M_lib() is not None else "port")
+    assert cb["cores"] == 1 and "sample" in cb and cb["value"] == line["value"]
     assert "workload" in line["config"] and "model" not in line["config"]
 
 

@@ -332,3 +332,26 @@ def test_config4_scale_free_space_sampled_rows(orc):
     sym = abs(float(torch.dot(F2.double(), u1.double()) - torch.dot(F1.double(), u2.double())))
     assert sym / float(F2.double().norm() * u1.double().norm()) < 2e-6
     ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("wall", [False, True])
+def test_apply_M_against_the_reference_members_golden(wall, precision):
+    """The CUDA product against outputs of the REFERENCE'S OWN rotne_prager_tensor + apply_M
+    (tests/golden/apply_M_ref_golden.npz, see tests/golden/make_golden.py): the committed cases in
+    tests/test_gpu_matvec.py::test_apply_M_matches_golden use fixtures that equal these to 1e-15;
+    here a ragged 257-blob cloud with overlapping and touching pairs, directly."""
+    from rigid_body_light_b200._lib import Context
+
+    ref = load_golden("apply_M_ref_golden")
+    r, F, a, eta = ref["cloud/r"], ref["cloud/F"], float(ref["cloud/a"]), float(ref["cloud/eta"])
+    ctx = Context(precision)
+    ctx.set_parameters(a, 0.01, 1.0, eta, np.zeros((1, 3)))
+    ctx.set_flags(0, wall)
+    out = ctx.apply_M(F, r)
+    if precision == "double":
+        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]) < TOL["double"]
+    else:  # the float reference accumulates 771-term sums in float itself: compare at its own accuracy
+        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]) < TOL["single"]
+        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f32"]) < TOL["single"]
+    ctx.close()

@@ -107,3 +107,50 @@ def test_live_against_compiled_reference(orc, sfx, ct, dt):
                                                  m9.ctypes.data, 0, 1, ct(dt(rj[2] / a)))
         assert st == 0
         assert np.array_equal(got, m9)
+
+
+# ---- the reference's own apply_M (assembly loop + B M B F), not just its pair kernels -------------
+from conftest import CASE_NAMES, rel_err  # noqa: E402
+
+
+@pytest.mark.parametrize("dt,sfx,tol", [(np.float64, "f64", 0.0), (np.float32, "f32", 0.0)])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_oracle_apply_M_equals_the_reference_members_golden(orc, name, dt, sfx, tol):
+    """oracle.apply_M_dense (the restatement of rotne_prager_tensor + make_damp_mat + apply_M) against
+    tests/golden/apply_M_ref_golden.npz = outputs of THOSE REFERENCE MEMBERS compiled from the
+    reference source (oracle/build_ref.sh; Eigen replaced by oracle/eigen_shim.inc).  Bit for bit in
+    both precisions: same pair kernels, same assembly order, same column-oriented GEMV.  The
+    matrix-free oracle (long-double row sums) agrees to rounding."""
+    g, ref = load_golden(name), load_golden("apply_M_ref_golden")
+    a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
+    want = ref[f"{name}/{sfx}"]
+    got = orc.apply_M_dense(g["lam"].astype(dt), g["r"].astype(dt), a, eta, wall, dtype=dt)
+    assert np.array_equal(got, want)
+    mf = orc.apply_M(g["lam"].astype(dt).astype(np.float64), g["r"].astype(dt).astype(np.float64), a, eta, wall)
+    assert rel_err(mf, want) < (1e-14 if dt == np.float64 else 1e-6)
+    if dt == np.float64:
+        assert rel_err(g["MF"], want) < 1e-14  # the fixture every GPU parity test compares with
+
+
+@pytest.mark.parametrize("wall", [False, True])
+def test_oracle_apply_M_equals_the_reference_members_on_a_ragged_cloud(orc, wall):
+    ref = load_golden("apply_M_ref_golden")
+    r, F, a, eta = ref["cloud/r"], ref["cloud/F"], float(ref["cloud/a"]), float(ref["cloud/eta"])
+    assert np.array_equal(orc.apply_M_dense(F, r, a, eta, wall), ref[f"cloud/wall{int(wall)}/f64"])
+    assert rel_err(orc.apply_M(F, r, a, eta, wall), ref[f"cloud/wall{int(wall)}/f64"]) < 1e-14
+    f32 = orc.apply_M_dense(F.astype(np.float32), r.astype(np.float32), a, eta, wall, dtype=np.float32)
+    assert np.array_equal(f32, ref[f"cloud/wall{int(wall)}/f32"])
+
+
+def test_reference_members_live_when_the_reference_tree_is_here(orc):
+    """where oracle/_ref/libref_apply_M.so exists (this container; it travels to the GPU box too):
+    the live library reproduces its committed golden outputs, and throws below the wall."""
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_apply_M.so not built (no /root/reference here)")
+    g, ref = load_golden("case_touch_wall"), load_golden("apply_M_ref_golden")
+    u = orc.ref_apply_M(g["lam"], g["r"], float(g["a"]), float(g["eta"]), True)
+    assert np.array_equal(u, ref["case_touch_wall/f64"])
+    r = g["r"].copy()
+    r[0, 2] = -0.1
+    with pytest.raises(orc.OracleError):
+        orc.ref_apply_M(g["lam"], r, float(g["a"]), float(g["eta"]), True)
