@@ -1,8 +1,9 @@
 #!/usr/bin/env bash
 # build_ref.sh -- compile the REFERENCE's own two pair kernels (mobilityUFRPY and
 # mobilityUFSingleWallCorrection, /root/reference/src/c_rigid_obj.cpp:31-142) from
-# the reference source WHERE IT LIES into oracle/_ref/libref_pair.so, and its dense
-# assembly + apply_M members (:413-459, 618-659) into oracle/_ref/libref_apply_M.so.
+# the reference source WHERE IT LIES into oracle/_ref/libref_pair.so, and its member
+# functions on the product path (state, placement, K/K^T/K^-1, dense assembly + apply_M,
+# integrator) into oracle/_ref/libref_members.so.
 #
 # The whole reference translation unit cannot be built here (Eigen3 + nanobind are
 # absent); these two free functions depend only on <cmath>/<iostream>/<stdexcept>,
@@ -49,20 +50,25 @@ WRAP
 }
 gen double f64
 gen float f32
-# ---- the reference's own dense assembly + apply_M (c_rigid_obj.cpp:413-459, 618-659) ------------
-# rotne_prager_tensor, make_damp_mat and apply_M are members of CManyBodies; they use only the
-# pair kernels, the members a / eta / PC_wall and a few Eigen dense operations.  Eigen3 is not
-# installed, so oracle/eigen_shim.inc (ours) supplies exactly those operations; the three member
-# functions are streamed from the reference source into a struct that holds the three data
-# members.  Result: libref_apply_M.so = the reference's assembly loop and its B M B F expression,
-# as written, in float and double.
-gen_apply() { # $1 = real type, $2 = suffix
+# ---- the reference's own member functions on the product path ---------------------------------
+# State handling, placement, K / K^T / K^-1, the dense assembly + apply_M and the integrator are
+# members of CManyBodies that use the pair kernels, a dozen data members and a subset of Eigen
+# (dense, quaternion, sparse-from-triplets).  Eigen3 is not installed, so oracle/eigen_shim.inc
+# (ours) supplies exactly that subset; the member functions are streamed from the reference source
+# into a struct that declares the data members.  Result: libref_members.so = the reference's
+#   removeMean .. KT_x_Lam (:176-410), rotne_prager_tensor (:413-459), make_damp_mat + apply_M
+#   (:618-659), Block_diag_invM / diag_invM / PC_invM / get_blk_diag_lu (:461-567), apply_PC (:589-616),
+#   Q_from_Om + update_X_Q(+_out) (:678-728), evolve_X_Q (:865-878)
+# as written, in float and double, behind a small C API.
+gen_members() { # $1 = real type, $2 = suffix
   {
     echo '#include <cmath>'
     echo '#include <iostream>'
     echo '#include <stdexcept>'
     echo '#include <cstdlib>'
     echo '#include <vector>'
+    echo '#include <tuple>'
+    echo '#include <utility>'
     echo '#include <algorithm>'
     echo '#include <initializer_list>'
     echo "namespace refm_$2 {"
@@ -70,31 +76,93 @@ gen_apply() { # $1 = real type, $2 = suffix
     cat "$HERE/eigen_shim.inc"
     awk '/^void mobilityUFRPY\(/{on=1} /^class CManyBodies/{on=0} on{print}' "$REF_SRC"
     echo 'struct RefBody {'
-    echo '  real a, eta; bool PC_wall;'
+    echo '  real a, dt, kBT, eta; bool PC_wall = false; bool block_diag_PC = false; double M_scale;'
+    echo '  bool PC_mat_Set = false; bool cfg_set = false; int N_bod = 0; std::vector<Quat> Q_n; std::vector<Vector> X_n;'
+    echo '  Matrix ref_cfg; int N_blb = 0; bool parametersSet = false; SparseM K, KT, Kinv;'
+    echo '  SparseM invM; SparseM Ninv; std::vector<Eigen::LLT<Matrix>> N_lu;'
+    awk '/^  void removeMean\(Matrix &cfg\)/{on=1} /preconditioner\/solver functions/{on=0} on{print}' "$REF_SRC"
     awk '/template <class AVector> Matrix rotne_prager_tensor\(/{on=1} /^  SparseM Block_diag_invM\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  DiagM make_damp_mat\(/{on=1} /^  Vector M_half_W\(\)/{on=0} on{print}' "$REF_SRC"
+    awk '/^  SparseM Block_diag_invM\(\)/{on=1} /template <class AVector> void test_PC\(/{on=0} on{print}' "$REF_SRC"
+    awk '/^  Vector apply_PC\(const Vector &IN\)/{on=1} /^  DiagM make_damp_mat\(/{on=0} on{print}' "$REF_SRC"
+    awk '/^  Quat Q_from_Om\(/{on=1} /^  Vector rand_vector\(/{on=0} on{print}' "$REF_SRC"
+    awk '/^  void evolve_X_Q\(Vector &U\)/{on=1} /^  void evolve_X_Q_RFD\(/{on=0} on{print}' "$REF_SRC"
     echo '};'
     echo '}'
     cat <<WRAP
-extern "C" int ref_apply_M_$2(const $1 *F, const $1 *r, int n_blobs, double a, double eta, int wall, $1 *U) {
-  refm_$2::RefBody b;
-  b.a = ($1)a; b.eta = ($1)eta; b.PC_wall = wall != 0;
-  refm_$2::Vector f(3L * n_blobs);
-  std::vector<$1> rv(r, r + 3L * n_blobs);
-  for (long i = 0; i < 3L * n_blobs; ++i) f(i) = F[i];
-  try {
-    refm_$2::Vector u = b.apply_M(f, rv);
-    for (long i = 0; i < 3L * n_blobs; ++i) U[i] = u(i);
-  } catch (const std::runtime_error &) { return 2; }
+namespace {
+using B_$2 = refm_$2::RefBody;
+using V_$2 = refm_$2::Vector;
+V_$2 in_$2(const $1 *p, long n) { V_$2 v(n); for (long i = 0; i < n; ++i) v(i) = p[i]; return v; }
+void out_$2(const refm_$2::Mat &v, $1 *p) { for (long i = 0; i < (long)v.a.size(); ++i) p[i] = v.a[(size_t)i]; }
+}
+extern "C" void *refm_create_$2() { return new B_$2(); }
+extern "C" void refm_destroy_$2(void *h) { delete static_cast<B_$2 *>(h); }
+extern "C" int refm_set_parameters_$2(void *h, double a, double dt, double kBT, double eta, const $1 *cfg, int n_blb) {
+  refm_$2::Matrix c(n_blb, 3);
+  for (int k = 0; k < n_blb; ++k) for (int d = 0; d < 3; ++d) c(k, d) = cfg[3 * k + d];
+  static_cast<B_$2 *>(h)->setParameters(($1)a, ($1)dt, ($1)kBT, ($1)eta, c);
   return 0;
 }
-WRAP
-  } > "$TMP/ref_apply_$2.cpp"
+extern "C" int refm_set_flags_$2(void *h, int blk, int wall) {
+  static_cast<B_$2 *>(h)->setBlkPC(blk != 0); static_cast<B_$2 *>(h)->setWallPC(wall != 0); return 0;
 }
-gen_apply double f64
-gen_apply float f32
-${CXX_SYS:-/usr/bin/g++} -O2 -ffp-contract=off -fPIC -shared -o "$OUT/libref_apply_M.so" "$TMP/ref_apply_f64.cpp" "$TMP/ref_apply_f32.cpp"
-echo "built $OUT/libref_apply_M.so from $REF_SRC"
+extern "C" int refm_set_config_$2(void *h, const $1 *X, const $1 *Q, int n_bod) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  b->setConfig(in_$2(X, 3L * n_bod), in_$2(Q, 4L * n_bod));
+  b->set_K_mats();
+  return 0;
+}
+extern "C" int refm_get_config_$2(void *h, $1 *X, $1 *Q) {
+  auto t = static_cast<B_$2 *>(h)->getConfig();
+  out_$2(t.first, X); out_$2(t.second, Q);
+  return 0;
+}
+extern "C" int refm_positions_$2(void *h, $1 *out) {
+  std::vector<$1> p = static_cast<B_$2 *>(h)->multi_body_pos();
+  for (size_t i = 0; i < p.size(); ++i) out[i] = p[i];
+  return 0;
+}
+extern "C" int refm_K_x_U_$2(void *h, const $1 *U, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h); out_$2(b->K_x_U(in_$2(U, 6L * b->N_bod)), out); return 0;
+}
+extern "C" int refm_KT_x_Lam_$2(void *h, const $1 *L, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h); out_$2(b->KT_x_Lam(in_$2(L, 3L * b->N_bod * b->N_blb)), out); return 0;
+}
+extern "C" int refm_Kinv_x_V_$2(void *h, const $1 *V, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h); out_$2(b->Kinv_x_V(in_$2(V, 3L * b->N_bod * b->N_blb)), out); return 0;
+}
+extern "C" int refm_KTinv_x_F_$2(void *h, const $1 *F, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h); out_$2(b->KTinv_x_F(in_$2(F, 6L * b->N_bod)), out); return 0;
+}
+extern "C" int refm_apply_PC_$2(void *h, const $1 *in, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  try { out_$2(b->apply_PC(in_$2(in, 3L * b->N_bod * b->N_blb + 6L * b->N_bod)), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+extern "C" int refm_evolve_$2(void *h, const $1 *U) {
+  B_$2 *b = static_cast<B_$2 *>(h); V_$2 u = in_$2(U, 6L * b->N_bod); b->evolve_X_Q(u); return 0;
+}
+extern "C" int refm_apply_M_$2(void *h, const $1 *F, const $1 *r, int n_blobs, $1 *U) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  std::vector<$1> rv(r, r + 3L * n_blobs);
+  try { out_$2(b->apply_M(in_$2(F, 3L * n_blobs), rv), U); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+// stateless convenience: apply_M for given (a, eta, wall)
+extern "C" int ref_apply_M_$2(const $1 *F, const $1 *r, int n_blobs, double a, double eta, int wall, $1 *U) {
+  B_$2 b;
+  b.a = ($1)a; b.eta = ($1)eta; b.PC_wall = wall != 0;
+  return refm_apply_M_$2(&b, F, r, n_blobs, U);
+}
+WRAP
+  } > "$TMP/ref_members_$2.cpp"
+}
+gen_members double f64
+gen_members float f32
+${CXX_SYS:-/usr/bin/g++} -O2 -ffp-contract=off -fPIC -shared -o "$OUT/libref_members.so" "$TMP/ref_members_f64.cpp" "$TMP/ref_members_f32.cpp"
+ln -sf libref_members.so "$OUT/libref_apply_M.so"
+echo "built $OUT/libref_members.so from $REF_SRC"
 # same flags for both sides of the bit-for-bit comparison: no FMA contraction
 ${CXX_SYS:-/usr/bin/g++} -O2 -ffp-contract=off -fPIC -shared -o "$OUT/libref_pair.so" "$TMP/ref_pair_f64.cpp" "$TMP/ref_pair_f32.cpp"
 echo "built $OUT/libref_pair.so from $REF_SRC"

@@ -12,15 +12,13 @@ What it restates (citations are into /root/reference/src/):
 * everything O(N) around it is plain numpy float64 below, one function per
   reference member function, each citing the lines it follows.
 
-Pinning status: the two pair kernels AND the dense assembly + apply_M members
-(rotne_prager_tensor, make_damp_mat, apply_M) are pinned bit-for-bit, in float and
-double, against the reference's own source compiled into ``oracle/_ref`` by
-build_ref.sh (tests/test_oracle_vs_ref.py; committed outputs in tests/golden/), and
-blob placement against scipy's ``Rotation`` exactly like the reference's
-tests/test_interface.py:55-73.  The reference holds no golden values for K, K^T or
-the preconditioner and those members need Eigen's sparse/LLT machinery (absent
-here): for those, parity is "unpinned by the reference" and defended by the checks
-in tests/test_oracle_physics.py and tests/test_oracle_bd_drift.py.
+Pinning status: every function here is pinned against the reference's OWN code, compiled
+from the reference source where it lies by build_ref.sh into ``oracle/_ref`` (Eigen3 is
+absent: ``eigen_shim.inc`` supplies the subset those members use) -- the two pair kernels
+and the dense ``apply_M`` bit for bit in float and double, state handling, placement, K,
+K^T, K^-1, both preconditioners and the integrator to rounding (tests/test_oracle_vs_ref.py,
+live through ``RefBody`` where ``_ref`` exists, and against committed outputs of the
+reference's code under tests/golden/ everywhere).
 """
 from __future__ import annotations
 
@@ -43,7 +41,7 @@ def build(force: bool = False) -> None:
         os.path.getmtime(s) > os.path.getmtime(so) for s in src
     )
     need_ref = os.path.exists("/root/reference/src/c_rigid_obj.cpp") and not all(
-        os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_pair.so", "libref_apply_M.so")
+        os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libref_pair.so", "libref_members.so")
     )
     if stale or need_ref:
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
@@ -82,22 +80,113 @@ _REF_APPLY = None
 
 
 def ref_apply_M_lib():
-    """The reference's own rotne_prager_tensor + make_damp_mat + apply_M members compiled from the
-    reference source (oracle/_ref/libref_apply_M.so, see build_ref.sh) or None."""
+    """The reference's own member functions on the product path compiled from the reference source
+    (oracle/_ref/libref_members.so, see build_ref.sh) or None."""
     global _REF_APPLY
     if _REF_APPLY is None:
-        p = os.path.join(_HERE, "_ref", "libref_apply_M.so")
+        p = os.path.join(_HERE, "_ref", "libref_members.so")
         if not os.path.exists(p):
             build()
         if not os.path.exists(p):
             return None
-        _REF_APPLY = ctypes.CDLL(p)
+        L = ctypes.CDLL(p)
+        vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
         for sfx in ("f64", "f32"):
-            f = getattr(_REF_APPLY, f"ref_apply_M_{sfx}")
-            f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
-                          ctypes.c_void_p]
-            f.restype = ctypes.c_int
+            getattr(L, f"ref_apply_M_{sfx}").argtypes = [vp, vp, ci, cd, cd, ci, vp]
+            getattr(L, f"refm_create_{sfx}").restype = vp
+            getattr(L, f"refm_destroy_{sfx}").argtypes = [vp]
+            getattr(L, f"refm_destroy_{sfx}").restype = None
+            getattr(L, f"refm_set_parameters_{sfx}").argtypes = [vp, cd, cd, cd, cd, vp, ci]
+            getattr(L, f"refm_set_flags_{sfx}").argtypes = [vp, ci, ci]
+            getattr(L, f"refm_set_config_{sfx}").argtypes = [vp, vp, vp, ci]
+            getattr(L, f"refm_get_config_{sfx}").argtypes = [vp, vp, vp]
+            getattr(L, f"refm_apply_M_{sfx}").argtypes = [vp, vp, vp, ci, vp]
+            for name in ("positions", "evolve"):
+                getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp]
+            for name in ("K_x_U", "KT_x_Lam", "Kinv_x_V", "KTinv_x_F", "apply_PC"):
+                getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp, vp]
+        _REF_APPLY = L
     return _REF_APPLY
+
+
+class RefBody:
+    """The reference's own CManyBodies members (state handling, placement, K / K^T / K^-1, apply_M,
+    both preconditioners, integrator: c_rigid_obj.cpp:176-410,413-567,589-659,678-728,865-878) compiled from the reference
+    source with oracle/eigen_shim.inc standing in for the absent Eigen3.  Same call sequence as
+    src/Rigid.py: parameters, flags, configuration (setConfig + set_K_mats).  TEST INFRASTRUCTURE."""
+
+    def __init__(self, rigid_config, X, Q, a, eta, dt, wall_PC=False, block_PC=False, dtype=np.float64):
+        L = ref_apply_M_lib()
+        if L is None:
+            raise OracleError("oracle/_ref/libref_members.so is not built (no /root/reference here)")
+        self.L, self.dt_ = L, np.dtype(dtype)
+        self.sfx = _CT[self.dt_][0]
+        self.h = ctypes.c_void_p(getattr(L, f"refm_create_{self.sfx}")())
+        cfg = _prep(rigid_config, dtype)
+        self.n_blb = cfg.size // 3
+        self._call("set_parameters", float(a), float(dt), 1.0, float(eta), cfg.ctypes.data, self.n_blb)
+        self._call("set_flags", int(block_PC), int(wall_PC))
+        self.set_config(X, Q)
+
+    def _call(self, name, *args):
+        st = getattr(self.L, f"refm_{name}_{self.sfx}")(self.h, *args)
+        if st != 0:
+            raise OracleError(f"reference member {name} threw")
+
+    def __del__(self):
+        try:
+            getattr(self.L, f"refm_destroy_{self.sfx}")(self.h)
+        except Exception:
+            pass
+
+    def _vec(self, x):
+        return _prep(x, self.dt_)
+
+    def set_config(self, X, Q):
+        X, Q = self._vec(X), self._vec(Q)
+        self.n_bod = X.size // 3
+        self._call("set_config", X.ctypes.data, Q.ctypes.data, self.n_bod)
+
+    def get_config(self):
+        X, Q = np.empty(3 * self.n_bod, self.dt_), np.empty(4 * self.n_bod, self.dt_)
+        self._call("get_config", X.ctypes.data, Q.ctypes.data)
+        return X.reshape(-1, 3), Q.reshape(-1, 4)
+
+    def positions(self):
+        out = np.empty(3 * self.n_bod * self.n_blb, self.dt_)
+        self._call("positions", out.ctypes.data)
+        return out.reshape(-1, 3)
+
+    def _mv(self, name, x, n_out):
+        x = self._vec(x)
+        out = np.empty(n_out, self.dt_)
+        self._call(name, x.ctypes.data, out.ctypes.data)
+        return out
+
+    def K_dot(self, U):
+        return self._mv("K_x_U", U, 3 * self.n_bod * self.n_blb)
+
+    def KT_dot(self, lam):
+        return self._mv("KT_x_Lam", lam, 6 * self.n_bod)
+
+    def Kinv_dot(self, V):
+        return self._mv("Kinv_x_V", V, 6 * self.n_bod)
+
+    def KTinv_dot(self, F):
+        return self._mv("KTinv_x_F", F, 3 * self.n_bod * self.n_blb)
+
+    def apply_M(self, F, r):
+        F, r = self._vec(F), self._vec(r)
+        out = np.empty_like(F)
+        self._call("apply_M", F.ctypes.data, r.ctypes.data, F.size // 3, out.ctypes.data)
+        return out
+
+    def apply_PC(self, b):
+        return self._mv("apply_PC", b, 3 * self.n_bod * self.n_blb + 6 * self.n_bod)
+
+    def evolve(self, U):
+        U = self._vec(U)
+        self._call("evolve", U.ctypes.data)
 
 
 def ref_apply_M(F, r, a, eta, wall, dtype=np.float64):

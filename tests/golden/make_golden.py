@@ -18,6 +18,9 @@ Run HERE (the build container), where /root/reference exists:
 * ``apply_M_ref_golden.npz`` -- apply_M of the cases above (and of a ragged cloud) computed by the
   REFERENCE'S OWN assembly + apply_M members compiled from the reference source
   (oracle/_ref/libref_apply_M.so); ``--apply-M-ref-only`` regenerates just this file.
+* ``members_ref_golden.npz`` -- quaternion normalisation, blob placement, K, K^T, K^-1, K^-T, both
+  preconditioners and the integrator of the cases above through the REFERENCE'S OWN member functions
+  (oracle/_ref/libref_members.so).
 * ``bd_golden.npz``    -- one fluctuating BD step per touching-sphere case with fixed noise through
   the dense oracle (both Brownian-increment routes).  ``--bd-only`` regenerates just this file.
 """
@@ -165,6 +168,32 @@ def apply_M_ref_golden():
     print("apply_M_ref_golden.npz:", len(out), "arrays from the reference's own apply_M")
 
 
+def members_ref_golden():
+    """Every committed case through THE REFERENCE'S OWN member functions (oracle.RefBody =
+    oracle/_ref/libref_members.so: setParameters / setConfig / set_K_mats / multi_body_pos / K_x_U /
+    KT_x_Lam / Kinv_x_V / KTinv_x_F / apply_PC (diagonal and block) / evolve_X_Q compiled from the
+    reference source), in double and float.  Pins the oracle's numpy restatement of those members where /root/reference is absent."""
+    out = {}
+    for name in CASES:
+        g = dict(np.load(os.path.join(HERE, name + ".npz")))
+        a, eta, wall, dt = float(g["a"]), float(g["eta"]), bool(g["wall"]), float(g["dt"])
+        for sfx, ndt in (("f64", np.float64), ("f32", np.float32)):
+            rb = orc.RefBody(g["cfg"], g["X"], g["Q"], a, eta, dt, wall_PC=wall, dtype=ndt)
+            X, Q = rb.get_config()
+            out[f"{name}/{sfx}/Qn"], out[f"{name}/{sfx}/r"] = Q, rb.positions()
+            out[f"{name}/{sfx}/KU"], out[f"{name}/{sfx}/KTlam"] = rb.K_dot(g["U"]), rb.KT_dot(g["lam"])
+            out[f"{name}/{sfx}/Kinv_lam"], out[f"{name}/{sfx}/KinvT_U"] = rb.Kinv_dot(g["lam"]), rb.KTinv_dot(g["U"])
+            for blk in (False, True):  # both preconditioners (lazily built at the first apply_PC, :591-596)
+                pcb = orc.RefBody(g["cfg"], g["X"], g["Q"], a, eta, dt, wall_PC=wall, block_PC=blk, dtype=ndt)
+                out[f"{name}/{sfx}/pc_{'block' if blk else 'diag'}"] = pcb.apply_PC(g["vec"])
+            rb.evolve(g["U"])
+            Xe, Qe = rb.get_config()
+            out[f"{name}/{sfx}/X_evolved"], out[f"{name}/{sfx}/Q_evolved"] = Xe, Qe
+            out[f"{name}/{sfx}/KU_evolved"] = rb.K_dot(g["U"])  # K rebuilt by evolve_X_Q (:876)
+    np.savez_compressed(os.path.join(HERE, "members_ref_golden.npz"), **out)
+    print("members_ref_golden.npz:", len(out), "arrays from the reference's own member functions")
+
+
 def bd_golden():
     """One fluctuating BD step per touching-sphere case with FIXED noise, through the dense oracle:
     Brownian increments by both routes (symmetric square root; block-Cholesky preconditioned root)
@@ -202,10 +231,12 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--apply-M-ref-only" in sys.argv:
         apply_M_ref_golden()
+        members_ref_golden()
         sys.exit(0)
     pair_golden()
     shells_check()
     for c in CASES:
         make_case(c)
     apply_M_ref_golden()
+    members_ref_golden()
     bd_golden()

@@ -380,3 +380,28 @@ def test_seeded_bd_step_equals_the_step_with_the_same_noise(orc, name):
     c = _solver(g, "double", block=True)
     Uc, _, _ = c.bd_step(F, kBT=0.004, seed=77, step=13, **kw)  # another step number: other noise
     assert rel_err(Uc, Ua) > 1e-3
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_cuda_path_against_the_reference_members_golden(name, precision):
+    """Every operator of the drop-in against tests/golden/members_ref_golden.npz: outputs of THE
+    REFERENCE'S OWN member functions (setConfig, multi_body_pos, K_x_U, KT_x_Lam, Kinv_x_V, KTinv_x_F,
+    apply_PC diagonal/block, evolve_X_Q) compiled from the reference source by oracle/build_ref.sh."""
+    g, ref = load_golden(name), load_golden("members_ref_golden")
+    want = lambda key: ref[f"{name}/f64/{key}"]  # noqa: E731
+    cb = _solver(g, precision)
+    X, Q = cb.get_config()
+    assert rel_err(Q, want("Qn")) < TOL_ON[precision]
+    assert rel_err(cb.get_blob_positions(), want("r")) < TOL_ON[precision]
+    assert rel_err(cb.K_dot(g["U"]), want("KU")) < TOL_ON[precision]
+    assert rel_err(cb.KT_dot(g["lam"]), want("KTlam")) < TOL_ON[precision]
+    assert rel_err(cb.Kinv_dot(g["lam"]), want("Kinv_lam")) < 10 * TOL_ON[precision]
+    assert rel_err(cb.KTinv_dot(g["U"]), want("KinvT_U")) < 10 * TOL_ON[precision]
+    if np.isfinite(want("pc_diag")).all():
+        for blk, key in ((False, "pc_diag"), (True, "pc_block")):
+            assert rel_err(_solver(g, precision, block=blk).apply_PC(g["vec"]), want(key)) < TOL_PC[precision], key
+    cb.evolve_rigid_bodies(g["U"])
+    Xe, Qe = cb.get_config()
+    assert rel_err(Xe, want("X_evolved")) < TOL_ON[precision] and rel_err(Qe, want("Q_evolved")) < TOL_ON[precision]
+    assert rel_err(cb.K_dot(g["U"]), want("KU_evolved")) < 2 * TOL_ON[precision]

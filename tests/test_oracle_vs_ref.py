@@ -154,3 +154,53 @@ def test_reference_members_live_when_the_reference_tree_is_here(orc):
     r[0, 2] = -0.1
     with pytest.raises(orc.OracleError):
         orc.ref_apply_M(g["lam"], r, float(g["a"]), float(g["eta"]), True)
+
+
+# ---- the reference's own state / placement / K / integrator members ----------------------------------
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_oracle_rigid_members_equal_the_reference_members_golden(orc, name):
+    """oracle.py's numpy restatement of setConfig (normalisation), multi_body_pos, K_x_U, KT_x_Lam,
+    Kinv_x_V, KTinv_x_F and evolve_X_Q against tests/golden/members_ref_golden.npz = outputs of those
+    REFERENCE MEMBERS compiled from the reference source (oracle.RefBody).  To rounding (the sums are a
+    handful of terms; the reference's sparse products and the oracle's closed forms order them
+    differently); the float build of the reference agrees at float accuracy."""
+    g, ref = load_golden(name), load_golden("members_ref_golden")
+    rcfg = orc.remove_mean(g["cfg"])
+    n_blb = rcfg.shape[0]
+    Qn = orc.normalize_quats(g["Q"])
+    r = orc.blob_positions(g["X"], Qn, rcfg)
+    got = {"Qn": Qn, "r": r, "KU": orc.K_dot(g["U"], r, g["X"], n_blb), "KTlam": orc.KT_dot(g["lam"], r, g["X"], n_blb),
+           "Kinv_lam": orc.Kinv_dense(r, g["X"], Qn, rcfg) @ g["lam"], "KinvT_U": orc.Kinv_dense(r, g["X"], Qn, rcfg).T @ g["U"]}
+    Xe, Qe = orc.evolve(g["X"], Qn, g["U"], float(g["dt"]))
+    got["X_evolved"], got["Q_evolved"] = Xe, Qe
+    got["KU_evolved"] = orc.K_dot(g["U"], orc.blob_positions(Xe, Qe, rcfg), Xe, n_blb)
+    for key, val in got.items():
+        assert rel_err(val, ref[f"{name}/f64/{key}"]) < 2e-15, key
+        assert rel_err(val, ref[f"{name}/f32/{key}"]) < 5e-6, key
+    # and the committed case fixtures the GPU tests use ARE these values
+    for key in ("Qn", "r", "KU", "KTlam", "Kinv_lam", "KinvT_U", "X_evolved", "Q_evolved"):
+        assert rel_err(g[key], ref[f"{name}/f64/{key}"]) < 2e-15, key
+    # both preconditioners: apply_PC of the reference (Eigen's inverse() / LLT through the shim) vs the
+    # oracle's PC class, on the cases where the reference's own LLT does not break down
+    if "pc_diag" in g:
+        for blk, key, tol in ((False, "pc_diag", 1e-14), (True, "pc_block", 1e-12)):
+            mine = orc.PC(g["X"], Qn, rcfg, float(g["a"]), float(g["eta"]), bool(g["wall"]), blk).apply(g["vec"])
+            assert rel_err(mine, ref[f"{name}/f64/{key}"]) < tol, key
+            assert rel_err(g[key], ref[f"{name}/f64/{key}"]) < tol, key
+            assert rel_err(mine, ref[f"{name}/f32/{key}"]) < 5e-3, key
+    else:  # blobs inside the wall-overlap layer: the reference's LLT of K^T Mt^-1 K yields NaNs
+        assert not np.isfinite(ref[f"{name}/f64/pc_diag"]).all()
+
+
+def test_reference_member_library_live(orc):
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_members.so not built (no /root/reference here)")
+    g, ref = load_golden("case_touch_wall"), load_golden("members_ref_golden")
+    rb = orc.RefBody(g["cfg"], g["X"], g["Q"], float(g["a"]), float(g["eta"]), float(g["dt"]), wall_PC=True)
+    assert np.array_equal(rb.positions(), ref["case_touch_wall/f64/r"])
+    assert np.array_equal(rb.K_dot(g["U"]), ref["case_touch_wall/f64/KU"])
+    assert np.array_equal(rb.KT_dot(g["lam"]), ref["case_touch_wall/f64/KTlam"])
+    # the reference's apply_M accepts more blobs than the bodies hold (tests/test_interface.py:171-177)
+    r = np.concatenate([rb.positions().reshape(-1), [7.0, -3.0, 2.0]])
+    F = np.concatenate([g["lam"], [0.3, -0.2, 0.9]])
+    assert rel_err(rb.apply_M(F, r), orc.apply_M(F, r, float(g["a"]), float(g["eta"]), True)) < 1e-14
