@@ -51,6 +51,32 @@ def cfg1(args):
         out["cpu_scipy_gmres_oracle_ops"] = {"seconds": dt, "pc_build_seconds": t_pc, "iterations": count[0], "info": int(info),
                                              "threads": orc.num_threads(),
                                              "vs_gpu_solution": float(np.linalg.norm(xc - x) / np.linalg.norm(x))}
+        if orc.ref_apply_M_lib() is not None:
+            # THE REFERENCE PATH ITSELF: scipy gmres over the reference's own members (compiled from its
+            # source, oracle.RefBody) composed exactly like src/Rigid.py:73-80 -- every operator application
+            # re-places the blobs, assembles the dense 12600 x 12600 matrix and runs a GEMV, single thread.
+            # Block PC like the fastest GPU run (the shim stores the reference's sparse matrices densely, so
+            # the PC set-up time is reported apart: Eigen's sparse products would be faster there).
+            rb = orc.RefBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=True)
+
+            def ref_saddle(v):
+                lam, U = v[:n3], v[n3:]
+                r = rb.positions()
+                return np.concatenate([rb.apply_M(lam, r) - rb.K_dot(U), rb.KT_dot(lam)])
+
+            t0 = time.perf_counter()
+            rb.apply_PC(np.zeros(n))
+            t_pc = time.perf_counter() - t0
+            Pr = LinearOperator((n, n), matvec=lambda v: rb.apply_PC(flip * v))
+            Ar = LinearOperator((n, n), matvec=ref_saddle)
+            count = [0]
+            t0 = time.perf_counter()
+            xr, info = gmres(Ar, rhs, M=Pr, rtol=1e-8, restart=60, maxiter=300, callback=lambda r_: count.__setitem__(0, count[0] + 1),
+                             callback_type="pr_norm")
+            dt = time.perf_counter() - t0
+            out["cpu_reference_members_scipy_gmres"] = {
+                "seconds": dt, "pc_build_seconds_shim_dense": t_pc, "iterations": count[0], "info": int(info), "threads": 1,
+                "preconditioner": "block", "vs_gpu_solution": float(np.linalg.norm(xr - x) / np.linalg.norm(x))}
     print(json.dumps(out), flush=True)
 
 
