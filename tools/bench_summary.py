@@ -21,7 +21,7 @@ def main():
     rows, bd_rows = [], []
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{rnd}_bench_*.json"))):
         d = load(path)
-        if not d or "config" not in d:
+        if not d or "config" not in d or d.get("impl") == "reference":
             continue
         name = os.path.basename(path)[len(rnd) + 7:-5]
         wl = d["config"]["workload"].split(";")[0]
