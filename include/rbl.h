@@ -241,8 +241,6 @@ int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
 int rbl_num_sym2_variants(const rbl_ctx* ctx);
 int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_sym2_variant(rbl_ctx* ctx, int idx); /* two-right-hand-side kernel; -1 = automatic */
-/* process-wide: 0 (default) thread-per-blob placement / K kernels, 1 shared-memory staged variants */
-int rbl_set_on_kernel_mode(int staged);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t rbl_launch_count(const rbl_ctx* ctx);
 /* mobility products (whole, or one rank's share) launched since creation */

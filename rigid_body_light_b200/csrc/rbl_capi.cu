@@ -7,7 +7,6 @@
 // call the same device path the rbl_dev_* entry points expose.
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -1597,7 +1596,6 @@ int rbl_create(int precision, int device, rbl_ctx** out) {
     g_create_error = "rbl_create: precision must be RBL_F32 (4) or RBL_F64 (8)";
     return RBL_ERR_INVALID;
   }
-  if (const char* e = std::getenv("RBL_ON_STAGED")) rbl::set_on_kernels_staged(e[0] == '1');  // A/B switch, see rbl.h
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -1761,7 +1759,6 @@ int rbl_noise_selfcheck(rbl_ctx* ctx, double* factor_err, double* inverse_err, i
   if (active) *active = a;
   return s;
 }
-int rbl_set_on_kernel_mode(int staged) { rbl::set_on_kernels_staged(staged != 0); return RBL_OK; }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }
 int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {

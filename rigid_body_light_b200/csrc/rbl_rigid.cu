@@ -104,76 +104,6 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// Alternative layout of place_blobs / k_dot below (selectable: set_on_kernels_staged): each CTA stages its
-// 256 blobs = 768 reals through shared memory so that every global load / store instruction is unit
-// stride (stride-3 shared accesses are conflict-free: gcd(3, 32) = 1); 32-bit index arithmetic.
-static int g_on_staged = 0;
-void set_on_kernels_staged(int on) { g_on_staged = on; }
-constexpr int kBlobBlock = 256;
-
-template <typename real>
-__global__ void __launch_bounds__(kBlobBlock) place_blobs_staged_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                                                        const real* __restrict__ ref, unsigned n, unsigned n_blb,
-                                                                        real* __restrict__ r) {
-  __shared__ real st[3 * kBlobBlock];
-  const unsigned i0 = blockIdx.x * kBlobBlock, i = i0 + threadIdx.x;
-  if (i < n) {
-    const unsigned b = i / n_blb, k = i - b * n_blb;
-    real R[9];
-    quat_to_rot(Q + 4 * (size_t)b, R);
-    const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
-    st[3 * threadIdx.x + 0] = R[0] * cx + R[1] * cy + R[2] * cz + X[3 * (size_t)b + 0];
-    st[3 * threadIdx.x + 1] = R[3] * cx + R[4] * cy + R[5] * cz + X[3 * (size_t)b + 1];
-    st[3 * threadIdx.x + 2] = R[6] * cx + R[7] * cy + R[8] * cz + X[3 * (size_t)b + 2];
-  }
-  __syncthreads();
-  const unsigned e0 = 3u * i0, e1 = 3u * n;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const unsigned e = e0 + q * kBlobBlock + threadIdx.x;
-    if (e < e1) r[e] = st[q * kBlobBlock + threadIdx.x];
-  }
-}
-
-template <typename real>
-__global__ void __launch_bounds__(kBlobBlock) k_dot_staged_kernel(const real* __restrict__ U, const real* __restrict__ r,
-                                                                  const real* __restrict__ X, unsigned n, unsigned n_blb,
-                                                                  real sign, const real* add, real* out) {
-  __shared__ real st[3 * kBlobBlock];
-  const unsigned i0 = blockIdx.x * kBlobBlock, i = i0 + threadIdx.x;
-  const unsigned e0 = 3u * i0, e1 = 3u * n;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const unsigned e = e0 + q * kBlobBlock + threadIdx.x;
-    if (e < e1) st[q * kBlobBlock + threadIdx.x] = r[e];
-  }
-  __syncthreads();
-  real vx = 0, vy = 0, vz = 0;
-  if (i < n) {
-    const unsigned b = i / n_blb;
-    const real* u = U + 6 * (size_t)b;
-    const real px = st[3 * threadIdx.x] - X[3 * (size_t)b], py = st[3 * threadIdx.x + 1] - X[3 * (size_t)b + 1],
-               pz = st[3 * threadIdx.x + 2] - X[3 * (size_t)b + 2];
-    vx = u[0] + (u[4] * pz - u[5] * py);
-    vy = u[1] + (u[5] * px - u[3] * pz);
-    vz = u[2] + (u[3] * py - u[4] * px);
-    vx *= sign; vy *= sign; vz *= sign;
-  }
-  // each thread overwrites only the three slots it read: no barrier needed before the writes
-  st[3 * threadIdx.x] = vx; st[3 * threadIdx.x + 1] = vy; st[3 * threadIdx.x + 2] = vz;
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const unsigned e = e0 + q * kBlobBlock + threadIdx.x;
-    if (e < e1) {
-      real v = st[q * kBlobBlock + threadIdx.x];
-      if (add) v += add[e];
-      out[e] = v;
-    }
-  }
-}
-
-
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
                                    const real* __restrict__ ref, int n_bod, int n_blb,
@@ -196,10 +126,7 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
-  if (g_on_staged)
-    place_blobs_staged_kernel<real><<<(unsigned)((n + kBlobBlock - 1) / kBlobBlock), kBlobBlock, 0, s>>>(X, Q, ref, (unsigned)n, (unsigned)n_blb, r);
-  else
-    place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
+  place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
   return cudaGetLastError();
 }
 
@@ -227,13 +154,9 @@ cudaError_t k_dot(const real* U, const real* r, const real* X, int n_bod, int n_
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
-  if (g_on_staged)
-    k_dot_staged_kernel<real><<<(unsigned)((n + kBlobBlock - 1) / kBlobBlock), kBlobBlock, 0, s>>>(U, r, X, (unsigned)n, (unsigned)n_blb, sign, add, out);
-  else
-    k_dot_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(U, r, X, n_bod, n_blb, sign, add, out);
+  k_dot_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(U, r, X, n_bod, n_blb, sign, add, out);
   return cudaGetLastError();
 }
-
 
 template <typename real>
 __global__ void kt_dot_kernel(const real* __restrict__ lam, const real* __restrict__ r,

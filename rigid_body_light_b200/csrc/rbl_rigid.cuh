@@ -39,10 +39,6 @@ cudaError_t ktk_inv_blocks(const real* Q, const real* ref, int n_bod, int n_blb,
 template <typename real>
 cudaError_t ktk_inv_apply(const real* S, int n_bod, int n_blb, real* v, cudaStream_t s);
 
-// 0 (default): thread-per-blob place_blobs / k_dot; 1: shared-memory staged variants (unit-stride
-// global accesses).  Process-wide switch for A/B measurements (tools/on_kernels_bw.py).
-void set_on_kernels_staged(int on);
-
 // ---- preconditioner -----------------------------------------------------------------
 // Common structure (apply_PC :589-616):  y = Mt^-1 slip ;  U_b = N_b (-F_b - K_b^T y_b) ;
 // Lambda = y + (Mt^-1 K)_b U_b.   Y = Mt^-1 K (sz x 6 per body, layout [b][c][sz]) and the

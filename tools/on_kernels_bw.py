@@ -27,12 +27,10 @@ def main():
     s = sphere_suspension(nb, shell, True)
     ref = s["cfg"] - s["cfg"].mean(axis=0)
     n = nb * shell
-    modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"])]
-    for precision, mode in [(p, m) for p in ("single", "double") for m in modes]:
+    for precision in ("single", "double"):
         tdt = torch.float32 if precision == "single" else torch.float64
         sz = 4 if precision == "single" else 8
         ctx = Context(precision)
-        ctx.L.rbl_set_on_kernel_mode(mode)
         ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
         ctx.set_flags(0, 1)
         ctx.set_config(s["X"], s["Q"])
@@ -64,7 +62,7 @@ def main():
                 fn()
             ms = ctx.timer_stop() / reps
             gbs = nbytes / (ms * 1e-3) / 1e9
-            print(json.dumps({"kernel": name, "precision": precision, "staged": mode, "blobs": n, "bodies": nb, "ms": ms,
+            print(json.dumps({"kernel": name, "precision": precision, "blobs": n, "bodies": nb, "ms": ms,
                               "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "peak_gbs": peak, "peak_source": src,
                               "frac": gbs / peak}), flush=True)
         ctx.close()
