@@ -204,3 +204,41 @@ def test_reference_member_library_live(orc):
     r = np.concatenate([rb.positions().reshape(-1), [7.0, -3.0, 2.0]])
     F = np.concatenate([g["lam"], [0.3, -0.2, 0.9]])
     assert rel_err(rb.apply_M(F, r), orc.apply_M(F, r, float(g["a"]), float(g["eta"]), True)) < 1e-14
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_equals_the_reference_members_on_random_suspensions(orc, seed):
+    """Beyond the five committed cases: seeded random suspensions (1-4 bodies, random blob clouds as
+    body shapes, random radius / viscosity / un-normalised quaternions, with and without the wall)
+    through the live reference-member library and through the oracle.  Skipped where
+    oracle/_ref/libref_members.so does not exist."""
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_members.so not built (no /root/reference here)")
+    rng = np.random.default_rng(1000 + seed)
+    nb, n_blb, wall = int(rng.integers(1, 5)), int(rng.integers(3, 9)), bool(seed % 2)
+    cfg = rng.uniform(-0.8, 0.8, (n_blb, 3))
+    a, eta, dt = float(rng.uniform(0.1, 0.4)), float(rng.uniform(0.5, 2.0)), 0.01
+    X = rng.uniform(-3, 3, (nb, 3))
+    X[:, 2] = rng.uniform(2.0, 4.0, nb)  # every blob above z = a
+    Q = rng.standard_normal((nb, 4)) * rng.uniform(0.3, 3.0, (nb, 1))
+    rb = orc.RefBody(cfg, X, Q, a, eta, dt, wall_PC=wall)
+    rcfg, Qn = orc.remove_mean(cfg), orc.normalize_quats(Q)
+    r = orc.blob_positions(X, Qn, rcfg)
+    lam, U = rng.standard_normal(3 * nb * n_blb), rng.standard_normal(6 * nb)
+    vec = rng.standard_normal(3 * nb * n_blb + 6 * nb)
+    assert rel_err(rb.get_config()[1], Qn) < 1e-15 and rel_err(rb.positions(), r) < 1e-15
+    assert rel_err(orc.K_dot(U, r, X, n_blb), rb.K_dot(U)) < 5e-15
+    assert rel_err(orc.KT_dot(lam, r, X, n_blb), rb.KT_dot(lam)) < 5e-15
+    Kinv = orc.Kinv_dense(r, X, Qn, rcfg)
+    assert rel_err(Kinv @ lam, rb.Kinv_dot(lam)) < 1e-13 and rel_err(Kinv.T @ U, rb.KTinv_dot(U)) < 1e-13
+    assert np.array_equal(orc.apply_M_dense(lam, r, a, eta, wall), rb.apply_M(lam, r))
+    assert rel_err(orc.apply_M(lam, r, a, eta, wall), rb.apply_M(lam, r)) < 1e-14
+    saddle = np.concatenate([rb.apply_M(vec[:lam.size], rb.positions()) - rb.K_dot(vec[lam.size:]), rb.KT_dot(vec[:lam.size])])
+    assert rel_err(orc.apply_saddle(vec, X, Qn, rcfg, a, eta, wall), saddle) < 1e-14  # Rigid.py:73-80 composition
+    for blk in (False, True):
+        ref_pc = orc.RefBody(cfg, X, Q, a, eta, dt, wall_PC=wall, block_PC=blk).apply_PC(vec)
+        if np.isfinite(ref_pc).all():
+            assert rel_err(orc.PC(X, Qn, rcfg, a, eta, wall, blk).apply(vec), ref_pc) < 1e-10
+    rb.evolve(U)
+    Xe, Qe = orc.evolve(X, Qn, U, dt)
+    assert rel_err(rb.get_config()[0], Xe) < 1e-15 and rel_err(rb.get_config()[1], Qe) < 1e-15
