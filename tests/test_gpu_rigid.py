@@ -405,3 +405,40 @@ def test_cuda_path_against_the_reference_members_golden(name, precision):
     Xe, Qe = cb.get_config()
     assert rel_err(Xe, want("X_evolved")) < TOL_ON[precision] and rel_err(Qe, want("Q_evolved")) < TOL_ON[precision]
     assert rel_err(cb.K_dot(g["U"]), want("KU_evolved")) < 2 * TOL_ON[precision]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("wall", [True, False])
+def test_cuda_path_against_the_live_reference_members(orc, wall, precision):
+    """The drop-in against THE REFERENCE'S OWN CODE running beside it (oracle.RefBody =
+    oracle/_ref/libref_members.so, compiled from the reference source; it travels to the GPU box with
+    the snapshot): 30 touching spheres of shell_N_42 (1260 blobs), every operator of src/Rigid.py on the
+    same inputs.  Skipped where the library is absent."""
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_members.so not built")
+    from Rigid import RigidBody
+    from rigid_body_light_b200.shells import sphere_suspension
+
+    s = sphere_suspension(30, 42, wall)
+    Q = s["Q"] * np.linspace(0.5, 2.0, 30)[:, None]  # un-normalised on purpose (:216)
+    ndt = np.float64 if precision == "double" else np.float32
+    cb = RigidBody(s["cfg"], s["X"], Q, s["a"], 0.8, 0.02, wall_PC=wall, block_PC=True, precision=precision)
+    rb = orc.RefBody(s["cfg"].astype(ndt), s["X"].astype(ndt), Q.astype(ndt), s["a"], 0.8, 0.02, wall_PC=wall, block_PC=True)
+    rng = np.random.default_rng(8)
+    n3, n6 = 3 * 30 * 42, 180
+    lam, U, vec = rng.standard_normal(n3).astype(ndt), rng.standard_normal(n6).astype(ndt), rng.standard_normal(n3 + n6).astype(ndt)
+    tol_on, tol_m, tol_pc = TOL_ON[precision], TOL[precision], TOL_PC[precision]
+    assert rel_err(cb.get_config()[1], rb.get_config()[1]) < tol_on
+    r = cb.get_blob_positions()
+    assert rel_err(r, rb.positions()) < tol_on
+    assert rel_err(cb.K_dot(U), rb.K_dot(U)) < tol_on and rel_err(cb.KT_dot(lam), rb.KT_dot(lam)) < tol_on
+    assert rel_err(cb.Kinv_dot(lam), rb.Kinv_dot(lam)) < 10 * tol_on and rel_err(cb.KTinv_dot(U), rb.KTinv_dot(U)) < 10 * tol_on
+    rr = rb.positions()
+    assert rel_err(cb.apply_M(lam, rr), rb.apply_M(lam, rr)) < tol_m
+    ref_saddle = np.concatenate([rb.apply_M(vec[:n3], rr) - rb.K_dot(vec[n3:]), rb.KT_dot(vec[:n3])])  # Rigid.py:73-80
+    assert rel_err(cb.apply_saddle(vec), ref_saddle) < 10 * tol_m
+    assert rel_err(cb.apply_PC(vec), rb.apply_PC(vec)) < tol_pc
+    cb.evolve_rigid_bodies(U)
+    rb.evolve(U)
+    assert rel_err(cb.get_config()[0], rb.get_config()[0]) < tol_on and rel_err(cb.get_config()[1], rb.get_config()[1]) < tol_on
+    assert rel_err(cb.get_blob_positions(), rb.positions()) < 2 * tol_on
