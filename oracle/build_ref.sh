@@ -63,6 +63,7 @@ gen float f32
 gen_members() { # $1 = real type, $2 = suffix
   {
     echo '#include <cmath>'
+    echo '#include <cstdio>'
     echo '#include <iostream>'
     echo '#include <stdexcept>'
     echo '#include <cstdlib>'
@@ -80,11 +81,18 @@ gen_members() { # $1 = real type, $2 = suffix
     echo '  bool PC_mat_Set = false; bool cfg_set = false; int N_bod = 0; std::vector<Quat> Q_n; std::vector<Vector> X_n;'
     echo '  Matrix ref_cfg; int N_blb = 0; bool parametersSet = false; SparseM K, KT, Kinv;'
     echo '  SparseM invM; SparseM Ninv; std::vector<Eigen::LLT<Matrix>> N_lu;'
+    # the reference seeds rand_vector from the wall clock (:730-741); here the test injects the noise
+    echo '  std::vector<Vector> injected_noise; size_t noise_pos = 0; bool split_rand = true;'
+    echo '  Vector rand_vector(int N) { (void)N; return injected_noise[noise_pos++ % injected_noise.size()]; }'
+    echo '  static double timeNow() { return 0.0; }'
     awk '/^  void removeMean\(Matrix &cfg\)/{on=1} /preconditioner\/solver functions/{on=0} on{print}' "$REF_SRC"
     awk '/template <class AVector> Matrix rotne_prager_tensor\(/{on=1} /^  SparseM Block_diag_invM\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  DiagM make_damp_mat\(/{on=1} /^  Vector M_half_W\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  SparseM Block_diag_invM\(\)/{on=1} /template <class AVector> void test_PC\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  Vector apply_PC\(const Vector &IN\)/{on=1} /^  DiagM make_damp_mat\(/{on=0} on{print}' "$REF_SRC"
+    awk '/^  Vector M_half_W\(\)/{on=1} /Dynamics\/time integration/{on=0} on{print}' "$REF_SRC"
+    awk '/^  Vector M_RFD\(\)/{on=1} /template <class AVector> auto M_RFD_cfgs\(/{on=0} on{print}' "$REF_SRC"
+    awk '/^  auto RHS_and_Midpoint\(/{on=1} /^  auto get_K\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  Quat Q_from_Om\(/{on=1} /^  Vector rand_vector\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  void evolve_X_Q\(Vector &U\)/{on=1} /^  void evolve_X_Q_RFD\(/{on=0} on{print}' "$REF_SRC"
     echo '};'
@@ -138,6 +146,28 @@ extern "C" int refm_KTinv_x_F_$2(void *h, const $1 *F, $1 *out) {
 extern "C" int refm_apply_PC_$2(void *h, const $1 *in, $1 *out) {
   B_$2 *b = static_cast<B_$2 *>(h);
   try { out_$2(b->apply_PC(in_$2(in, 3L * b->N_bod * b->N_blb + 6L * b->N_bod)), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+extern "C" int refm_M_RFD_$2(void *h, const $1 *W, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  b->injected_noise = {in_$2(W, 3L * b->N_bod * b->N_blb)}; b->noise_pos = 0;
+  try { out_$2(b->M_RFD(), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+extern "C" int refm_M_half_W_$2(void *h, const $1 *W, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  b->injected_noise = {in_$2(W, 3L * b->N_bod * b->N_blb)}; b->noise_pos = 0;
+  try { out_$2(b->M_half_W(), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+// RHS_and_Midpoint (:917-976) with rand_vector returning W1, W2 (M_half_W twice), then Wr (M_RFD)
+extern "C" int refm_RHS_$2(void *h, const $1 *slip, const $1 *force, const $1 *W1, const $1 *W2, const $1 *Wr, double kBT, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  const long n3 = 3L * b->N_bod * b->N_blb;
+  b->kBT = ($1)kBT;
+  b->injected_noise = {in_$2(W1, n3), in_$2(W2, n3), in_$2(Wr, n3)}; b->noise_pos = 0;
+  V_$2 s = in_$2(slip, n3), f = in_$2(force, 6L * b->N_bod);
+  try { out_$2(b->RHS_and_Midpoint(s, f), out); } catch (const std::runtime_error &) { return 2; }
   return 0;
 }
 extern "C" int refm_evolve_$2(void *h, const $1 *U) {

@@ -103,7 +103,8 @@ def ref_apply_M_lib():
             getattr(L, f"refm_apply_M_{sfx}").argtypes = [vp, vp, vp, ci, vp]
             for name in ("positions", "evolve"):
                 getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp]
-            for name in ("K_x_U", "KT_x_Lam", "Kinv_x_V", "KTinv_x_F", "apply_PC"):
+            getattr(L, f"refm_RHS_{sfx}").argtypes = [vp, vp, vp, vp, vp, vp, cd, vp]
+            for name in ("K_x_U", "KT_x_Lam", "Kinv_x_V", "KTinv_x_F", "apply_PC", "M_RFD", "M_half_W"):
                 getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp, vp]
         _REF_APPLY = L
     return _REF_APPLY
@@ -183,6 +184,23 @@ class RefBody:
 
     def apply_PC(self, b):
         return self._mv("apply_PC", b, 3 * self.n_bod * self.n_blb + 6 * self.n_bod)
+
+    def M_RFD(self, W):
+        """the reference's M_RFD (:769-796) with ITS rand_vector replaced by the given noise W"""
+        return self._mv("M_RFD", W, 3 * self.n_bod * self.n_blb)
+
+    def M_half_W(self, W):
+        """the reference's M_half_W (:661-675: chol(B M B) W) with the given noise W"""
+        return self._mv("M_half_W", W, 3 * self.n_bod * self.n_blb)
+
+    def RHS_and_Midpoint(self, slip, force, W1, W2, Wr, kBT):
+        """the reference's RHS_and_Midpoint (:917-976) with rand_vector returning W1, W2, Wr in the order
+        it draws them: [slip - kBT M_RFD - c2 (M^{1/2}W1 - M^{1/2}W2) ; -force]"""
+        a = [self._vec(x) for x in (slip, force, W1, W2, Wr)]
+        out = np.empty(3 * self.n_bod * self.n_blb + 6 * self.n_bod, self.dt_)
+        self._call("RHS", a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data, float(kBT),
+                   out.ctypes.data)
+        return out
 
     def evolve(self, U):
         U = self._vec(U)
@@ -626,7 +644,19 @@ def noise_block_cholesky(factors, A, W):
     return L @ (S @ W)
 
 
-def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta=1.0e-4, noise="symmetric"):
+def rfd_M(X, Q, ref_cfg, a, eta, wall, W, delta=1.0e-4):
+    """M_RFD (c_rigid_obj.cpp:769-796): (M(q+) - M(q-)) W / delta with q+- = q +- (delta/2) K^-1 W."""
+    ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
+    r = blob_positions(X, Q, ref)
+    uom = Kinv_apply(W, r, X, Q, ref)
+    Xp, Qp = update_X_Q(X, Q, 0.5 * delta * uom)
+    Xn, Qn = update_X_Q(X, Q, -0.5 * delta * uom)
+    rp, rn = blob_positions(Xp, Qp, ref), blob_positions(Xn, Qn, ref)
+    return (apply_M(W, rp, a, eta, wall) - apply_M(W, rn, a, eta, wall)) / delta
+
+
+def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta=1.0e-4, noise="symmetric",
+            return_rhs=False):
     """The trapezoidal-slip midpoint step RHS_and_Midpoint sets up (c_rigid_obj.cpp:917-976),
     completed as intended (the reference computes the midpoint configuration but never installs
     it) and evaluated with dense float64 linear algebra:
@@ -634,7 +664,9 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
       different square root with the same covariance; Lanczos converges to the symmetric one),
       RFD (:769-796), BI (:945-948), midpoint (:954-958), dense solve of
       [M -K; K^T 0][lam;U] = [slip - kBT RFD - BI ; F_ext] at the midpoint, evolve from q^n.
-    Returns (U, X_new, Q_new)."""
+    Returns (U, X_new, Q_new); with return_rhs the assembled right-hand side and the midpoint
+    configuration instead (rhs, X_mid, Q_mid).  noise: "symmetric" (sqrtm), "block_cholesky" (the
+    product path's default) or "cholesky" (the reference's M_half_W)."""
     from scipy.linalg import sqrtm
 
     ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
@@ -656,14 +688,13 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
             fac = noise_factors(r, Q, ref, a, eta, wall)
             mh1 = noise_block_cholesky(fac, M, W1)
             mh2 = noise_block_cholesky(fac, M, W2)
+        elif noise == "cholesky":  # the reference's own M_half_W (:661-675): the lower Cholesky factor of B M B
+            Lc = np.linalg.cholesky(M)
+            mh1, mh2 = Lc @ W1, Lc @ W2
         else:
             S = np.real(sqrtm(M))
             mh1, mh2 = S @ W1, S @ W2
-        uom = Kinv_apply(Wr, r, X, Q, ref)
-        Xp, Qp = update_X_Q(X, Q, 0.5 * delta * uom)
-        Xn, Qn = update_X_Q(X, Q, -0.5 * delta * uom)
-        rp, rn = blob_positions(Xp, Qp, ref), blob_positions(Xn, Qn, ref)
-        rfd = (apply_M(Wr, rp, a, eta, wall) - apply_M(Wr, rn, a, eta, wall)) / delta
+        rfd = rfd_M(X, Q, ref, a, eta, wall, Wr, delta)
         c1, c2 = 2.0 * np.sqrt(kBT / dt), np.sqrt(kBT / dt)
         rhs_slip -= kBT * rfd + c2 * (mh1 - mh2)
         Xm, Qm = update_X_Q(X, Q, 0.5 * dt * Kinv_apply(c1 * mh1, r, X, Q, ref))
@@ -674,7 +705,10 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
         Mm = B[:, None] * Mm * B[None, :]
     K = K_dense(rm, Xm, n_blb)
     A = np.block([[Mm, -K], [K.T, np.zeros((6 * nb, 6 * nb))]])
-    sol = np.linalg.solve(A, np.concatenate([rhs_slip, np.asarray(F_ext, dtype=np.float64).reshape(-1)]))
+    rhs = np.concatenate([rhs_slip, np.asarray(F_ext, dtype=np.float64).reshape(-1)])
+    if return_rhs:
+        return rhs, Xm, Qm
+    sol = np.linalg.solve(A, rhs)
     U = sol[n3:]
     Xn, Qn = evolve(X, Q, U, dt)
     return U, Xn, Qn

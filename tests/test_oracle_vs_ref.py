@@ -242,3 +242,70 @@ def test_oracle_equals_the_reference_members_on_random_suspensions(orc, seed):
     rb.evolve(U)
     Xe, Qe = orc.evolve(X, Qn, U, dt)
     assert rel_err(rb.get_config()[0], Xe) < 1e-15 and rel_err(rb.get_config()[1], Qe) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free", "case_overlap_wall"])
+def test_rfd_and_brownian_increment_against_the_reference_members(orc, name):
+    """The stochastic pieces of the BD step against the reference's own M_RFD (:769-796) and M_half_W
+    (:661-675), compiled from its source with rand_vector returning an injected noise vector (the
+    reference seeds it from the wall clock): the oracle's random finite difference is the reference's
+    for the same noise, and the reference's Brownian increment chol(B M B) W has the covariance the
+    drop-in's increments have (a different square root of the same matrix)."""
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_members.so not built (no /root/reference here)")
+    g = load_golden(name)
+    a, eta, wall, dt = float(g["a"]), float(g["eta"]), bool(g["wall"]), float(g["dt"])
+    rb = orc.RefBody(g["cfg"], g["X"], g["Q"], a, eta, dt, wall_PC=wall)
+    rcfg = orc.remove_mean(g["cfg"])
+    W = np.random.default_rng(3).standard_normal(g["r"].size)
+    mine = orc.rfd_M(g["X"], g["Qn"], rcfg, a, eta, wall, W, delta=1.0e-4)
+    # a difference quotient with delta = 1e-4 amplifies rounding by 1e4: agreement to ~1e-10
+    assert rel_err(mine, rb.M_RFD(W)) < 1e-8
+    n = g["r"].size
+    if n <= 200:
+        A = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
+        B = orc.damp_diag(g["r"], a)
+        A = B[:, None] * A * B[None, :]
+        L = np.stack([rb.M_half_W(e) for e in np.eye(n)], axis=1)
+        assert np.allclose(L, np.tril(L)) and np.linalg.norm(L @ L.T - A) / np.linalg.norm(A) < 1e-13
+        fac = orc.noise_factors(g["r"], g["Qn"], rcfg, a, eta, wall)
+        S = np.stack([orc.noise_block_cholesky(fac, A, e) for e in np.eye(n)], axis=1)
+        assert np.linalg.norm(S @ S.T - L @ L.T) / np.linalg.norm(A) < 1e-9  # same covariance, different roots
+        assert np.linalg.norm(S - L) / np.linalg.norm(L) > 1e-2
+
+
+@pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
+def test_bd_right_hand_side_against_the_reference_RHS_and_Midpoint(orc, name):
+    """The right-hand side of the BD step's saddle solve against the reference's own RHS_and_Midpoint
+    (:917-976) compiled from its source, fed the same three noise vectors in the order it draws them
+    and the reference's own noise route (Cholesky factor): slip row  slip - kBT M_RFD - sqrt(kBT/dt)
+    (M^{1/2}W1 - M^{1/2}W2)  identical; force row: the reference returns -F for its PC's
+    [M -K; -K^T 0] convention, the drop-in solves apply_saddle = [M -K; +K^T 0] with +F
+     -- the same equations."""
+    if orc.ref_apply_M_lib() is None:
+        pytest.skip("oracle/_ref/libref_members.so not built (no /root/reference here)")
+    g = dict(load_golden(name))
+    a, eta, wall, dt = float(g["a"]), float(g["eta"]), bool(g["wall"]), float(g["dt"])
+    rcfg = orc.remove_mean(g["cfg"])
+    if not wall:
+        # the reference's M_half_W multiplies by the wall damping B = min(1, z/a) even without the wall
+        # (:668-669; the drop-in applies B with the wall only, DESIGN.md section 6): lift the free-space
+        # case so that every blob has z >= a and B = I, which is what this test is not about
+        g["X"] = g["X"] + np.array([0.0, 0.0, 5.0])
+        g["r"] = orc.blob_positions(g["X"], g["Qn"], rcfg)
+        assert g["r"][:, 2].min() >= a
+    rb = orc.RefBody(g["cfg"], g["X"], g["Q"], a, eta, dt, wall_PC=wall)
+    rng = np.random.default_rng(31)
+    nb, n3 = g["X"].shape[0], g["r"].size
+    F, slip = rng.standard_normal(6 * nb), 0.1 * rng.standard_normal(n3)
+    W = [rng.standard_normal(n3) for _ in range(3)]
+    kBT = 0.004
+    ref_rhs = rb.RHS_and_Midpoint(slip, F, *W, kBT)
+    rhs, Xm, Qm = orc.bd_step(g["X"], g["Qn"], rcfg, a, eta, dt, kBT, wall, F, slip, *W, noise="cholesky", return_rhs=True)
+    assert rel_err(rhs[:n3], ref_rhs[:n3]) < 1e-9
+    assert np.array_equal(ref_rhs[n3:], -F) and np.array_equal(rhs[n3:], F)
+    # the step moved to the midpoint along K^-1 (2 sqrt(kBT/dt) M^{1/2} W1) dt/2  (:954-958)
+    Lc = np.linalg.cholesky(np.asarray(orc.dense_mobility(g["r"], a, eta, wall)) * np.outer(orc.damp_diag(g["r"], a), orc.damp_diag(g["r"], a)))
+    uom = orc.Kinv_apply(2.0 * np.sqrt(kBT / dt) * (Lc @ W[0]), g["r"], g["X"], g["Qn"], rcfg)
+    Xw, Qw = orc.update_X_Q(g["X"], g["Qn"], 0.5 * dt * uom)
+    assert rel_err(Xm, Xw) < 1e-14 and rel_err(Qm, Qw) < 1e-14
