@@ -115,6 +115,74 @@ def build_suspension(workload):
     return s
 
 
+
+PARITY_TOL = {"single": 1e-5, "double": 1e-12}  # BASELINE.json north_star
+
+
+def oracle_parity(precision, op, s, x_local_np, out_local_np, ranges, rank, world, n_rows, dist, torch):
+    """Sampled rows of THIS run's output against the CPU oracle (outside every timed region; the
+    oracle is the checker here, never the thing measured).  Rows: the first and the last blob of
+    the suspension, the two blobs either side of every rank boundary, and seeded random rows, up
+    to `n_rows`; every rank checks the sampled rows it owns -- slip rows (M lam - K U)_i against
+    oracle.apply_M(rows) - oracle.K_dot, and the force/torque rows K^T lam of the bodies those
+    blobs belong to -- on the same inputs the GPU saw (positions as placed on the device, lambda
+    and U in the run's precision).  Raises if the relative L2 error over the sampled rows exceeds
+    north_star's bound (1e-5 float, 1e-12 double)."""
+    from oracle import oracle as orc
+
+    ndt = np.float32 if precision == "single" else np.float64
+    nb, n_blb, wall = s["n_bodies"], s["n_blb"], s["wall"]
+    n_all = nb * n_blb
+    lo, hi = ranges[rank]
+    t0, n_local = lo * n_blb, (hi - lo) * n_blb
+    rows = {0, n_all - 1}
+    for (l, _h) in ranges[1:]:
+        rows.update((l * n_blb - 1, l * n_blb))
+    extra = np.random.default_rng(7).permutation(n_all)
+    for r in extra:
+        if len(rows) >= n_rows:
+            break
+        rows.add(int(r))
+    rows = np.array(sorted(rows), dtype=np.int64)
+    mine = rows[(rows >= t0) & (rows < t0 + n_local)]
+    r_all = op.r_all.cpu().numpy().astype(np.float64)
+    lam_all = op.lam_all.cpu().numpy().astype(np.float64)  # the all-gathered lambda of the last step
+    X_local = np.asarray(s["X"][lo:hi], dtype=ndt).astype(np.float64)
+    U_local = x_local_np[3 * n_local:].astype(ndt).astype(np.float64).reshape(-1, 6)
+    got = out_local_np.astype(np.float64)
+    num = den = knum = kden = 0.0
+    worst = 0.0
+    if mine.size:
+        want = orc.apply_M(lam_all, r_all, s["a"], 1.0, wall, rows=mine.astype(np.int32)).reshape(-1, 3)
+        b_of = (mine - t0) // n_blb
+        rho = r_all.reshape(-1, 3)[mine] - X_local[b_of]
+        want = want - (U_local[b_of, :3] + np.cross(U_local[b_of, 3:], rho))
+        g = got[: 3 * n_local].reshape(-1, 3)[mine - t0]
+        num, den = float(((g - want) ** 2).sum()), float((want ** 2).sum())
+        worst = float((np.linalg.norm(g - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+        bodies = np.unique(b_of)
+        rl = r_all.reshape(-1, 3)[t0:t0 + n_local].reshape(-1, n_blb, 3)[bodies]
+        ll = lam_all.reshape(-1, 3)[t0:t0 + n_local].reshape(-1, n_blb, 3)[bodies]
+        wantk = orc.KT_dot(ll.reshape(-1), rl.reshape(-1), X_local[bodies], n_blb).reshape(-1, 6)
+        gk = got[3 * n_local:].reshape(-1, 6)[bodies]
+        knum, kden = float(((gk - wantk) ** 2).sum()), float((wantk ** 2).sum())
+    acc = [num, den, knum, kden, float(mine.size)]
+    if world > 1:
+        t = torch.tensor(acc, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        w = torch.tensor([worst], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        acc, worst = t.tolist(), float(w.item())
+    rel = float(np.sqrt(acc[0] / acc[1]))
+    rel_k = float(np.sqrt(acc[2] / acc[3]))
+    tol = PARITY_TOL[precision]
+    if not (rel <= tol and rel_k <= tol):
+        raise AssertionError(f"oracle parity FAILED ({precision}, {world} GPUs): slip rows {rel:.3e}, K^T rows {rel_k:.3e} > {tol:g}")
+    return {"rows": int(acc[4]), "rel_err": rel, "max_row_rel_err": worst, "kt_rel_err": rel_k, "tol": tol,
+            "rows_include": "first/last blob, both sides of every rank boundary, seeded random rows",
+            "against": "oracle.apply_M(rows=...) - oracle.K_dot and oracle.KT_dot (CPU restatement of c_rigid_obj.cpp:31-142,"
+                       "404-459,618-659; long-double row sums) on the positions the device placed; relative L2 over the sampled rows"}
+
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
@@ -234,6 +302,7 @@ def run_ours(args):
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
+                ctx.call("rbl_flush_l2")              # same experiment as `value`: L2 flushed between steps
                 ctx.call("rbl_apply_saddle", hx, ho)  # H2D + step + D2H, synchronous
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
             host_out = np.frombuffer((ctypes.c_char * nbytes).from_address(ho.value), dtype=ndt).copy()
@@ -247,6 +316,7 @@ def run_ours(args):
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
+                ctx.call("rbl_flush_l2")
                 x_local.copy_(hx, non_blocking=True)
                 op.apply(x_local, out_local)
                 ho.copy_(out_local, non_blocking=True)
@@ -262,6 +332,10 @@ def run_ours(args):
             raise AssertionError(f"host-buffer and device-resident paths disagree ({precision}): relative L2 {agree:.3e}, "
                                  f"max |diff| {dd.max():.3e} at {int(dd.argmax())}")
         ctx.call("rbl_sync")
+        parity = None
+        if args.parity_rows > 0:
+            parity = oracle_parity(precision, op, s, x_local_np, dev_out, ranges, rank, world, args.parity_rows,
+                                   dist if world > 1 else None, torch)
 
         traffic = None
         try:
@@ -287,7 +361,7 @@ def run_ours(args):
                                        "than the convention assumes; issue-slot utilisation is in profiles/",
                          "peak_source": "FMA-chain microbenchmark run live on this GPU (rbl_fma_peak); nominal "
                                         + ("74.4" if precision == "single" else "37.2") + " TFLOP/s at 148 SM x 1.965 GHz"},
-            "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()),
+            "clocks": clocks, "checksum": float(np.abs(dev_out.astype(np.float64)).sum()), "parity": parity,
             "comm_ms_per_step": None if comm is None else {"allgather_lambda": comm[0], "product_incl_pack": comm[1],
                                                             "reduce_partials": comm[2],
                                                             "note": "CUDA events per step, max over ranks; a rank that "
@@ -322,11 +396,11 @@ def run_ours(args):
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "clocks": head["clocks"], "cpu_baseline": cpu, "comm_ms_per_step": head["comm_ms_per_step"],
-            "bd_step": bd,
+            "parity": head["parity"], "bd_step": bd,
         }
         if "double" in results and head_p == "single":
             d = results["double"]
-            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step")}
+            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step", "parity")}
         print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
@@ -384,7 +458,9 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
             times.append(dt); iters.append(int(it)); lz.append([l1.value, l2.value]); rel.append(float(rr))
         products = (int(pb.ctx.L.rbl_product_count(pb.ctx.h)) - prod0) / max(1, args.bd_steps)
         X, _ = pb.get_config()
-        out[precision] = {"seconds_per_step": float(np.mean(times)), "gmres_iterations": iters, "lanczos_iterations": lz,
+        out[precision] = {"seconds_per_step": float(np.mean(times)), "seconds_per_step_min": float(np.min(times)),
+                          "seconds_per_step_max": float(np.max(times)), "seconds_each_step": [float(t) for t in times],
+                          "gmres_iterations": iters, "lanczos_iterations": lz,
                           "gmres_tol": tol, "lanczos_tol": ltol, "gmres_max_iter": args.bd_gmres_max_iter,
                           "lanczos_max_iter": args.bd_lanczos_max_iter, "relres": rel, "mobility_products_per_step": products,
                           "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U))}
@@ -494,7 +570,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="both", choices=["both", "single", "double"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bd-steps", type=int, default=1, help="timed full BD steps after the matvec bench (0 = skip)")
+    ap.add_argument("--parity-rows", type=int, default=64,
+                    help="sampled output rows checked against the CPU oracle after the timed region, at every N (0 = off)")
+    ap.add_argument("--bd-steps", type=int, default=3, help="timed full BD steps after the matvec bench (0 = skip)")
     ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--bd-warmup", type=int, default=1, help="0: time the very first BD step (allocations included)")
     ap.add_argument("--bd-gmres-max-iter", type=int, default=200)

@@ -265,6 +265,12 @@ class PartitionedRigidBody:
         self.dist.all_gather_object(parts, np.asarray(x_local))
         return join_system(parts, self.ranges)
 
+    def get_blob_positions(self):
+        """Positions of THIS rank's blobs, (N_local, 3) (multi_body_pos, c_rigid_obj.cpp:295-300)."""
+        r = np.empty(3 * self.total_blobs, dtype=self.real)
+        self.ctx.call("rbl_blob_positions", r.ctypes.data)
+        return r.reshape(-1, 3)
+
     # -- collective operators (rank-local slices in and out) ---------------------------------
     def apply_saddle(self, x_local):
         x = self._in(x_local, self.sys_size, "x")

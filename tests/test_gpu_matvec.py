@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import CASE_NAMES, TOL, load_golden, rel_err
+from conftest import CASE_NAMES, TOL, load_golden, rel_err, check
 
 pytestmark = pytest.mark.gpu
 
@@ -44,10 +44,10 @@ def test_apply_M_matches_golden(orc, name, precision):
     out = cb.apply_M(g["lam"], g["r"])
     assert out.dtype == _dtype(precision) and out.shape == (g["lam"].size,)
     if precision == "double":
-        assert rel_err(out, g["MF"]) < TOL["double"]
+        check(rel_err(out, g["MF"]), TOL["double"])
     else:
         want = _oracle_for(orc, g["lam"], g["r"], float(g["a"]), float(g["eta"]), bool(g["wall"]), precision)
-        assert rel_err(out, want) < TOL["single"]
+        check(rel_err(out, want), TOL["single"])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -58,7 +58,7 @@ def test_apply_M_extra_free_blob(orc, precision):
     r = np.concatenate([g["r"].reshape(-1), [7.0, -3.0, 2.0]])
     F = np.concatenate([g["lam"], [0.3, -0.2, 0.9]])
     out = cb.apply_M(F, r)
-    assert rel_err(out, _oracle_for(orc, F, r, float(g["a"]), float(g["eta"]), False, precision)) < TOL[precision]
+    check(rel_err(out, _oracle_for(orc, F, r, float(g["a"]), float(g["eta"]), False, precision)), TOL[precision])
 
 
 def _random_cloud(n, wall, seed, a=0.11):
@@ -87,7 +87,7 @@ def test_ragged_sizes(orc, n, wall, precision):
     ctx.set_parameters(a, 0.01, 1.0, eta, np.zeros((1, 3)))
     ctx.set_flags(0, wall)
     out = ctx.apply_M(F, r)
-    assert rel_err(out, _oracle_for(orc, F, r, a, eta, wall, precision)) < TOL[precision]
+    check(rel_err(out, _oracle_for(orc, F, r, a, eta, wall, precision)), TOL[precision])
     ctx.close()
 
 
@@ -118,14 +118,14 @@ def test_every_kernel_variant_agrees(orc, wall, precision):
     for v in range(nv):
         ctx.call("rbl_set_matvec_variant", v)
         out = ctx.apply_M(F, r)
-        assert rel_err(out, want) < TOL[precision], v
+        check(rel_err(out, want), TOL[precision])
         assert np.array_equal(ctx.apply_M(F, r), out), v  # bit-reproducible
     ctx.call("rbl_set_matvec_mode", 0)  # symmetric kernel
     ns = ctx.L.rbl_num_sym_variants(ctx.h)
     assert ns >= 2
     for v in range(ns):
         ctx.call("rbl_set_sym_variant", v)
-        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], ("sym", v)
+        check(rel_err(ctx.apply_M(F, r), want), TOL[precision])
     ctx.close()
 
 
@@ -151,7 +151,7 @@ def test_both_kernels_on_a_suspension(orc, mode, precision):
     want = _oracle_for(orc, F, r, s["a"], 1.0, True, precision)
     for v in range(ctx.L.rbl_num_sym_variants(ctx.h) if mode == 0 else ctx.L.rbl_num_matvec_variants(ctx.h)):
         ctx.call("rbl_set_sym_variant" if mode == 0 else "rbl_set_matvec_variant", v)
-        assert rel_err(ctx.apply_M(F, r), want) < TOL[precision], (mode, v)
+        check(rel_err(ctx.apply_M(F, r), want), TOL[precision])
     ctx.close()
 
 
@@ -180,7 +180,7 @@ def test_partial_products_sum_to_the_product(orc, n_parts, precision):
         ctx.call("rbl_sync")
         total += part
     want = _oracle_for(orc, F, r, a, eta, True, precision)
-    assert rel_err(total.cpu().numpy(), want) < TOL[precision]
+    check(rel_err(total.cpu().numpy(), want), TOL[precision])
     ctx.close()
 
 
@@ -195,7 +195,7 @@ def test_suspension_10k_blobs_full_oracle(orc, precision):
     r = cb.get_blob_positions()
     F = np.random.default_rng(2).standard_normal(r.size)
     out = cb.apply_M(F, r)
-    assert rel_err(out, _oracle_for(orc, F, r, s["a"], 1.0, True, precision)) < TOL[precision]
+    check(rel_err(out, _oracle_for(orc, F, r, s["a"], 1.0, True, precision)), TOL[precision])
 
 
 @pytest.fixture(scope="module")
@@ -226,7 +226,7 @@ def test_full_size_sampled_rows_and_properties(orc, config2, precision):
     rows[:3] = [0, 161999, 81000]
     want = _oracle_for(orc, F1, r, s["a"], 1.0, True, precision, rows=rows)
     got = u1.reshape(-1, 3)[rows].reshape(-1)
-    assert rel_err(got, want) < TOL[precision]
+    check(rel_err(got, want), TOL[precision])
     sym = abs(np.dot(F2.astype(np.float64), u1.astype(np.float64)) - np.dot(F1.astype(np.float64), u2.astype(np.float64)))
     scale = np.linalg.norm(F2) * np.linalg.norm(u1)
     assert sym / scale < (1e-12 if precision == "double" else 2e-6)
@@ -237,7 +237,7 @@ def test_full_size_sampled_rows_and_properties(orc, config2, precision):
     # the default (symmetric) kernel accumulates with floating-point atomics: reproducible to
     # rounding; the ordered kernel is bit-reproducible
     again = cb.apply_M(F1, r)
-    assert rel_err(again, u1) < (1e-14 if precision == "double" else 2e-6)
+    check(rel_err(again, u1), (1e-14 if precision == "double" else 2e-6))
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -273,8 +273,8 @@ def test_sharded_target_ranges_tile_the_full_product(orc, precision):
     ctx.call("rbl_sync")
     got = torch.cat(parts).cpu().numpy()
     want = _oracle_for(orc, F.cpu().numpy(), r.cpu().numpy(), s["a"], 1.0, True, precision)
-    assert rel_err(got, want) < TOL[precision]
-    assert rel_err(full.cpu().numpy(), want) < TOL[precision]
+    check(rel_err(got, want), TOL[precision])
+    check(rel_err(full.cpu().numpy(), want), TOL[precision])
     ctx.close()
 
 
@@ -299,39 +299,70 @@ def test_blob_below_wall_raises(precision):
     assert np.linalg.norm(cb.apply_M(vec[:36], cb.get_blob_positions())) > 0
 
 
-def test_config4_scale_free_space_sampled_rows(orc):
-    """BASELINE.json configs[3] geometry: 1000 spheres of shell_N_2562 = 2 562 000 blobs in free
-    space (6.6e12 ordered pairs), float: 64 sampled rows against the oracle + symmetry of the
-    whole product.  Exercises the 64-bit index paths of the tile triangle at full size."""
+def _full_size_sampled_rows(orc, bodies, shell, wall, precision, n_rows=64, symmetry=True):
+    """One product at a BASELINE.json configuration's full size through the device-pointer C ABI:
+    `n_rows` sampled target rows (first, last, seeded random) against the oracle, and -- with a second
+    product -- the symmetry <F2, M F1> = <F1, M F2> of the whole vector."""
+    import torch
+
     from rigid_body_light_b200._lib import Context
     from rigid_body_light_b200.shells import sphere_suspension
 
-    import torch
-
-    s = sphere_suspension(1000, 2562, False)
+    s = sphere_suspension(bodies, shell, wall)
     ref = s["cfg"] - s["cfg"].mean(axis=0)
-    ctx = Context("single")
+    ndt = _dtype(precision)
+    tdt = torch.float64 if precision == "double" else torch.float32
+    ctx = Context(precision)
     ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
-    ctx.set_flags(0, 0)
+    ctx.set_flags(0, int(wall))
     ctx.set_config(s["X"], s["Q"])
-    n = 2562000
-    r = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    n = bodies * shell
+    r = torch.empty(3 * n, dtype=tdt, device="cuda")
     ctx.call("rbl_dev_blob_positions", r.data_ptr())
     rng = np.random.default_rng(2)
-    F1 = torch.from_numpy(rng.standard_normal(3 * n).astype(np.float32)).cuda()
-    F2 = torch.from_numpy(rng.standard_normal(3 * n).astype(np.float32)).cuda()
-    u1, u2 = torch.empty_like(F1), torch.empty_like(F1)
+    F1 = torch.from_numpy(rng.standard_normal(3 * n).astype(ndt)).cuda()
+    u1 = torch.empty_like(F1)
     ctx.call("rbl_dev_apply_M", F1.data_ptr(), r.data_ptr(), n, 0, n, u1.data_ptr())
-    ctx.call("rbl_dev_apply_M", F2.data_ptr(), r.data_ptr(), n, 0, n, u2.data_ptr())
     ctx.call("rbl_sync")
-    rows = np.random.default_rng(5).choice(n, 64, replace=False)
+    rows = np.random.default_rng(5).choice(n, n_rows, replace=False)
     rows[:2] = [0, n - 1]
-    want = _oracle_for(orc, F1.cpu().numpy(), r.cpu().numpy(), s["a"], 1.0, False, "single", rows=rows)
+    want = _oracle_for(orc, F1.cpu().numpy(), r.cpu().numpy(), s["a"], 1.0, wall, precision, rows=rows)
     got = u1.cpu().numpy().reshape(-1, 3)[rows].reshape(-1)
-    assert rel_err(got, want) < TOL["single"]
-    sym = abs(float(torch.dot(F2.double(), u1.double()) - torch.dot(F1.double(), u2.double())))
-    assert sym / float(F2.double().norm() * u1.double().norm()) < 2e-6
+    err = rel_err(got, want)
+    msg = f"[{bodies} x shell_N_{shell}, wall={wall}, {precision}] sampled-row error {err:.3e}"
+    if symmetry:
+        F2 = torch.from_numpy(rng.standard_normal(3 * n).astype(ndt)).cuda()
+        u2 = torch.empty_like(F1)
+        ctx.call("rbl_dev_apply_M", F2.data_ptr(), r.data_ptr(), n, 0, n, u2.data_ptr())
+        ctx.call("rbl_sync")
+        sym = abs(float(torch.dot(F2.double(), u1.double()) - torch.dot(F1.double(), u2.double())))
+        sym /= float(F2.double().norm() * u1.double().norm())
+        msg += f"  symmetry {sym:.3e}"
+        assert sym < (1e-12 if precision == "double" else 2e-6), msg
+    print(msg)
+    assert err < TOL[precision], msg
     ctx.close()
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_config3_scale_wall_sampled_rows(orc, precision):
+    """BASELINE.json configs[2] geometry: 4096 spheres of shell_N_42 above the wall = 172 032 blobs."""
+    _full_size_sampled_rows(orc, 4096, 42, True, precision)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_config4_scale_free_space_sampled_rows(orc, precision):
+    """BASELINE.json configs[3] geometry: 1000 spheres of shell_N_2562 = 2 562 000 blobs in free
+    space (6.6e12 ordered pairs), float and double: 64 sampled rows against the oracle + symmetry of
+    the whole product.  Exercises the 64-bit index paths of the tile triangle at full size."""
+    _full_size_sampled_rows(orc, 1000, 2562, False, precision)
+
+
+def test_config5_scale_wall_sampled_rows(orc):
+    """BASELINE.json configs[4] geometry: 10 000 spheres of shell_N_642 = 6 420 000 blobs above the
+    wall (4.1e13 ordered pairs, ~70 s on one B200 in float): the wall kernel with 64-bit triangle
+    indices.  One product, 64 sampled rows against the oracle (slow, but part of the gate)."""
+    _full_size_sampled_rows(orc, 10000, 642, True, "single", symmetry=False)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -350,8 +381,8 @@ def test_apply_M_against_the_reference_members_golden(wall, precision):
     ctx.set_flags(0, wall)
     out = ctx.apply_M(F, r)
     if precision == "double":
-        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]) < TOL["double"]
+        check(rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]), TOL["double"])
     else:  # the float reference accumulates 771-term sums in float itself: compare at its own accuracy
-        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]) < TOL["single"]
-        assert rel_err(out, ref[f"cloud/wall{int(wall)}/f32"]) < TOL["single"]
+        check(rel_err(out, ref[f"cloud/wall{int(wall)}/f64"]), TOL["single"])
+        check(rel_err(out, ref[f"cloud/wall{int(wall)}/f32"]), TOL["single"])
     ctx.close()

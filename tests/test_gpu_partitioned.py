@@ -1,7 +1,8 @@
 """Partitioned suspensions (NCCL inside librbl, include/rbl.h `rbl_comm_init`): the collective
 saddle operator, GMRES, Lanczos and the BD step on rank-local slices must agree with one
 context holding the whole suspension.  World size 1 runs on any GPU box (the full NCCL code
-path with a single rank); world sizes 2 and 3 (uneven body ranges) need that many GPUs."""
+path with a single rank); world sizes 2, 3, 4 and 8 (uneven body ranges) need that many GPUs.  The
+worker also compares the partitioned saddle operator with the CPU oracle, and prints every observed error."""
 import os
 import subprocess
 import sys
@@ -18,15 +19,21 @@ def _run(world, n_bodies):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29000 + os.getpid() % 2000 + world), WORKER, str(n_bodies)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0 and "PARTITIONED-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    obs = [ln for ln in r.stdout.splitlines() if ln.startswith("OBS ")]
+    print("\n".join(obs))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"partitioned_world{world}.log"), "w") as fh:
+            fh.write("\n".join(obs) + "\nPARTITIONED-OK\n")
 
 
 def test_partitioned_world1_matches_single_context():
     _run(1, 4)
 
 
-@pytest.mark.parametrize("world,n_bodies", [(2, 5), (3, 7)])
+@pytest.mark.parametrize("world,n_bodies", [(2, 5), (3, 7), (4, 9), (8, 19)])
 def test_partitioned_multi_gpu_matches_single_context(world, n_bodies):
     import torch
 

@@ -3,7 +3,7 @@ the integrator and the Krylov drivers with the oracle / golden fixtures (-m gpu)
 import numpy as np
 import pytest
 
-from conftest import CASE_NAMES, TOL, load_golden, rel_err
+from conftest import CASE_NAMES, TOL, load_golden, rel_err, check
 
 pytestmark = pytest.mark.gpu
 PRECISIONS = ["double", "single"]
@@ -27,15 +27,16 @@ def test_config_positions_K_KT_Kinv(name, precision):
     cb = _solver(g, precision)
     X, Q = cb.get_config()
     assert X.shape == g["X"].shape and Q.shape == g["Q"].shape
-    assert np.allclose(X, g["X"], rtol=1e-6) and rel_err(Q, g["Qn"]) < TOL_ON[precision]
-    assert rel_err(cb.get_blob_positions(), g["r"]) < TOL_ON[precision]
+    assert np.allclose(X, g["X"], rtol=1e-6)
+    check(rel_err(Q, g["Qn"]), TOL_ON[precision])
+    check(rel_err(cb.get_blob_positions(), g["r"]), TOL_ON[precision])
     assert cb.get_blob_positions().shape == g["r"].shape
-    assert rel_err(cb.K_dot(g["U"]), g["KU"]) < TOL_ON[precision]
-    assert rel_err(cb.KT_dot(g["lam"]), g["KTlam"]) < TOL_ON[precision]
+    check(rel_err(cb.K_dot(g["U"]), g["KU"]), TOL_ON[precision])
+    check(rel_err(cb.KT_dot(g["lam"]), g["KTlam"]), TOL_ON[precision])
     assert cb.K_dot(g["U"].reshape(-1, 3)).shape == g["r"].shape
     assert cb.KT_dot(g["lam"]).shape == (2 * g["X"].shape[0], 3)
-    assert rel_err(cb.Kinv_dot(g["lam"]), g["Kinv_lam"]) < 10 * TOL_ON[precision]
-    assert rel_err(cb.KTinv_dot(g["U"]), g["KinvT_U"]) < 10 * TOL_ON[precision]
+    check(rel_err(cb.Kinv_dot(g["lam"]), g["Kinv_lam"]), 10 * TOL_ON[precision])
+    check(rel_err(cb.KTinv_dot(g["U"]), g["KinvT_U"]), 10 * TOL_ON[precision])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -50,9 +51,9 @@ def test_sparse_K_and_Kinv_exports(name, precision):
     K, Kinv = cb.get_K(), cb.get_Kinv()
     n3, n6 = g["r"].size, 6 * g["X"].shape[0]
     assert sp.issparse(K) and K.shape == (n3, n6) and Kinv.shape == (n6, n3)
-    assert rel_err(K @ g["U"], g["KU"]) < TOL_ON[precision]
-    assert rel_err(K.T @ g["lam"], g["KTlam"]) < TOL_ON[precision]
-    assert rel_err(Kinv @ g["lam"], g["Kinv_lam"]) < 10 * TOL_ON[precision]
+    check(rel_err(K @ g["U"], g["KU"]), TOL_ON[precision])
+    check(rel_err(K.T @ g["lam"], g["KTlam"]), TOL_ON[precision])
+    check(rel_err(Kinv @ g["lam"], g["Kinv_lam"]), 10 * TOL_ON[precision])
     assert np.abs((Kinv @ K).toarray() - np.eye(n6)).max() < (1e-11 if precision == "double" else 1e-4)
 
 
@@ -64,14 +65,14 @@ def test_fused_saddle_matches_golden_and_composition(orc, name, precision):
     out = cb.apply_saddle(g["vec"])
     n3 = g["r"].size
     if precision == "double":
-        assert rel_err(out, g["saddle"]) < TOL["double"]
+        check(rel_err(out, g["saddle"]), TOL["double"])
     else:
-        assert rel_err(out, g["saddle"]) < 5 * TOL["single"]
+        check(rel_err(out, g["saddle"]), 5 * TOL["single"])
     # the reference composes it in Python (Rigid.py:73-80); same numbers
     lam, U = g["vec"][:n3], g["vec"][n3:]
     slip = cb.apply_M(lam, cb.get_blob_positions()) - cb.K_dot(U).reshape(-1)
     comp = np.concatenate([slip, cb.KT_dot(lam).reshape(-1)])
-    assert rel_err(out, comp) < (1e-14 if precision == "double" else 1e-6)
+    check(rel_err(out, comp), (1e-14 if precision == "double" else 1e-6))
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -82,7 +83,7 @@ def test_apply_PC_matches_golden(name, block, precision):
     cb = _solver(g, precision, block=block)
     out = cb.apply_PC(g["vec"])
     assert out.shape == g["vec"].shape
-    assert rel_err(out, g["pc_block" if block else "pc_diag"]) < TOL_PC[precision]
+    check(rel_err(out, g["pc_block" if block else "pc_diag"]), TOL_PC[precision])
     # second call re-uses the built factorisation (PC_mat_Set, c_rigid_obj.cpp:591-596)
     assert np.array_equal(cb.apply_PC(g["vec"]), out)
 
@@ -99,7 +100,7 @@ def test_pc_inverts_its_saddle_matrix_on_device(orc, block):
     ref = orc.remove_mean(s["cfg"])
     pc = orc.PC(s["X"], s["Q"], ref, s["a"], 1.0, False, block)
     vec = np.random.default_rng(1).standard_normal(3 * 27 * 42 + 6 * 27)
-    assert rel_err(cb.apply_PC(vec), pc.apply(vec)) < TOL_PC["double"]
+    check(rel_err(cb.apply_PC(vec), pc.apply(vec)), TOL_PC["double"])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -109,14 +110,15 @@ def test_evolve_matches_oracle_and_invalidates_pc(orc, precision):
     before = cb.apply_PC(g["vec"])
     cb.evolve_rigid_bodies(g["U"])
     X, Q = cb.get_config()
-    assert rel_err(X, g["X_evolved"]) < TOL_ON[precision] and rel_err(Q, g["Q_evolved"]) < TOL_ON[precision]
+    check(rel_err(X, g["X_evolved"]), TOL_ON[precision])
+    check(rel_err(Q, g["Q_evolved"]), TOL_ON[precision])
     ref = orc.remove_mean(g["cfg"])
     r = orc.blob_positions(g["X_evolved"], g["Q_evolved"], ref)
-    assert rel_err(cb.get_blob_positions(), r) < TOL_ON[precision]
-    assert rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r, g["X_evolved"], ref.shape[0])) < TOL_ON[precision]
+    check(rel_err(cb.get_blob_positions(), r), TOL_ON[precision])
+    check(rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r, g["X_evolved"], ref.shape[0])), TOL_ON[precision])
     after = cb.apply_PC(g["vec"])  # rebuilt for the new configuration (:877)
     want = orc.PC(g["X_evolved"], g["Q_evolved"], ref, float(g["a"]), float(g["eta"]), True, False).apply(g["vec"])
-    assert rel_err(after, want) < TOL_PC[precision]
+    check(rel_err(after, want), TOL_PC[precision])
     assert not np.array_equal(before, after)
 
 
@@ -139,14 +141,14 @@ def test_gmres_solves_the_saddle_system(orc, name, block):
     rhs = g["vec"]
     x, iters, relres = cb.gmres(rhs, tol=1e-10, restart=80, max_iter=400)
     assert relres <= 1e-10 and 0 < iters < 400
-    assert rel_err(cb.apply_saddle(x), rhs) < 1e-9
+    check(rel_err(cb.apply_saddle(x), rhs), 1e-9)
     # dense oracle solve of [M -K; K^T 0] x = rhs
     a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
     M = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
     K = orc.K_dense(g["r"], g["X"], g["cfg"].shape[0])
     n3, n6 = M.shape[0], K.shape[1]
     A = np.block([[M, -K], [K.T, np.zeros((n6, n6))]])
-    assert rel_err(x, np.linalg.solve(A, rhs)) < 1e-7
+    check(rel_err(x, np.linalg.solve(A, rhs)), 1e-7)
 
 
 def test_gmres_single_precision_converges(orc):
@@ -154,7 +156,7 @@ def test_gmres_single_precision_converges(orc):
     cb = _solver(g, "single", block=True)
     x, iters, relres = cb.gmres(g["vec"], tol=1e-4, restart=60, max_iter=200)
     assert relres <= 1e-4
-    assert rel_err(cb.apply_saddle(x), g["vec"]) < 1e-3
+    check(rel_err(cb.apply_saddle(x), g["vec"]), 1e-3)
 
 
 @pytest.mark.parametrize("name", ["case_touch_wall", "case_overlap_free"])
@@ -174,7 +176,7 @@ def test_lanczos_sqrt_matches_dense_sqrtm(orc, name):
     W = np.random.default_rng(9).standard_normal(M.shape[0])
     out, iters = cb.brownian_sqrt(W, tol=1e-10, max_iter=150)
     want = np.real(sqrtm(M)) @ W
-    assert rel_err(out, want) < 1e-7
+    check(rel_err(out, want), 1e-7)
     assert 1 < iters <= 150
 
 
@@ -209,9 +211,10 @@ def test_bd_step_deterministic(orc, name):
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.0,
                              bool(g["wall"]), F, slip, None, None, None)
     assert relres <= 1e-11
-    assert rel_err(U, Uo) < 1e-8
+    check(rel_err(U, Uo), 1e-8)
     X, Q = cb.get_config()
-    assert rel_err(X, Xo) < 1e-10 and rel_err(Q, Qo) < 1e-10
+    check(rel_err(X, Xo), 1e-10)
+    check(rel_err(Q, Qo), 1e-10)
 
 
 @pytest.mark.parametrize("name", ["case_touch_wall", "case_touch_free"])
@@ -231,12 +234,13 @@ def test_bd_step_brownian_given_noise(orc, name):
     ref = orc.remove_mean(g["cfg"])
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), kBT,
                              bool(g["wall"]), F, None, *noise, noise="block_cholesky")  # the default noise of bd_step
-    assert rel_err(U, Uo) < 1e-6
+    check(rel_err(U, Uo), 1e-6)
     X, Q = cb.get_config()
-    assert rel_err(X, Xo) < 1e-8 and rel_err(Q, Qo) < 1e-8
+    check(rel_err(X, Xo), 1e-8)
+    check(rel_err(Q, Qo), 1e-8)
     # the context is back on a consistent configuration: K matches the evolved positions
     r_new = orc.blob_positions(Xo, Qo, ref)
-    assert rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r_new, Xo, ref.shape[0])) < 1e-8
+    check(rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r_new, Xo, ref.shape[0])), 1e-8)
 
 
 def test_bd_step_needs_noise_when_brownian():
@@ -264,9 +268,10 @@ def test_bd_step_symmetric_square_root_noise(orc, name):
     ref = orc.remove_mean(g["cfg"])
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.004,
                              bool(g["wall"]), F, None, *noise)
-    assert rel_err(U, Uo) < 1e-6
+    check(rel_err(U, Uo), 1e-6)
     X, Q = cb.get_config()
-    assert rel_err(X, Xo) < 1e-8 and rel_err(Q, Qo) < 1e-8
+    check(rel_err(X, Xo), 1e-8)
+    check(rel_err(Q, Qo), 1e-8)
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -296,15 +301,15 @@ def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, na
     lim = 1e-7 if precision == "double" else 2e-3
     if spd:
         want = orc.noise_block_cholesky(orc.noise_factors(g["r"], g["Qn"], orc.remove_mean(g["cfg"]), a, eta, wall), A, W)
-        assert rel_err(out, want) < lim
+        check(rel_err(out, want), lim)
         assert iters < ref_iters  # the point of the exercise
     else:  # body blocks not positive definite (blobs in the wall-overlap layer): plain recurrence
-        assert rel_err(out, ref_out) < lim
+        check(rel_err(out, ref_out), lim)
     # (case_near_wall has blobs inside the wall-overlap layer: B M B itself is indefinite there,
     # min eigenvalue -0.17, so no square root exists -- the reference's Cholesky would fail too)
     if precision == "double" and A.shape[0] <= 400 and np.linalg.eigvalsh(A).min() > 0:
         S = np.stack([cb.brownian_sqrt(e, tol=1e-12, max_iter=200)[0] for e in np.eye(A.shape[0])], axis=1)
-        assert np.linalg.norm(S @ S.T - A) / np.linalg.norm(A) < 1e-8
+        check(np.linalg.norm(S @ S.T - A) / np.linalg.norm(A), 1e-8)
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -341,14 +346,15 @@ def test_bd_step_matches_the_committed_golden_step(name, mode):
     key = f"{name}/{'block_cholesky' if mode else 'symmetric'}"
     U, iters, relres = cb.bd_step(bd[f"{name}/F"], kBT=float(bd[f"{name}/kBT"]), noise=tuple(bd[f"{name}/W"]), tol=1e-11,
                                   restart=100, max_iter=400, lanczos_tol=1e-12, lanczos_max_iter=200)
-    assert rel_err(U, bd[key + "/U"]) < 1e-6
+    check(rel_err(U, bd[key + "/U"]), 1e-6)
     X, Q = cb.get_config()
-    assert rel_err(X, bd[key + "/X"]) < 1e-8 and rel_err(Q, bd[key + "/Q"]) < 1e-8
+    check(rel_err(X, bd[key + "/X"]), 1e-8)
+    check(rel_err(Q, bd[key + "/Q"]), 1e-8)
     # and the Brownian increment itself
     cb2 = _solver(g, "double")
     cb2.set_noise_preconditioner(2 if mode else 0)
     y, _ = cb2.brownian_sqrt(bd[f"{name}/W"][0], tol=1e-12, max_iter=200)
-    assert rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]) < 1e-7
+    check(rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]), 1e-7)
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -375,8 +381,8 @@ def test_seeded_bd_step_equals_the_step_with_the_same_noise(orc, name):
     Ua, _, _ = a.bd_step(F, kBT=0.004, seed=77, step=12, **kw)
     b = _solver(g, "double", block=True)
     Ub, _, _ = b.bd_step(F, kBT=0.004, noise=orc.philox_normals(77, 12, 0, n3), **kw)
-    assert rel_err(Ua, Ub) < 1e-9
-    assert rel_err(a.get_config()[0], b.get_config()[0]) < 1e-12
+    check(rel_err(Ua, Ub), 1e-9)
+    check(rel_err(a.get_config()[0], b.get_config()[0]), 1e-12)
     c = _solver(g, "double", block=True)
     Uc, _, _ = c.bd_step(F, kBT=0.004, seed=77, step=13, **kw)  # another step number: other noise
     assert rel_err(Uc, Ua) > 1e-3
@@ -392,19 +398,20 @@ def test_cuda_path_against_the_reference_members_golden(name, precision):
     want = lambda key: ref[f"{name}/f64/{key}"]  # noqa: E731
     cb = _solver(g, precision)
     X, Q = cb.get_config()
-    assert rel_err(Q, want("Qn")) < TOL_ON[precision]
-    assert rel_err(cb.get_blob_positions(), want("r")) < TOL_ON[precision]
-    assert rel_err(cb.K_dot(g["U"]), want("KU")) < TOL_ON[precision]
-    assert rel_err(cb.KT_dot(g["lam"]), want("KTlam")) < TOL_ON[precision]
-    assert rel_err(cb.Kinv_dot(g["lam"]), want("Kinv_lam")) < 10 * TOL_ON[precision]
-    assert rel_err(cb.KTinv_dot(g["U"]), want("KinvT_U")) < 10 * TOL_ON[precision]
+    check(rel_err(Q, want("Qn")), TOL_ON[precision])
+    check(rel_err(cb.get_blob_positions(), want("r")), TOL_ON[precision])
+    check(rel_err(cb.K_dot(g["U"]), want("KU")), TOL_ON[precision])
+    check(rel_err(cb.KT_dot(g["lam"]), want("KTlam")), TOL_ON[precision])
+    check(rel_err(cb.Kinv_dot(g["lam"]), want("Kinv_lam")), 10 * TOL_ON[precision])
+    check(rel_err(cb.KTinv_dot(g["U"]), want("KinvT_U")), 10 * TOL_ON[precision])
     if np.isfinite(want("pc_diag")).all():
         for blk, key in ((False, "pc_diag"), (True, "pc_block")):
-            assert rel_err(_solver(g, precision, block=blk).apply_PC(g["vec"]), want(key)) < TOL_PC[precision], key
+            check(rel_err(_solver(g, precision, block=blk).apply_PC(g["vec"]), want(key)), TOL_PC[precision])
     cb.evolve_rigid_bodies(g["U"])
     Xe, Qe = cb.get_config()
-    assert rel_err(Xe, want("X_evolved")) < TOL_ON[precision] and rel_err(Qe, want("Q_evolved")) < TOL_ON[precision]
-    assert rel_err(cb.K_dot(g["U"]), want("KU_evolved")) < 2 * TOL_ON[precision]
+    check(rel_err(Xe, want("X_evolved")), TOL_ON[precision])
+    check(rel_err(Qe, want("Q_evolved")), TOL_ON[precision])
+    check(rel_err(cb.K_dot(g["U"]), want("KU_evolved")), 2 * TOL_ON[precision])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -428,17 +435,20 @@ def test_cuda_path_against_the_live_reference_members(orc, wall, precision):
     n3, n6 = 3 * 30 * 42, 180
     lam, U, vec = rng.standard_normal(n3).astype(ndt), rng.standard_normal(n6).astype(ndt), rng.standard_normal(n3 + n6).astype(ndt)
     tol_on, tol_m, tol_pc = TOL_ON[precision], TOL[precision], TOL_PC[precision]
-    assert rel_err(cb.get_config()[1], rb.get_config()[1]) < tol_on
+    check(rel_err(cb.get_config()[1], rb.get_config()[1]), tol_on)
     r = cb.get_blob_positions()
-    assert rel_err(r, rb.positions()) < tol_on
-    assert rel_err(cb.K_dot(U), rb.K_dot(U)) < tol_on and rel_err(cb.KT_dot(lam), rb.KT_dot(lam)) < tol_on
-    assert rel_err(cb.Kinv_dot(lam), rb.Kinv_dot(lam)) < 10 * tol_on and rel_err(cb.KTinv_dot(U), rb.KTinv_dot(U)) < 10 * tol_on
+    check(rel_err(r, rb.positions()), tol_on)
+    check(rel_err(cb.K_dot(U), rb.K_dot(U)), tol_on)
+    check(rel_err(cb.KT_dot(lam), rb.KT_dot(lam)), tol_on)
+    check(rel_err(cb.Kinv_dot(lam), rb.Kinv_dot(lam)), 10 * tol_on)
+    check(rel_err(cb.KTinv_dot(U), rb.KTinv_dot(U)), 10 * tol_on)
     rr = rb.positions()
-    assert rel_err(cb.apply_M(lam, rr), rb.apply_M(lam, rr)) < tol_m
+    check(rel_err(cb.apply_M(lam, rr), rb.apply_M(lam, rr)), tol_m)
     ref_saddle = np.concatenate([rb.apply_M(vec[:n3], rr) - rb.K_dot(vec[n3:]), rb.KT_dot(vec[:n3])])  # Rigid.py:73-80
-    assert rel_err(cb.apply_saddle(vec), ref_saddle) < 10 * tol_m
-    assert rel_err(cb.apply_PC(vec), rb.apply_PC(vec)) < tol_pc
+    check(rel_err(cb.apply_saddle(vec), ref_saddle), 10 * tol_m)
+    check(rel_err(cb.apply_PC(vec), rb.apply_PC(vec)), tol_pc)
     cb.evolve_rigid_bodies(U)
     rb.evolve(U)
-    assert rel_err(cb.get_config()[0], rb.get_config()[0]) < tol_on and rel_err(cb.get_config()[1], rb.get_config()[1]) < tol_on
-    assert rel_err(cb.get_blob_positions(), rb.positions()) < 2 * tol_on
+    check(rel_err(cb.get_config()[0], rb.get_config()[0]), tol_on)
+    check(rel_err(cb.get_config()[1], rb.get_config()[1]), tol_on)
+    check(rel_err(cb.get_blob_positions(), rb.positions()), 2 * tol_on)

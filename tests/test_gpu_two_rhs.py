@@ -5,7 +5,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import CASE_NAMES, TOL, load_golden, rel_err
+from conftest import CASE_NAMES, TOL, load_golden, rel_err, check
 from test_gpu_matvec import _dtype, _oracle_for, _random_cloud, _solver
 
 pytestmark = pytest.mark.gpu
@@ -28,8 +28,8 @@ def test_apply_M2_matches_oracle_on_golden_cases(orc, name, precision):
     o1, o2 = cb.apply_M2(g["lam"], F2, g["r"])
     assert o1.dtype == _dtype(precision)
     a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
-    assert rel_err(o1, _oracle_for(orc, g["lam"], g["r"], a, eta, wall, precision)) < TOL[precision]
-    assert rel_err(o2, _oracle_for(orc, F2, g["r"], a, eta, wall, precision)) < TOL[precision]
+    check(rel_err(o1, _oracle_for(orc, g["lam"], g["r"], a, eta, wall, precision)), TOL[precision])
+    check(rel_err(o2, _oracle_for(orc, F2, g["r"], a, eta, wall, precision)), TOL[precision])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -51,7 +51,8 @@ def test_apply_M2_ragged_sizes_and_variants(orc, n, wall, precision):
     for v in [-1] + list(range(nv)):
         ctx.call("rbl_set_sym2_variant", v)
         o1, o2 = _apply_M2(ctx, F1, F2, r)
-        assert rel_err(o1, w1) < TOL[precision] and rel_err(o2, w2) < TOL[precision], v
+        check(rel_err(o1, w1), TOL[precision])
+        check(rel_err(o2, w2), TOL[precision])
     ctx.close()
 
 
@@ -69,10 +70,11 @@ def test_apply_M2_equals_two_single_products_on_a_suspension(orc, precision):
     F1, F2 = rng.standard_normal(r.size), rng.standard_normal(r.size)
     o1, o2 = cb.apply_M2(F1, F2, r)
     tol = 1e-13 if precision == "double" else 5e-6
-    assert rel_err(o1, cb.apply_M(F1, r)) < tol and rel_err(o2, cb.apply_M(F2, r)) < tol
+    check(rel_err(o1, cb.apply_M(F1, r)), tol)
+    check(rel_err(o2, cb.apply_M(F2, r)), tol)
     rows = np.random.default_rng(4).choice(r.shape[0], 64, replace=False)
     want = _oracle_for(orc, F2, r, s["a"], 1.0, True, precision, rows=rows)
-    assert rel_err(o2.reshape(-1, 3)[rows], want) < TOL[precision]
+    check(rel_err(o2.reshape(-1, 3)[rows], want), TOL[precision])
 
 
 def test_blob_below_wall_raises_in_the_two_rhs_product():
@@ -101,11 +103,14 @@ def test_paired_lanczos_equals_two_single_runs(name, precision):
     s1, j1 = cb.brownian_sqrt(W1, tol=tol, max_iter=150)
     s2, j2 = cb.brownian_sqrt(W2, tol=tol, max_iter=150)
     lim = 1e-9 if precision == "double" else 2e-4
-    assert rel_err(y1, s1) < lim and rel_err(y2, s2) < lim
+    check(rel_err(y1, s1), lim)
+    check(rel_err(y2, s2), lim)
     assert abs(k1 - j1) <= 1 and abs(k2 - j2) <= 1
     # one vector zero: that recurrence is skipped, the other is unaffected
     z1, z2, m1, m2 = cb.brownian_sqrt_pair(np.zeros(n), W2, tol=tol, max_iter=150)
-    assert m1 == 0 and not z1.any() and rel_err(z2, s2) < lim
+    assert m1 == 0
+    assert not z1.any()
+    check(rel_err(z2, s2), lim)
 
 
 def test_bd_step_paired_and_unpaired_lanczos_agree():
@@ -124,8 +129,8 @@ def test_bd_step_paired_and_unpaired_lanczos_agree():
         U, it, rr = cb.bd_step(F, kBT=0.004, noise=noise, tol=1e-11, restart=100, max_iter=400, lanczos_tol=1e-12,
                                lanczos_max_iter=200)
         out.append((U, cb.get_config()))
-    assert rel_err(out[0][0], out[1][0]) < 1e-9
-    assert rel_err(out[0][1][0], out[1][1][0]) < 1e-11
+    check(rel_err(out[0][0], out[1][0]), 1e-9)
+    check(rel_err(out[0][1][0], out[1][1][0]), 1e-11)
 
 
 def test_full_size_krylov_properties_config3():
@@ -146,10 +151,13 @@ def test_full_size_krylov_properties_config3():
     z1, z2, _, _ = cb.brownian_sqrt_pair(y1, y2, tol=1e-5, max_iter=80)
     r = cb.get_blob_positions()
     m1, m2 = cb.apply_M2(W1, W2, r)
-    assert rel_err(z1, m1) < 2e-3 and rel_err(z2, m2) < 2e-3
+    check(rel_err(z1, m1), 2e-3)
+    check(rel_err(z2, m2), 2e-3)
     s2, s1, j2, j1 = cb.brownian_sqrt_pair(W2, W1, tol=1e-5, max_iter=80)
-    assert (j1, j2) == (k1, k2) and rel_err(s1, y1) < 1e-4 and rel_err(s2, y2) < 1e-4
+    assert (j1, j2) == (k1, k2)
+    check(rel_err(s1, y1), 1e-4)
+    check(rel_err(s2, y2), 1e-4)
     rhs = np.concatenate([np.zeros(n3), rng.standard_normal(n6)]).astype(np.float32)
     x, it, rr = cb.gmres(rhs, tol=1e-4, restart=60, max_iter=120)
     assert rr <= 1e-4 and it < 60
-    assert rel_err(cb.apply_saddle(x), rhs) < 5e-4
+    check(rel_err(cb.apply_saddle(x), rhs), 5e-4)
