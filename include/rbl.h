@@ -238,6 +238,8 @@ int rbl_set_matvec_mode(rbl_ctx* ctx, int mode);
 int rbl_num_sym_variants(const rbl_ctx* ctx);
 int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
+/* sources per warp-private reaction-reduction chunk of symmetric variant idx (0: warp butterfly) */
+int rbl_sym_variant_chunk(const rbl_ctx* ctx, int idx);
 int rbl_num_sym2_variants(const rbl_ctx* ctx);
 int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_sym2_variant(rbl_ctx* ctx, int idx); /* two-right-hand-side kernel; -1 = automatic */

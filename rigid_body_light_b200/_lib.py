@@ -94,6 +94,7 @@ SYMBOLS = {
     "rbl_num_sym_variants": (_i, [_vp]),
     "rbl_sym_variant_info": (_i, [_vp, _i, _pi, _pi]),
     "rbl_set_sym_variant": (_i, [_vp, _i]),
+    "rbl_sym_variant_chunk": (_i, [_vp, _i]),
     "rbl_launch_count": (_i64, [_vp]),
     "rbl_product_count": (_i64, [_vp]),
     "rbl_bd_stats": (_i, [_vp, _pi, _pi]),

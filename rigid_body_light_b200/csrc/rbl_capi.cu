@@ -97,6 +97,7 @@ struct rbl_ctx {
   virtual int variant_info(int idx, int* T, int* threads) const = 0;
   virtual int num_sym_variants() const = 0;
   virtual int sym_variant_info(int idx, int* T, int* threads) const = 0;
+  virtual int sym_variant_chunk(int idx) const = 0;
   virtual int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) = 0;
   virtual int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) = 0;
   virtual int comm_init(const void* uid128, int rank, int world, const int* blobs_per_rank) = 0;
@@ -1569,6 +1570,10 @@ struct Ctx final : rbl_ctx {
     *threads = v.threads;
     return RBL_OK;
   }
+  int sym_variant_chunk(int idx) const override {
+    if (idx < 0 || idx >= rbl::matvec_sym_num_variants<real>()) return -1;
+    return rbl::matvec_sym_variant<real>(idx).rc;
+  }
   int num_variants() const override { return rbl::matvec_num_variants<real>(); }
   int variant_info(int idx, int* T, int* threads) const override {
     if (idx < 0 || idx >= rbl::matvec_num_variants<real>()) return RBL_ERR_INVALID;
@@ -1874,6 +1879,7 @@ int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {
   if (!ctx || !T || !threads) return RBL_ERR_INVALID;
   return ctx->sym_variant_info(idx, T, threads);
 }
+int rbl_sym_variant_chunk(const rbl_ctx* ctx, int idx) { return ctx ? ctx->sym_variant_chunk(idx) : -1; }
 int rbl_set_sym_variant(rbl_ctx* ctx, int idx) {
   CTX_OR_FAIL(ctx);
   if (idx >= ctx->num_sym_variants()) return ctx->fail(RBL_ERR_INVALID, "no such symmetric matvec variant");

@@ -641,6 +641,95 @@ __device__ __forceinline__ void tile_compute_sym(const real* __restrict__ sb, co
   }
 }
 
+// ---- reaction sums through a warp-private shared-memory tile ---------------------------------
+// The butterfly above costs ~19.5 issue slots per source and warp (5 shuffle stages x 3 values).
+// Here every lane parks its partial reaction on source j (summed over its T targets) in row
+// (j, component) of a warp-private tile, and after RC sources the tile is read back TRANSPOSED:
+// 32 / RC lanes per source, each sums RC consecutive lane-partials with 128-bit loads and adds its
+// share to the global accumulator (RED.ADD).  3 STS per source + (3 RC/4 LDS.128 + 3 (RC-1) adds
+// + 3 RED) per RC sources  ~=  7 issue slots per source and warp, and the sum order inside the
+// warp is fixed.  Row stride: 3 * stride words = 12 (mod 32) makes the transposed 128-bit reads of
+// a quarter-warp hit 8 distinct 4-bank groups; the writes are lane-contiguous.
+template <typename real>
+struct RedLayout;
+template <>
+struct RedLayout<float> {
+  static constexpr int kStride = 36;  // 3 * 36 words = 108 = 12 (mod 32)
+};
+template <>
+struct RedLayout<double> {
+  static constexpr int kStride = 34;  // 3 * 68 words = 204 = 12 (mod 32)
+};
+template <typename real, int RC>
+__host__ __device__ constexpr size_t red_tile_reals() {
+  return RC > 0 ? (size_t)RC * 3 * RedLayout<real>::kStride : 0;
+}
+
+template <int RC>
+__device__ __forceinline__ float row_sum(const float* __restrict__ row) {
+  const float4* q = reinterpret_cast<const float4*>(row);
+  float4 v = q[0];
+#pragma unroll
+  for (int k = 1; k < RC / 4; ++k) {
+    const float4 w = q[k];
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  return (v.x + v.y) + (v.z + v.w);
+}
+template <int RC>
+__device__ __forceinline__ double row_sum(const double* __restrict__ row) {
+  const double2* q = reinterpret_cast<const double2*>(row);
+  double2 v = q[0], u = q[1];
+#pragma unroll
+  for (int k = 1; k < RC / 4; ++k) {
+    const double2 w0 = q[2 * k], w1 = q[2 * k + 1];
+    v.x += w0.x; v.y += w0.y; u.x += w1.x; u.y += w1.y;
+  }
+  return (v.x + v.y) + (u.x + u.y);
+}
+
+template <typename real, bool WALL, bool NEAR, int T, int RC>
+__device__ __forceinline__ void tile_compute_symt(const real* __restrict__ sb, const PairConsts<real>& C,
+                                                  const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
+                                                  const real (&fxi)[T], const real (&fyi)[T], const real (&fzi)[T],
+                                                  const real (&nz4i)[T], real (&lx)[T], real (&ly)[T],
+                                                  real (&lz)[T], real* __restrict__ raw_tile,
+                                                  real* __restrict__ red, int jb, int je) {
+  static_assert(RC == 8 || RC == 16 || RC == 32, "reduction chunk");
+  constexpr int STR = RedLayout<real>::kStride;
+  const int lane = threadIdx.x & 31;
+  const int src = lane % RC, part = lane / RC;
+  real* __restrict__ wr = red + lane;
+  const real* __restrict__ rd = red + (size_t)(src * 3) * STR + part * RC;
+  for (int j0 = jb; j0 < je; j0 += RC) {
+#pragma unroll 1
+    for (int jj = 0; jj < RC / 2; ++jj) {
+      real xa, ya, za, fxa, fya, fza, nz4a, xb, yb, zb, fxb, fyb, fzb, nz4b;
+      load_full_rec(sb + (size_t)(j0 + jj) * kRecReals, xa, ya, za, fxa, fya, fza, nz4a);
+      load_full_rec(sb + (size_t)(j0 + jj + RC / 2) * kRecReals, xb, yb, zb, fxb, fyb, fzb, nz4b);
+      real ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xa, ya, za, fxa, fya,
+                                   fza, nz4a, lx[t], ly[t], lz[t], ax, ay, az);
+        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xb, yb, zb, fxb, fyb,
+                                   fzb, nz4b, lx[t], ly[t], lz[t], bx, by, bz);
+      }
+      real* __restrict__ wa = wr + (size_t)(jj * 3) * STR;
+      real* __restrict__ wb = wr + (size_t)((jj + RC / 2) * 3) * STR;
+      wa[0] = ax; wa[STR] = ay; wa[2 * STR] = az;
+      wb[0] = bx; wb[STR] = by; wb[2 * STR] = bz;
+    }
+    __syncwarp();
+    const real sx = row_sum<RC>(rd), sy = row_sum<RC>(rd + STR), sz = row_sum<RC>(rd + 2 * STR);
+    real* o = raw_tile + 3 * (size_t)(j0 + src);
+    atomicAdd(o, sx);
+    atomicAdd(o + 1, sy);
+    atomicAdd(o + 2, sz);
+    __syncwarp();
+  }
+}
+
 constexpr int kSymChunks = kSrcTile / 32;  // 32-source chunks per tile unit
 
 // first unit index of row I of the triangle: rows have n_src_tiles - I*diag units
@@ -648,11 +737,23 @@ __device__ __host__ __forceinline__ long long sym_row_offset(long long I, int ns
   return I * ns - (long long)diag * (I * (I - 1) / 2);
 }
 
-template <typename real, bool WALL, int T, int NT>
+// RC = 0: reaction sums by the warp butterfly (tile_compute_sym); RC = 8/16/32: through the
+// warp-private shared-memory tile (tile_compute_symt).  Target sums are flushed into the global
+// accumulators (RED.ADD) after every tile unit -- that IS the second summation level of the fp32
+// path, and it frees the 3T registers a running sum per target would hold.
+template <typename real, int T, int NT, int RC>
+__host__ __device__ constexpr size_t sym_smem_bytes() {
+  return (2 * (size_t)kSrcTile * kRecReals + (size_t)(NT / 32) * red_tile_reals<real, RC>()) * sizeof(real);
+}
+
+template <typename real, bool WALL, int T, int NT, int RC>
 __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> A) {
   constexpr int TT = T * NT;
   constexpr uint32_t kTileBytes = kSrcTile * kRecReals * sizeof(real);
-  __shared__ __align__(128) real sbuf[2][kSrcTile * kRecReals];
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  real* const sbuf0 = reinterpret_cast<real*>(smem_dyn);
+  real* const sbuf1 = sbuf0 + kSrcTile * kRecReals;
+  real* const red = sbuf1 + kSrcTile * kRecReals + (size_t)(threadIdx.x >> 5) * red_tile_reals<real, RC>();
   __shared__ __align__(8) unsigned long long mbar[2];
 
   const int tid = threadIdx.x;
@@ -687,10 +788,10 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
   int J = I * D + (int)(g0 - sym_row_offset(I, ns, D));  // source tile of the first unit
   if (tid == 0) {
     mbar_expect_tx(&mbar[0], kTileBytes);
-    tma_load_1d(sbuf[0], A.rec + (size_t)J * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
+    tma_load_1d(sbuf0, A.rec + (size_t)J * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
   }
 
-  real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], nz4i[T], ux[T], uy[T], uz[T];
+  real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], nz4i[T];
   bool fresh = true;
   const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
 
@@ -701,11 +802,13 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     const bool row_end = (J + 1 == ns);
     const int jb = (g == g0) ? jb_first : 0;
     const int je = (g == g_last) ? je_last : kSrcTile;
+    const real* cur = buf ? sbuf1 : sbuf0;
+    real* nxt = buf ? sbuf0 : sbuf1;
 
     if (tid == 0 && g + 1 < g1) {
       const int nJ = row_end ? (I + 1) * D : J + 1;
       mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
-      tma_load_1d(sbuf[buf ^ 1], A.rec + (size_t)nJ * kSrcTile * kRecReals, kTileBytes, &mbar[buf ^ 1]);
+      tma_load_1d(nxt, A.rec + (size_t)nJ * kSrcTile * kRecReals, kTileBytes, &mbar[buf ^ 1]);
     }
 
     if (fresh) {
@@ -716,7 +819,6 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
         if (pad) li = A.plan.n - 1;
         load_full_rec(A.rec + (size_t)li * kRecReals, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t]);
         if (pad) fxi[t] = fyi[t] = fzi[t] = (real)0;  // padding lanes exert nothing
-        ux[t] = uy[t] = uz[t] = (real)0;
       }
       fresh = false;
     }
@@ -724,33 +826,43 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     const bool far = box_gap2(A.box_tgt + 6 * (size_t)I, A.box_src + 6 * (size_t)J) > near2;
     const bool diagonal = J < (I + 1) * D;  // source tile lies inside this target tile: ordered
 
+    real ux[T], uy[T], uz[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ux[t] = uy[t] = uz[t] = (real)0;
+
     mbar_wait(&mbar[buf], parity);
     if (diagonal) {
-      tile_compute<WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, ux, uy, uz, jb, je);
+      tile_compute<WALL, true, T>(cur, A.C, xi, yi, zi, ux, uy, uz, jb, je);
     } else {
       real* raw_tile = A.raw + 3 * (size_t)J * kSrcTile;
-      if (far)
-        tile_compute_sym<real, WALL, false, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
-      else
-        tile_compute_sym<real, WALL, true, T>(sbuf[buf], A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
-    }
-    __syncthreads();
-
-    if (row_end || g + 1 == g1) {
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int li = I * TT + tid + t * NT;
-        if (li < A.plan.n) {
-          atomicAdd(A.raw + 3 * (size_t)li + 0, ux[t]);
-          atomicAdd(A.raw + 3 * (size_t)li + 1, uy[t]);
-          atomicAdd(A.raw + 3 * (size_t)li + 2, uz[t]);
-        }
+      if constexpr (RC == 0) {
+        if (far)
+          tile_compute_sym<real, WALL, false, T>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
+        else
+          tile_compute_sym<real, WALL, true, T>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
+      } else {
+        if (far)
+          tile_compute_symt<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, red, jb, je);
+        else
+          tile_compute_symt<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, red, jb, je);
       }
-      fresh = true;
     }
+    // flush this unit's target sums (per-tile accumulators: the first summation level)
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int li = I * TT + tid + t * NT;
+      if (li < A.plan.n) {
+        atomicAdd(A.raw + 3 * (size_t)li + 0, ux[t]);
+        atomicAdd(A.raw + 3 * (size_t)li + 1, uy[t]);
+        atomicAdd(A.raw + 3 * (size_t)li + 2, uz[t]);
+      }
+    }
+    __syncthreads();  // every thread is done with `cur` before it is refilled
+
     if (row_end) {
       ++I;
       J = I * D;
+      fresh = true;
     } else {
       ++J;
     }
@@ -768,17 +880,18 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
   A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
 }
 
-#define RBL_F32_SYM_VARIANTS(X) X(4, 256) X(6, 128) X(8, 128) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
-#define RBL_F64_SYM_VARIANTS(X) X(3, 256) X(4, 128) X(2, 256) X(2, 128) X(1, 256)
+// (T targets per thread, NT threads per CTA, RC reaction-reduction chunk; RC = 0: warp butterfly)
+#define RBL_F32_SYM_VARIANTS(X) \
+  X(4, 256, 16) X(6, 128, 16) X(4, 256, 0) X(6, 128, 0) X(4, 256, 8) X(4, 256, 32) X(6, 128, 8) X(8, 128, 16) \
+  X(5, 256, 16) X(6, 256, 16) X(4, 128, 16) X(2, 256, 8) X(1, 256, 8)
+#define RBL_F64_SYM_VARIANTS(X) \
+  X(3, 256, 16) X(4, 128, 16) X(3, 256, 0) X(4, 128, 0) X(3, 256, 8) X(4, 128, 8) X(4, 256, 16) X(2, 256, 16) \
+  X(2, 128, 8) X(1, 256, 8)
 
-template <>
-int matvec_sym_num_variants<float>() { return 7; }
-template <>
-int matvec_sym_num_variants<double>() { return 5; }
 template <>
 MatvecVariant matvec_sym_variant<float>(int idx) {
   static const MatvecVariant v[] = {
-#define X(T, NT) {T, NT},
+#define X(T, NT, RC) {T, NT, RC},
       RBL_F32_SYM_VARIANTS(X)
 #undef X
   };
@@ -787,32 +900,55 @@ MatvecVariant matvec_sym_variant<float>(int idx) {
 template <>
 MatvecVariant matvec_sym_variant<double>(int idx) {
   static const MatvecVariant v[] = {
-#define X(T, NT) {T, NT},
+#define X(T, NT, RC) {T, NT, RC},
       RBL_F64_SYM_VARIANTS(X)
 #undef X
   };
   return v[idx];
 }
-
-// measured on B200 at 162 000 blobs (profiles/): wall fp32 (4,256), fp64 (3,256); free space
-// fp32 (6,128), fp64 (4,128); small problems take the smallest target tile so that the unit
-// triangle still covers the SMs
 template <>
-int matvec_sym_default_variant<float>(bool wall, int n) { return n < 16384 ? 6 : (wall ? 0 : 1); }
+int matvec_sym_num_variants<float>() {
+  int n = 0;
+#define X(T, NT, RC) ++n;
+  RBL_F32_SYM_VARIANTS(X)
+#undef X
+  return n;
+}
 template <>
-int matvec_sym_default_variant<double>(bool wall, int n) { return n < 16384 ? 4 : (wall ? 0 : 1); }
+int matvec_sym_num_variants<double>() {
+  int n = 0;
+#define X(T, NT, RC) ++n;
+  RBL_F64_SYM_VARIANTS(X)
+#undef X
+  return n;
+}
 
-template <typename real, bool WALL, int T, int NT>
+// defaults measured on B200 (profiles/): index 0 with the wall, 1 in free space; small problems take
+// the smallest target tile (the last variant) so that the unit triangle still covers the SMs
+template <>
+int matvec_sym_default_variant<float>(bool wall, int n) {
+  return n < 16384 ? matvec_sym_num_variants<float>() - 1 : (wall ? 0 : 1);
+}
+template <>
+int matvec_sym_default_variant<double>(bool wall, int n) {
+  return n < 16384 ? matvec_sym_num_variants<double>() - 1 : (wall ? 0 : 1);
+}
+
+template <typename real, bool WALL, int T, int NT, int RC>
 static cudaError_t sym_occupancy_of(int* bps) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym_kernel<real, WALL, T, NT>, NT, 0);
+  constexpr size_t smem = sym_smem_bytes<real, T, NT, RC>();
+  cudaError_t e = cudaFuncSetAttribute(rpy_matvec_sym_kernel<real, WALL, T, NT, RC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym_kernel<real, WALL, T, NT, RC>, NT, smem);
 }
 template <typename real>
 static cudaError_t sym_variant_occupancy(int variant, bool wall, int* bps);
 template <>
 cudaError_t sym_variant_occupancy<float>(int variant, bool wall, int* bps) {
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return wall ? sym_occupancy_of<float, true, T, NT>(bps) : sym_occupancy_of<float, false, T, NT>(bps);
+#define X(T, NT, RC) \
+  if (variant == k++) return wall ? sym_occupancy_of<float, true, T, NT, RC>(bps) : sym_occupancy_of<float, false, T, NT, RC>(bps);
   RBL_F32_SYM_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -820,8 +956,8 @@ cudaError_t sym_variant_occupancy<float>(int variant, bool wall, int* bps) {
 template <>
 cudaError_t sym_variant_occupancy<double>(int variant, bool wall, int* bps) {
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return wall ? sym_occupancy_of<double, true, T, NT>(bps) : sym_occupancy_of<double, false, T, NT>(bps);
+#define X(T, NT, RC) \
+  if (variant == k++) return wall ? sym_occupancy_of<double, true, T, NT, RC>(bps) : sym_occupancy_of<double, false, T, NT, RC>(bps);
   RBL_F64_SYM_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -849,13 +985,14 @@ cudaError_t matvec_sym_plan(int variant, bool wall, int n, int part, int n_parts
   return cudaSuccess;
 }
 
-template <typename real, bool WALL, int T, int NT>
+template <typename real, bool WALL, int T, int NT, int RC>
 static cudaError_t sym_launch_one(const SymArgs<real>& a, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
   static_assert((T * NT) % kSrcTile == 0, "target tile must be a multiple of the source tile");
   cudaError_t e = cudaMemsetAsync(a.raw, 0, 3 * (size_t)a.plan.n_src_tiles * kSrcTile * sizeof(real), s);
   if (e != cudaSuccess) return e;
   if (ev0) cudaEventRecord(ev0, s);
-  if (a.plan.u1 > a.plan.u0) rpy_matvec_sym_kernel<real, WALL, T, NT><<<a.plan.grid, NT, 0, s>>>(a);
+  if (a.plan.u1 > a.plan.u0)
+    rpy_matvec_sym_kernel<real, WALL, T, NT, RC><<<a.plan.grid, NT, sym_smem_bytes<real, T, NT, RC>(), s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (ev1) cudaEventRecord(ev1, s);
@@ -868,8 +1005,8 @@ cudaError_t matvec_sym_launch<float>(int variant, const SymArgs<float>& a, cudaS
                                      cudaEvent_t ev1) {
   if (a.plan.n <= 0) return cudaSuccess;
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return a.wall ? sym_launch_one<float, true, T, NT>(a, s, ev0, ev1) : sym_launch_one<float, false, T, NT>(a, s, ev0, ev1);
+#define X(T, NT, RC) \
+  if (variant == k++) return a.wall ? sym_launch_one<float, true, T, NT, RC>(a, s, ev0, ev1) : sym_launch_one<float, false, T, NT, RC>(a, s, ev0, ev1);
   RBL_F32_SYM_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -879,8 +1016,8 @@ cudaError_t matvec_sym_launch<double>(int variant, const SymArgs<double>& a, cud
                                       cudaEvent_t ev1) {
   if (a.plan.n <= 0) return cudaSuccess;
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return a.wall ? sym_launch_one<double, true, T, NT>(a, s, ev0, ev1) : sym_launch_one<double, false, T, NT>(a, s, ev0, ev1);
+#define X(T, NT, RC) \
+  if (variant == k++) return a.wall ? sym_launch_one<double, true, T, NT, RC>(a, s, ev0, ev1) : sym_launch_one<double, false, T, NT, RC>(a, s, ev0, ev1);
   RBL_F64_SYM_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;

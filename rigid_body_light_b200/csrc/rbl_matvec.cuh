@@ -49,6 +49,7 @@ struct MatvecArgs {
 struct MatvecVariant {
   int T;
   int threads;
+  int rc = 0;  // symmetric kernel: sources per warp-private reaction-reduction chunk (0 = warp butterfly)
 };
 
 template <typename real>

@@ -174,8 +174,8 @@ RBL_HD void pair(const PairConsts<real>& C, real xi, real yi, real zi, real xj, 
     const real q1 = fma_(E, C.q1a, C.q1b);
     const real q2 = fma_(E, C.q2a, C.q2b);
     const real h3 = fma_(q2, W, q1);
-    const real b = fma_(zi * ZW, (real)-6, (real)1);
-    const real a3 = fma_(-ZW, h3, z2j * b);
+    // a3 = 2 z_j (1 - 6 z_i Z W) - Z W h3 = 2 z_j - 12 p Z - Z W h3   (z_i z_j Z W = p Z)
+    const real a3 = fma_(-ZW, h3, fma_(p * Z, (real)-12, z2j));
     const real a4 = fma_(ZW * W, C.a4c, z2j);
     const real o1 = fma_(E, C.o1a, C.o1b);
     const real a5n = fma_(o1, W, -fma_(E, C.fa2, zz4j));
@@ -199,8 +199,8 @@ RBL_HD void pair(const PairConsts<real>& C, real xi, real yi, real zi, real xj, 
 // SOURCE height) and the accumulation.  ~92 issue slots per unordered pair instead of
 // 2 x 65 for two ordered evaluations.
 //   fi*, fj* are already multiplied by the blob's wall damping B; nzz4 = -4 z^2.  (2 z_src, which
-//   the ordered kernel reads from the record, is folded into b2 = 2 - 12 z_tgt Z W here so a thread
-//   need not keep it per target.)
+//   the ordered kernel reads from the record, enters as a literal-operand FMA on z_src here so a
+//   thread need not keep it per target.)
 template <typename real, bool WALL, bool NEAR>
 RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real fxi, real fyi,
                      real fzi, real nzz4i, real xj, real yj, real zj, real fxj, real fyj,
@@ -255,6 +255,9 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     const real q1 = fma_(E, C.q1a, C.q1b);
     const real q2 = fma_(E, C.q2a, C.q2b);
     const real nZWh3 = -ZW * fma_(q2, W, q1);
+    // a3 of the two directions: 2 z_src (1 - 6 z_tgt Z W) - Z W h3 = 2 z_src + S3 with the shared
+    // S3 = -12 p Z - Z W h3 (z_i z_j Z W = p Z): one literal-operand FMA per direction
+    const real S3 = fma_(p * Z, (real)-12, nZWh3);
     const real cZW2 = (ZW * W) * C.a4c;
     const real o1 = fma_(E, C.o1a, C.o1b);
     const real nS5 = fma_(o1, W, -(E * C.fa2));  // -(4a^2 E) - (4a^4/3)(2-15E) W
@@ -262,8 +265,7 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     const real cF = fma_(w, a1n, c1);
     // direction i <- j (source height z_j)
     {
-      const real b2 = fma_(zi * ZW, (real)-12, (real)2);
-      const real a3 = fma_(zj, b2, nZWh3);
+      const real a3 = fma_(zj, (real)2, S3);
       const real a4 = fma_(zj, (real)2, cZW2);
       const real a5n = nzz4j + nS5;
       const real A = wW * fma_(a3, fzj, a2n * gj);
@@ -275,8 +277,7 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     }
     // direction j <- i (source height z_i, in-plane separation -d)
     {
-      const real b2 = fma_(zj * ZW, (real)-12, (real)2);
-      const real a3 = fma_(zi, b2, nZWh3);
+      const real a3 = fma_(zi, (real)2, S3);
       const real a4 = fma_(zi, (real)2, cZW2);
       const real a5n = nzz4i + nS5;
       const real A = wW * fma_(a3, fzi, a2n * gi);
@@ -352,10 +353,11 @@ RBL_HD void pair_symR(const PairConsts<real>& C, real xi, real yi, real zi, cons
     const real nS5 = fma_(o1, W, -(E * C.fa2));
     const real cF = fma_(w, a1n, c1);
     // geometry-only coefficients of the two directions, pre-multiplied by wW
-    const real a3j = wW * fma_(zj, fma_(zi * ZW, (real)-12, (real)2), nZWh3);  // i <- j
+    const real S3 = fma_(p * Z, (real)-12, nZWh3);  // shared part of a3 (see pair_sym)
+    const real a3j = wW * fma_(zj, (real)2, S3);  // i <- j
     const real a4j = wW * fma_(zj, (real)2, cZW2);
     const real a5j = wW * (nzz4j + nS5);
-    const real a3i = wW * fma_(zi, fma_(zj * ZW, (real)-12, (real)2), nZWh3);  // j <- i
+    const real a3i = wW * fma_(zi, (real)2, S3);  // j <- i
     const real a4i = wW * fma_(zi, (real)2, cZW2);
     const real a5i = wW * (nzz4i + nS5);
 #pragma unroll

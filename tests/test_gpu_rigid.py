@@ -9,8 +9,10 @@ pytestmark = pytest.mark.gpu
 PRECISIONS = ["double", "single"]
 # O(N) kernels are a handful of flops per output: float results carry ~1e-7
 TOL_ON = {"double": 1e-13, "single": 2e-6}
-# the preconditioner involves dense per-body inverses (cond ~1e2..1e4): stated tolerance
-TOL_PC = {"double": 1e-9, "single": 2e-3}
+# the preconditioner involves dense per-body inverses; worst observed on B200 over every committed case
+# (touching a = sep/2 spheres AND the reference's overlapping a = 1 geometry, diagonal and block PC):
+# 4.0e-15 (double) / 1.8e-6 (float) -- the tolerance is ~10x that (gpurun_out/parity_observed.jsonl)
+TOL_PC = {"double": 5e-14, "single": 2e-5}
 
 
 def _solver(g, precision, block=False):
@@ -54,7 +56,7 @@ def test_sparse_K_and_Kinv_exports(name, precision):
     check(rel_err(K @ g["U"], g["KU"]), TOL_ON[precision])
     check(rel_err(K.T @ g["lam"], g["KTlam"]), TOL_ON[precision])
     check(rel_err(Kinv @ g["lam"], g["Kinv_lam"]), 10 * TOL_ON[precision])
-    assert np.abs((Kinv @ K).toarray() - np.eye(n6)).max() < (1e-11 if precision == "double" else 1e-4)
+    check(np.abs((Kinv @ K).toarray() - np.eye(n6)).max(), 1e-11 if precision == "double" else 1e-4, "max |Kinv K - I|")
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -67,7 +69,7 @@ def test_fused_saddle_matches_golden_and_composition(orc, name, precision):
     if precision == "double":
         check(rel_err(out, g["saddle"]), TOL["double"])
     else:
-        check(rel_err(out, g["saddle"]), 5 * TOL["single"])
+        check(rel_err(out, g["saddle"]), TOL["single"])  # observed 1.3e-7
     # the reference composes it in Python (Rigid.py:73-80); same numbers
     lam, U = g["vec"][:n3], g["vec"][n3:]
     slip = cb.apply_M(lam, cb.get_blob_positions()) - cb.K_dot(U).reshape(-1)
@@ -141,14 +143,16 @@ def test_gmres_solves_the_saddle_system(orc, name, block):
     rhs = g["vec"]
     x, iters, relres = cb.gmres(rhs, tol=1e-10, restart=80, max_iter=400)
     assert relres <= 1e-10 and 0 < iters < 400
-    check(rel_err(cb.apply_saddle(x), rhs), 1e-9)
+    check(rel_err(cb.apply_saddle(x), rhs), 2e-10, "true residual of the GMRES solution (requested 1e-10)")
     # dense oracle solve of [M -K; K^T 0] x = rhs
     a, eta, wall = float(g["a"]), float(g["eta"]), bool(g["wall"])
     M = np.asarray(orc.dense_mobility(g["r"], a, eta, wall))
     K = orc.K_dense(g["r"], g["X"], g["cfg"].shape[0])
     n3, n6 = M.shape[0], K.shape[1]
     A = np.block([[M, -K], [K.T, np.zeros((n6, n6))]])
-    check(rel_err(x, np.linalg.solve(A, rhs)), 1e-7)
+    condA = np.linalg.cond(A)
+    print(f"[{name}, block={block}] cond(saddle matrix) = {condA:.2e}, GMRES relres {relres:.1e}")
+    check(rel_err(x, np.linalg.solve(A, rhs)), 1e-9, f"GMRES solution vs dense solve, cond {condA:.1e} x relres 1e-10")  # observed 8e-11
 
 
 def test_gmres_single_precision_converges(orc):
@@ -156,7 +160,7 @@ def test_gmres_single_precision_converges(orc):
     cb = _solver(g, "single", block=True)
     x, iters, relres = cb.gmres(g["vec"], tol=1e-4, restart=60, max_iter=200)
     assert relres <= 1e-4
-    check(rel_err(cb.apply_saddle(x), g["vec"]), 1e-3)
+    check(rel_err(cb.apply_saddle(x), g["vec"]), 2e-4, "true residual of the float GMRES solution (requested 1e-4)")  # observed 6e-5
 
 
 @pytest.mark.parametrize("name", ["case_touch_wall", "case_overlap_free"])
@@ -176,7 +180,7 @@ def test_lanczos_sqrt_matches_dense_sqrtm(orc, name):
     W = np.random.default_rng(9).standard_normal(M.shape[0])
     out, iters = cb.brownian_sqrt(W, tol=1e-10, max_iter=150)
     want = np.real(sqrtm(M)) @ W
-    check(rel_err(out, want), 1e-7)
+    check(rel_err(out, want), 2e-9, "Lanczos square root vs scipy sqrtm (stopping tolerance 1e-10)")  # observed 1.8e-10
     assert 1 < iters <= 150
 
 
@@ -211,7 +215,7 @@ def test_bd_step_deterministic(orc, name):
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.0,
                              bool(g["wall"]), F, slip, None, None, None)
     assert relres <= 1e-11
-    check(rel_err(U, Uo), 1e-8)
+    check(rel_err(U, Uo), 2e-10, "deterministic step vs dense oracle solve (GMRES 1e-11)")  # observed 1.3e-11
     X, Q = cb.get_config()
     check(rel_err(X, Xo), 1e-10)
     check(rel_err(Q, Qo), 1e-10)
@@ -234,13 +238,13 @@ def test_bd_step_brownian_given_noise(orc, name):
     ref = orc.remove_mean(g["cfg"])
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), kBT,
                              bool(g["wall"]), F, None, *noise, noise="block_cholesky")  # the default noise of bd_step
-    check(rel_err(U, Uo), 1e-6)
+    check(rel_err(U, Uo), 1e-10, "Brownian step vs dense oracle composition")  # observed 1e-11
     X, Q = cb.get_config()
-    check(rel_err(X, Xo), 1e-8)
-    check(rel_err(Q, Qo), 1e-8)
+    check(rel_err(X, Xo), 1e-12)  # observed 3e-14
+    check(rel_err(Q, Qo), 1e-12)  # observed 3e-14
     # the context is back on a consistent configuration: K matches the evolved positions
     r_new = orc.blob_positions(Xo, Qo, ref)
-    check(rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r_new, Xo, ref.shape[0])), 1e-8)
+    check(rel_err(cb.K_dot(g["U"]), orc.K_dot(g["U"], r_new, Xo, ref.shape[0])), 1e-12)
 
 
 def test_bd_step_needs_noise_when_brownian():
@@ -268,10 +272,10 @@ def test_bd_step_symmetric_square_root_noise(orc, name):
     ref = orc.remove_mean(g["cfg"])
     Uo, Xo, Qo = orc.bd_step(g["X"], g["Qn"], ref, float(g["a"]), float(g["eta"]), float(g["dt"]), 0.004,
                              bool(g["wall"]), F, None, *noise)
-    check(rel_err(U, Uo), 1e-6)
+    check(rel_err(U, Uo), 1e-10, "Brownian step vs dense oracle composition")  # observed 1e-11
     X, Q = cb.get_config()
-    check(rel_err(X, Xo), 1e-8)
-    check(rel_err(Q, Qo), 1e-8)
+    check(rel_err(X, Xo), 1e-12)  # observed 3e-14
+    check(rel_err(Q, Qo), 1e-12)  # observed 3e-14
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -298,7 +302,7 @@ def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, na
     out, iters = cb.brownian_sqrt(W, tol=tol, max_iter=150)
     plain = _solver(g, precision)
     ref_out, ref_iters = plain.brownian_sqrt(W, tol=tol, max_iter=150)
-    lim = 1e-7 if precision == "double" else 2e-3
+    lim = 1e-10 if precision == "double" else 5e-5  # Lanczos stops at 1e-11 / 1e-5; observed 3.6e-12 / 1.4e-5
     if spd:
         want = orc.noise_block_cholesky(orc.noise_factors(g["r"], g["Qn"], orc.remove_mean(g["cfg"]), a, eta, wall), A, W)
         check(rel_err(out, want), lim)
@@ -309,7 +313,7 @@ def test_preconditioned_noise_matches_dense_and_has_the_right_covariance(orc, na
     # min eigenvalue -0.17, so no square root exists -- the reference's Cholesky would fail too)
     if precision == "double" and A.shape[0] <= 400 and np.linalg.eigvalsh(A).min() > 0:
         S = np.stack([cb.brownian_sqrt(e, tol=1e-12, max_iter=200)[0] for e in np.eye(A.shape[0])], axis=1)
-        check(np.linalg.norm(S @ S.T - A) / np.linalg.norm(A), 1e-8)
+        check(np.linalg.norm(S @ S.T - A) / np.linalg.norm(A), 1e-11)  # observed 1.2e-13
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -331,7 +335,8 @@ def test_noise_factor_selfcheck_at_large_body_sizes(shell, n_bodies, wall, preci
     ctx.call("rbl_noise_selfcheck", ctypes.byref(f), ctypes.byref(g), ctypes.byref(act))
     assert act.value == 1
     lim = 1e-10 if precision == "double" else 2e-3
-    assert f.value < lim and g.value < lim, (f.value, g.value)
+    check(f.value, lim, f"|L L^T x - Mt x| / |Mt x|, {n_bodies} x shell_N_{shell}, wall={wall}, {precision}")
+    check(g.value, lim, f"|G L x - x| / |x|, {n_bodies} x shell_N_{shell}, wall={wall}, {precision}")
     ctx.close()
 
 
@@ -346,15 +351,15 @@ def test_bd_step_matches_the_committed_golden_step(name, mode):
     key = f"{name}/{'block_cholesky' if mode else 'symmetric'}"
     U, iters, relres = cb.bd_step(bd[f"{name}/F"], kBT=float(bd[f"{name}/kBT"]), noise=tuple(bd[f"{name}/W"]), tol=1e-11,
                                   restart=100, max_iter=400, lanczos_tol=1e-12, lanczos_max_iter=200)
-    check(rel_err(U, bd[key + "/U"]), 1e-6)
+    check(rel_err(U, bd[key + "/U"]), 1e-10)  # observed 1e-11
     X, Q = cb.get_config()
-    check(rel_err(X, bd[key + "/X"]), 1e-8)
-    check(rel_err(Q, bd[key + "/Q"]), 1e-8)
+    check(rel_err(X, bd[key + "/X"]), 1e-12)
+    check(rel_err(Q, bd[key + "/Q"]), 1e-12)
     # and the Brownian increment itself
     cb2 = _solver(g, "double")
     cb2.set_noise_preconditioner(2 if mode else 0)
     y, _ = cb2.brownian_sqrt(bd[f"{name}/W"][0], tol=1e-12, max_iter=200)
-    check(rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]), 1e-7)
+    check(rel_err(y, bd[f"{name}/noise_{'block_cholesky' if mode else 'symmetric'}"]), 1e-11)  # observed 9e-13
 
 
 @pytest.mark.parametrize("precision", ["double", "single"])
@@ -381,7 +386,7 @@ def test_seeded_bd_step_equals_the_step_with_the_same_noise(orc, name):
     Ua, _, _ = a.bd_step(F, kBT=0.004, seed=77, step=12, **kw)
     b = _solver(g, "double", block=True)
     Ub, _, _ = b.bd_step(F, kBT=0.004, noise=orc.philox_normals(77, 12, 0, n3), **kw)
-    check(rel_err(Ua, Ub), 1e-9)
+    check(rel_err(Ua, Ub), 1e-12)  # observed 1.1e-14
     check(rel_err(a.get_config()[0], b.get_config()[0]), 1e-12)
     c = _solver(g, "double", block=True)
     Uc, _, _ = c.bd_step(F, kBT=0.004, seed=77, step=13, **kw)  # another step number: other noise
@@ -445,7 +450,7 @@ def test_cuda_path_against_the_live_reference_members(orc, wall, precision):
     rr = rb.positions()
     check(rel_err(cb.apply_M(lam, rr), rb.apply_M(lam, rr)), tol_m)
     ref_saddle = np.concatenate([rb.apply_M(vec[:n3], rr) - rb.K_dot(vec[n3:]), rb.KT_dot(vec[:n3])])  # Rigid.py:73-80
-    check(rel_err(cb.apply_saddle(vec), ref_saddle), 10 * tol_m)
+    check(rel_err(cb.apply_saddle(vec), ref_saddle), tol_m)  # observed 8e-16 / 2.5e-7
     check(rel_err(cb.apply_PC(vec), rb.apply_PC(vec)), tol_pc)
     cb.evolve_rigid_bodies(U)
     rb.evolve(U)

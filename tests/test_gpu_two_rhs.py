@@ -102,7 +102,7 @@ def test_paired_lanczos_equals_two_single_runs(name, precision):
     y1, y2, k1, k2 = cb.brownian_sqrt_pair(W1, W2, tol=tol, max_iter=150)
     s1, j1 = cb.brownian_sqrt(W1, tol=tol, max_iter=150)
     s2, j2 = cb.brownian_sqrt(W2, tol=tol, max_iter=150)
-    lim = 1e-9 if precision == "double" else 2e-4
+    lim = 1e-13 if precision == "double" else 2e-6  # observed 4.6e-15 / 1.4e-7
     check(rel_err(y1, s1), lim)
     check(rel_err(y2, s2), lim)
     assert abs(k1 - j1) <= 1 and abs(k2 - j2) <= 1
@@ -129,8 +129,8 @@ def test_bd_step_paired_and_unpaired_lanczos_agree():
         U, it, rr = cb.bd_step(F, kBT=0.004, noise=noise, tol=1e-11, restart=100, max_iter=400, lanczos_tol=1e-12,
                                lanczos_max_iter=200)
         out.append((U, cb.get_config()))
-    check(rel_err(out[0][0], out[1][0]), 1e-9)
-    check(rel_err(out[0][1][0], out[1][1][0]), 1e-11)
+    check(rel_err(out[0][0], out[1][0]), 1e-13)  # observed 4e-15
+    check(rel_err(out[0][1][0], out[1][1][0]), 1e-14)
 
 
 def test_full_size_krylov_properties_config3():
@@ -151,13 +151,14 @@ def test_full_size_krylov_properties_config3():
     z1, z2, _, _ = cb.brownian_sqrt_pair(y1, y2, tol=1e-5, max_iter=80)
     r = cb.get_blob_positions()
     m1, m2 = cb.apply_M2(W1, W2, r)
-    check(rel_err(z1, m1), 2e-3)
-    check(rel_err(z2, m2), 2e-3)
+    # Krylov convergence, not parity: each square root stops at a relative change of 1e-5; observed 4.4e-5
+    check(rel_err(z1, m1), 4e-4, "S(S W) vs M W with the Lanczos stopping tolerance 1e-5, float")
+    check(rel_err(z2, m2), 4e-4, "S(S W) vs M W with the Lanczos stopping tolerance 1e-5, float")
     s2, s1, j2, j1 = cb.brownian_sqrt_pair(W2, W1, tol=1e-5, max_iter=80)
     assert (j1, j2) == (k1, k2)
-    check(rel_err(s1, y1), 1e-4)
-    check(rel_err(s2, y2), 1e-4)
+    check(rel_err(s1, y1), 5e-6)  # observed 3.5e-7
+    check(rel_err(s2, y2), 5e-6)
     rhs = np.concatenate([np.zeros(n3), rng.standard_normal(n6)]).astype(np.float32)
     x, it, rr = cb.gmres(rhs, tol=1e-4, restart=60, max_iter=120)
     assert rr <= 1e-4 and it < 60
-    check(rel_err(cb.apply_saddle(x), rhs), 5e-4)
+    check(rel_err(cb.apply_saddle(x), rhs), 2e-4, "true residual of the float GMRES solution (requested 1e-4)")  # observed 6.2e-5

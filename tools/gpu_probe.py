@@ -64,9 +64,10 @@ def main():
                     ctx.call("rbl_dev_apply_M", F.data_ptr(), r.data_ptr(), n, 0, n, out.data_ptr())
                 ms = ctx.timer_stop() / args.reps
                 kms, nl = ctx.matvec_profile(reset=True)
+                rc = ctx.L.rbl_sym_variant_chunk(ctx.h, v) if args.kernel == "symmetric" else 0
                 pairs = float(n) * n
                 tf = pairs * FLOPS[wall] / (kms * 1e-3) / 1e12
-                print(json.dumps({"probe": "matvec", "kernel": args.kernel, "precision": precision, "wall": wall, "variant": v, "T": T.value,
+                print(json.dumps({"probe": "matvec", "kernel": args.kernel, "precision": precision, "wall": wall, "variant": v, "T": T.value, "rc": rc,
                                   "threads": th.value, "n": n, "ms_call": round(ms, 3), "ms_kernel": round(kms, 3),
                                   "gpairs_s": round(pairs / (ms * 1e-3) / 1e9, 1), "alg_tflops": round(tf, 2),
                                   "frac_of_fma_peak": round(tf / peak, 3), "sum": float(out.double().abs().sum())}),
