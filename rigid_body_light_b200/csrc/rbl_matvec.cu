@@ -882,11 +882,9 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
 
 // (T targets per thread, NT threads per CTA, RC reaction-reduction chunk; RC = 0: warp butterfly)
 #define RBL_F32_SYM_VARIANTS(X) \
-  X(4, 256, 16) X(6, 128, 16) X(4, 256, 0) X(6, 128, 0) X(4, 256, 8) X(4, 256, 32) X(6, 128, 8) X(8, 128, 16) \
-  X(5, 256, 16) X(6, 256, 16) X(4, 128, 16) X(2, 256, 8) X(1, 256, 8)
+  X(6, 256, 16) X(4, 128, 16) X(4, 256, 16) X(5, 256, 16) X(4, 256, 0) X(2, 256, 8) X(1, 256, 8)
 #define RBL_F64_SYM_VARIANTS(X) \
-  X(3, 256, 16) X(4, 128, 16) X(3, 256, 0) X(4, 128, 0) X(3, 256, 8) X(4, 128, 8) X(4, 256, 16) X(2, 256, 16) \
-  X(2, 128, 8) X(1, 256, 8)
+  X(4, 256, 16) X(3, 256, 16) X(4, 128, 16) X(3, 256, 0) X(2, 128, 8) X(1, 256, 8)
 
 template <>
 MatvecVariant matvec_sym_variant<float>(int idx) {
@@ -923,11 +921,12 @@ int matvec_sym_num_variants<double>() {
   return n;
 }
 
-// defaults measured on B200 (profiles/): index 0 with the wall, 1 in free space; small problems take
-// the smallest target tile (the last variant) so that the unit triangle still covers the SMs
+// defaults measured on B200 at 162 000 blobs (profiles/r02_probe_variants.md): fp32 (6,256,16) with and
+// without the wall; fp64 (4,256,16) with the wall, (3,256,16) in free space; small problems take the
+// smallest target tile (the last variant) so that the unit triangle still covers the SMs
 template <>
-int matvec_sym_default_variant<float>(bool wall, int n) {
-  return n < 16384 ? matvec_sym_num_variants<float>() - 1 : (wall ? 0 : 1);
+int matvec_sym_default_variant<float>(bool, int n) {
+  return n < 16384 ? matvec_sym_num_variants<float>() - 1 : 0;
 }
 template <>
 int matvec_sym_default_variant<double>(bool wall, int n) {
@@ -1164,13 +1163,72 @@ __device__ __forceinline__ void tile_compute_sym2(const real* __restrict__ sb, c
       for (int c = 0; c < 3; ++c) u[t][k][c] = kTwoLevel ? u[t][k][c] + l[t][k][c] : l[t][k][c];
 }
 
-template <typename real, bool WALL, int T, int NT>
+// Two right-hand sides through the warp-private reduction tile (see tile_compute_symt): 6 rows per
+// source (2 right-hand sides x 3 components), rows ordered component-major, row = (k*3 + c) * RC +
+// source, so that consecutive sources are one row stride apart (36 words = 4 mod 32 in fp32, 68
+// words = 4 mod 32 in fp64: the transposed 128-bit reads of a quarter-warp hit distinct bank groups).
+template <typename real, int RC>
+__host__ __device__ constexpr size_t red2_tile_reals() {
+  return RC > 0 ? (size_t)RC * 6 * RedLayout<real>::kStride : 0;
+}
+
+template <typename real, bool WALL, bool NEAR, int T, int RC>
+__device__ __forceinline__ void tile_compute_sym2t(const real* __restrict__ sb, const PairConsts<real>& C,
+                                                   const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
+                                                   const real (&nz4i)[T], const real (&fi)[T][2][3],
+                                                   real (&u)[T][2][3], real* __restrict__ raw1,
+                                                   real* __restrict__ raw2, real* __restrict__ red, int jb, int je) {
+  static_assert(RC == 8 || RC == 16 || RC == 32, "reduction chunk");
+  constexpr int STR = RedLayout<real>::kStride;
+  const int lane = threadIdx.x & 31;
+  const int src = lane % RC, part = lane / RC;
+  real* __restrict__ wr = red + lane;
+  const real* __restrict__ rd = red + (size_t)src * STR + part * RC;
+  for (int j0 = jb; j0 < je; j0 += RC) {
+#pragma unroll 1
+    for (int jj = 0; jj < RC / 2; ++jj) {
+      Rec2<real> sa, sb2;
+      load_rec2(sb + (size_t)(j0 + jj) * kRec2Reals, sa);
+      load_rec2(sb + (size_t)(j0 + jj + RC / 2) * kRec2Reals, sb2);
+      real ra[2][3] = {{0, 0, 0}, {0, 0, 0}}, rb[2][3] = {{0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sa.x, sa.y, sa.z, sa.f, sa.nz4, u[t], ra);
+        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sb2.x, sb2.y, sb2.z, sb2.f, sb2.nz4, u[t], rb);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wr[(size_t)((k * 3 + c) * RC + jj) * STR] = ra[k][c];
+          wr[(size_t)((k * 3 + c) * RC + jj + RC / 2) * STR] = rb[k][c];
+        }
+    }
+    __syncwarp();
+    real* o1 = raw1 + 3 * (size_t)(j0 + src);
+    real* o2 = raw2 + 3 * (size_t)(j0 + src);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(o1 + c, row_sum<RC>(rd + (size_t)(c * RC) * STR));
+      atomicAdd(o2 + c, row_sum<RC>(rd + (size_t)((3 + c) * RC) * STR));
+    }
+    __syncwarp();
+  }
+}
+
+template <typename real, int T, int NT, int RC>
+__host__ __device__ constexpr size_t sym2_smem_bytes() {
+  return (2 * (size_t)kSrcTile * kRec2Reals + (size_t)(NT / 32) * red2_tile_reals<real, RC>()) * sizeof(real);
+}
+
+template <typename real, bool WALL, int T, int NT, int RC>
 __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real> A) {
   constexpr int TT = T * NT;
   constexpr uint32_t kTileBytes = kSrcTile * kRec2Reals * sizeof(real);
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   real* sbuf0 = reinterpret_cast<real*>(smem_dyn);
   real* sbuf1 = sbuf0 + kSrcTile * kRec2Reals;
+  real* const red = sbuf1 + kSrcTile * kRec2Reals + (size_t)(threadIdx.x >> 5) * red2_tile_reals<real, RC>();
   __shared__ __align__(8) unsigned long long mbar[2];
 
   const int tid = threadIdx.x;
@@ -1205,7 +1263,7 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
     tma_load_1d(sbuf0, A.rec + (size_t)J * kSrcTile * kRec2Reals, kTileBytes, &mbar[0]);
   }
 
-  real xi[T], yi[T], zi[T], nz4i[T], fi[T][2][3], u[T][2][3];
+  real xi[T], yi[T], zi[T], nz4i[T], fi[T][2][3];
   bool fresh = true;
   const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
   const size_t raw_ld = 3 * (size_t)ns * kSrcTile;
@@ -1238,10 +1296,7 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            fi[t][k][c] = pad ? (real)0 : me.f[k][c];
-            u[t][k][c] = (real)0;
-          }
+          for (int c = 0; c < 3; ++c) fi[t][k][c] = pad ? (real)0 : me.f[k][c];
       }
       fresh = false;
     }
@@ -1249,35 +1304,49 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
     const bool far = box_gap2(A.box_tgt + 6 * (size_t)I, A.box_src + 6 * (size_t)J) > near2;
     const bool diagonal = J < (I + 1) * D;
 
+    real u[T][2][3];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) u[t][k][c] = (real)0;
+
     mbar_wait(&mbar[buf], parity);
     if (diagonal) {
       tile_compute2_ordered<real, WALL, T>(cur, A.C, xi, yi, zi, u, jb, je);
     } else {
       real* raw1 = A.raw + 3 * (size_t)J * kSrcTile;
       real* raw2 = raw1 + raw_ld;
-      if (far)
-        tile_compute_sym2<real, WALL, false, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
-      else
-        tile_compute_sym2<real, WALL, true, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
+      if constexpr (RC == 0) {
+        if (far)
+          tile_compute_sym2<real, WALL, false, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
+        else
+          tile_compute_sym2<real, WALL, true, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
+      } else {
+        if (far)
+          tile_compute_sym2t<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, red, jb, je);
+        else
+          tile_compute_sym2t<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, red, jb, je);
+      }
+    }
+    // flush this unit's target sums (the per-tile accumulators are the first summation level)
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int li = I * TT + tid + t * NT;
+      if (li < A.plan.n) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) atomicAdd(A.raw + k * raw_ld + 3 * (size_t)li + c, u[t][k][c]);
+      }
     }
     __syncthreads();
 
-    if (row_end || g + 1 == g1) {
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int li = I * TT + tid + t * NT;
-        if (li < A.plan.n) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) atomicAdd(A.raw + k * raw_ld + 3 * (size_t)li + c, u[t][k][c]);
-        }
-      }
-      fresh = true;
-    }
     if (row_end) {
       ++I;
       J = I * D;
+      fresh = true;
     } else {
       ++J;
     }
@@ -1298,17 +1367,29 @@ __global__ void rpy_sym2_scale_kernel(const Sym2Args<real> A) {
   }
 }
 
-#define RBL_F32_SYM2_VARIANTS(X) X(4, 256) X(2, 256) X(4, 128) X(1, 256)
-#define RBL_F64_SYM2_VARIANTS(X) X(2, 256) X(2, 128) X(1, 256)
+#define RBL_F32_SYM2_VARIANTS(X) X(3, 256, 8) X(4, 128, 8) X(4, 128, 0) X(2, 256, 8) X(1, 256, 8)
+#define RBL_F64_SYM2_VARIANTS(X) X(3, 256, 8) X(2, 256, 8) X(2, 256, 0) X(1, 256, 8)
 
 template <>
-int matvec_sym2_num_variants<float>() { return 4; }
+int matvec_sym2_num_variants<float>() {
+  int n = 0;
+#define X(T, NT, RC) ++n;
+  RBL_F32_SYM2_VARIANTS(X)
+#undef X
+  return n;
+}
 template <>
-int matvec_sym2_num_variants<double>() { return 3; }
+int matvec_sym2_num_variants<double>() {
+  int n = 0;
+#define X(T, NT, RC) ++n;
+  RBL_F64_SYM2_VARIANTS(X)
+#undef X
+  return n;
+}
 template <>
 MatvecVariant matvec_sym2_variant<float>(int idx) {
   static const MatvecVariant v[] = {
-#define X(T, NT) {T, NT},
+#define X(T, NT, RC) {T, NT, RC},
       RBL_F32_SYM2_VARIANTS(X)
 #undef X
   };
@@ -1317,37 +1398,35 @@ MatvecVariant matvec_sym2_variant<float>(int idx) {
 template <>
 MatvecVariant matvec_sym2_variant<double>(int idx) {
   static const MatvecVariant v[] = {
-#define X(T, NT) {T, NT},
+#define X(T, NT, RC) {T, NT, RC},
       RBL_F64_SYM2_VARIANTS(X)
 #undef X
   };
   return v[idx];
 }
-// measured on B200 at 172 032 blobs with the wall (profiles/r01_sym2_sweep_cfg3.jsonl): fp32 (4,128)
-// 75.96 ms, (4,256) 76.56 ms; fp64 (2,256) 148.7 ms -- against 102.2 / 196.1 ms for two single passes
+// index 0 = the default measured on B200 at 172 032 blobs with the wall (profiles/r02_sym2_sweep_cfg3.jsonl:
+// fp32 (3,256,8) 70.6 ms against 96.7 ms for two single passes, fp64 (3,256,8) 136.6 against 179.5 ms); small
+// problems take the smallest target tile (the last variant)
 template <>
-int matvec_sym2_default_variant<float>(bool, int n) { return n < 16384 ? 3 : 2; }
+int matvec_sym2_default_variant<float>(bool, int n) { return n < 16384 ? matvec_sym2_num_variants<float>() - 1 : 0; }
 template <>
-int matvec_sym2_default_variant<double>(bool, int n) { return n < 16384 ? 2 : 0; }
+int matvec_sym2_default_variant<double>(bool, int n) { return n < 16384 ? matvec_sym2_num_variants<double>() - 1 : 0; }
 
-template <typename real>
-constexpr size_t sym2_smem_bytes() { return 2 * (size_t)kSrcTile * kRec2Reals * sizeof(real); }
-
-template <typename real, bool WALL, int T, int NT>
+template <typename real, bool WALL, int T, int NT, int RC>
 static cudaError_t sym2_occupancy_of(int* bps) {
-  cudaError_t e = cudaFuncSetAttribute(rpy_matvec_sym2_kernel<real, WALL, T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sym2_smem_bytes<real>());
+  constexpr size_t smem = sym2_smem_bytes<real, T, NT, RC>();
+  cudaError_t e = cudaFuncSetAttribute(rpy_matvec_sym2_kernel<real, WALL, T, NT, RC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym2_kernel<real, WALL, T, NT>, NT,
-                                                       sym2_smem_bytes<real>());
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, rpy_matvec_sym2_kernel<real, WALL, T, NT, RC>, NT, smem);
 }
 template <typename real>
 static cudaError_t sym2_variant_occupancy(int variant, bool wall, int* bps);
 template <>
 cudaError_t sym2_variant_occupancy<float>(int variant, bool wall, int* bps) {
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return wall ? sym2_occupancy_of<float, true, T, NT>(bps) : sym2_occupancy_of<float, false, T, NT>(bps);
+#define X(T, NT, RC) \
+  if (variant == k++) return wall ? sym2_occupancy_of<float, true, T, NT, RC>(bps) : sym2_occupancy_of<float, false, T, NT, RC>(bps);
   RBL_F32_SYM2_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -1355,8 +1434,8 @@ cudaError_t sym2_variant_occupancy<float>(int variant, bool wall, int* bps) {
 template <>
 cudaError_t sym2_variant_occupancy<double>(int variant, bool wall, int* bps) {
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return wall ? sym2_occupancy_of<double, true, T, NT>(bps) : sym2_occupancy_of<double, false, T, NT>(bps);
+#define X(T, NT, RC) \
+  if (variant == k++) return wall ? sym2_occupancy_of<double, true, T, NT, RC>(bps) : sym2_occupancy_of<double, false, T, NT, RC>(bps);
   RBL_F64_SYM2_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -1384,14 +1463,14 @@ cudaError_t matvec_sym2_plan(int variant, bool wall, int n, int part, int n_part
   return cudaSuccess;
 }
 
-template <typename real, bool WALL, int T, int NT>
+template <typename real, bool WALL, int T, int NT, int RC>
 static cudaError_t sym2_launch_one(const Sym2Args<real>& a, cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1) {
   static_assert((T * NT) % kSrcTile == 0, "target tile must be a multiple of the source tile");
   cudaError_t e = cudaMemsetAsync(a.raw, 0, 2 * 3 * (size_t)a.plan.n_src_tiles * kSrcTile * sizeof(real), s);
   if (e != cudaSuccess) return e;
   if (ev0) cudaEventRecord(ev0, s);
   if (a.plan.u1 > a.plan.u0)
-    rpy_matvec_sym2_kernel<real, WALL, T, NT><<<a.plan.grid, NT, sym2_smem_bytes<real>(), s>>>(a);
+    rpy_matvec_sym2_kernel<real, WALL, T, NT, RC><<<a.plan.grid, NT, sym2_smem_bytes<real, T, NT, RC>(), s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (ev1) cudaEventRecord(ev1, s);
@@ -1404,8 +1483,8 @@ cudaError_t matvec_sym2_launch<float>(int variant, const Sym2Args<float>& a, cud
                                       cudaEvent_t ev1) {
   if (a.plan.n <= 0) return cudaSuccess;
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return a.wall ? sym2_launch_one<float, true, T, NT>(a, s, ev0, ev1) : sym2_launch_one<float, false, T, NT>(a, s, ev0, ev1);
+#define X(T, NT, RC) \
+  if (variant == k++) return a.wall ? sym2_launch_one<float, true, T, NT, RC>(a, s, ev0, ev1) : sym2_launch_one<float, false, T, NT, RC>(a, s, ev0, ev1);
   RBL_F32_SYM2_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
@@ -1415,8 +1494,8 @@ cudaError_t matvec_sym2_launch<double>(int variant, const Sym2Args<double>& a, c
                                        cudaEvent_t ev1) {
   if (a.plan.n <= 0) return cudaSuccess;
   int k = 0;
-#define X(T, NT) \
-  if (variant == k++) return a.wall ? sym2_launch_one<double, true, T, NT>(a, s, ev0, ev1) : sym2_launch_one<double, false, T, NT>(a, s, ev0, ev1);
+#define X(T, NT, RC) \
+  if (variant == k++) return a.wall ? sym2_launch_one<double, true, T, NT, RC>(a, s, ev0, ev1) : sym2_launch_one<double, false, T, NT, RC>(a, s, ev0, ev1);
   RBL_F64_SYM2_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -157,12 +157,11 @@ RBL_HD void pair(const PairConsts<real>& C, real xi, real yi, real zi, real xj, 
     uz = fma_(c1, fz, uz); uz = fma_(t, dz, uz);
   } else {
     const real Z = zi + zj;
-    const real Z2 = Z * Z;
-    const real R2 = q + Z2;
+    const real R2 = fma_(Z, Z, q);
     const real w = rsqrt_fast(R2);
     const real W = w * w;
     const real g = fma_(Z, fz, s);
-    const real E = Z2 * W;
+    const real E = fma_(-q, W, (real)1);  // Z^2 W = 1 - (dx^2 + dy^2) W: E only ever enters next to O(1) terms
     const real p = (zi * zj) * W;
     const real k1 = fma_(E, C.k1a, C.k1b);
     const real k2 = fma_(E, C.k2a, C.k2b);
@@ -237,13 +236,12 @@ RBL_HD void pair_sym(const PairConsts<real>& C, real xi, real yi, real zi, real 
     uzj = fma_(c1, fzi, uzj); uzj = fma_(ti, dz, uzj);
   } else {
     const real Z = zi + zj;
-    const real Z2 = Z * Z;
-    const real R2 = q + Z2;
+    const real R2 = fma_(Z, Z, q);
     const real w = rsqrt_fast(R2);
     const real W = w * w;
     const real gj = fma_(Z, fzj, sj);   // (dx,dy,Z) . f_j
     const real gi = fma_(Z, fzi, -si);  // (-dx,-dy,Z) . f_i
-    const real E = Z2 * W;
+    const real E = fma_(-q, W, (real)1);  // Z^2 W = 1 - (dx^2 + dy^2) W
     const real p = (zi * zj) * W;
     const real k1 = fma_(E, C.k1a, C.k1b);
     const real k2 = fma_(E, C.k2a, C.k2b);
@@ -331,11 +329,10 @@ RBL_HD void pair_symR(const PairConsts<real>& C, real xi, real yi, real zi, cons
     }
   } else {
     const real Z = zi + zj;
-    const real Z2 = Z * Z;
-    const real R2 = q + Z2;
+    const real R2 = fma_(Z, Z, q);
     const real w = rsqrt_fast(R2);
     const real W = w * w;
-    const real E = Z2 * W;
+    const real E = fma_(-q, W, (real)1);  // Z^2 W = 1 - (dx^2 + dy^2) W
     const real p = (zi * zj) * W;
     const real k1 = fma_(E, C.k1a, C.k1b);
     const real k2 = fma_(E, C.k2a, C.k2b);
