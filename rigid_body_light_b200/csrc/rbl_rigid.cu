@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "rbl_pair.cuh"
 #include "rbl_rigid.cuh"
 
 #ifndef M_PI
@@ -331,111 +332,107 @@ cudaError_t pc_fill_kcols(const real* r, const real* X, int n_bod, int n_blb, re
   return cudaGetLastError();
 }
 
-// 3x3 block of the (8 pi eta a)-normalised mobility between blobs at ri, rj, following the
-// reference's formulas for ENTRIES (c_rigid_obj.cpp:31-142) -- set-up path, not hot.
-template <typename real>
-__device__ void mobility_block(const real* ri, const real* rj, bool self, real a, bool wall,
-                               real* B) {
-  const real f43 = (real)4 / (real)3;
-  const real inv_a = (real)1 / a;
-  real rx = (ri[0] - rj[0]) * inv_a, ry = (ri[1] - rj[1]) * inv_a, rz = (ri[2] - rj[2]) * inv_a;
-  if (self) {
-    B[0] = f43; B[1] = 0; B[2] = 0; B[3] = 0; B[4] = f43; B[5] = 0; B[6] = 0; B[7] = 0; B[8] = f43;
-  } else {
-    const real r2 = rx * rx + ry * ry + rz * rz;
-    const real rr = sqrt(r2);
-    const real invr = (real)1 / rr, invr2 = invr * invr;
-    real c1, c2, sc;
-    if (rr >= (real)2) {
-      c1 = (real)1 + (real)2 / ((real)3 * r2);
-      c2 = ((real)1 - (real)2 * invr2) * invr2;
-      sc = invr;
-    } else {
-      c1 = f43 * ((real)1 - (real)0.28125 * rr);
-      c2 = f43 * (real)0.09375 * invr;
-      sc = 1;
-    }
-    B[0] = (c1 + c2 * rx * rx) * sc; B[1] = (c2 * rx * ry) * sc; B[2] = (c2 * rx * rz) * sc;
-    B[4] = (c1 + c2 * ry * ry) * sc; B[5] = (c2 * ry * rz) * sc; B[8] = (c1 + c2 * rz * rz) * sc;
-    B[3] = B[1]; B[6] = B[2]; B[7] = B[5];
-  }
-  if (wall) {
-    const real hj = rj[2] * inv_a;
-    if (self) {
-      const real inv = (real)1 / hj, i3 = inv * inv * inv, i5 = i3 * inv * inv;
-      B[0] += -(9 * inv - 2 * i3 + i5) / (real)12;
-      B[4] += -(9 * inv - 2 * i3 + i5) / (real)12;
-      B[8] += -(9 * inv - 4 * i3 + i5) / (real)6;
-    } else {
-      const real Rz = (ri[2] + rj[2]) * inv_a;
-      const real hh = hj / Rz;
-      const real invR = (real)1 / sqrt(rx * rx + ry * ry + Rz * Rz);
-      const real ex = rx * invR, ey = ry * invR, ez = Rz * invR;
-      const real invR3 = invR * invR * invR, invR5 = invR3 * invR * invR;
-      const real f1 = -(3 * (1 + 2 * hh * (1 - hh) * ez * ez) * invR + 2 * (1 - 3 * ez * ez) * invR3 - 2 * (1 - 5 * ez * ez) * invR5) / (real)3;
-      const real f2 = -(3 * (1 - 6 * hh * (1 - hh) * ez * ez) * invR - 6 * (1 - 5 * ez * ez) * invR3 + 10 * (1 - 7 * ez * ez) * invR5) / (real)3;
-      const real f3 = ez * (3 * hh * (1 - 6 * (1 - hh) * ez * ez) * invR - 6 * (1 - 5 * ez * ez) * invR3 + 10 * (2 - 7 * ez * ez) * invR5) * (real)2 / (real)3;
-      const real f4 = ez * (3 * hh * invR - 10 * invR5) * (real)2 / (real)3;
-      const real f5 = -(3 * hh * hh * ez * ez * invR + 3 * ez * ez * invR3 + (2 - 15 * ez * ez) * invR5) * (real)4 / (real)3;
-      B[0] += f1 + f2 * ex * ex; B[1] += f2 * ex * ey; B[2] += f2 * ex * ez + f3 * ex;
-      B[3] += f2 * ey * ex; B[4] += f1 + f2 * ey * ey; B[5] += f2 * ey * ez + f3 * ey;
-      B[6] += f2 * ez * ex + f4 * ex; B[7] += f2 * ez * ey + f4 * ey;
-      B[8] += f1 + f2 * ez * ez + f3 * ez + f4 * ez + f5;
-    }
-  }
-}
-
-template <typename real>
-__global__ void pc_block_assemble_kernel(const real* __restrict__ r, int n_blb, real a,
-                                         real norm, int wall, real* __restrict__ M,
-                                         int* __restrict__ below) {
+// Dense mobility block of one body, M_b (3 n_blb x 3 n_blb), from the SAME pair arithmetic as the
+// product kernels (rbl::pair, rbl_pair.cuh): column q of the 3x3 block (i, j) is the velocity of blob
+// i for a unit force e_q on blob j.  Upper triangle evaluated with the source's height and mirrored
+// transposed, like the reference's assembly loop (c_rigid_obj.cpp:430-452).  Set-up path, not hot.
+template <typename real, bool WALL>
+__global__ void pc_block_assemble_kernel(const real* __restrict__ r, int n_blb, const PairConsts<real> C,
+                                         real* __restrict__ M, int* __restrict__ below) {
   const int b = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_blb * n_blb) return;
   const int i = idx / n_blb, j = idx - i * n_blb;
-  if (i > j) return;  // upper triangle, mirrored below (c_rigid_obj.cpp:449-452)
+  if (i > j) return;
   const real* rb = r + 3 * (size_t)b * n_blb;
-  if (wall && i == j && rb[3 * i + 2] < (real)0) *below = 1;
-  real B[9];
-  mobility_block(rb + 3 * i, rb + 3 * j, i == j, a, wall != 0, B);
+  const real xi = rb[3 * i], yi = rb[3 * i + 1], zi = rb[3 * i + 2];
+  const real xj = rb[3 * j], yj = rb[3 * j + 1], zj = rb[3 * j + 2];
+  if (WALL && i == j && zi < (real)0) *below = 1;
   const int sz = 3 * n_blb;
   real* Mb = M + (size_t)b * sz * sz;
 #pragma unroll
-  for (int p = 0; p < 3; ++p)
+  for (int q = 0; q < 3; ++q) {
+    real u[3] = {0, 0, 0};
+    pair<real, WALL, true>(C, xi, yi, zi, xj, yj, zj, q == 0 ? (real)1 : (real)0, q == 1 ? (real)1 : (real)0,
+                           q == 2 ? (real)1 : (real)0, (real)2 * zj, (real)4 * zj * zj, u[0], u[1], u[2]);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const real v = B[3 * p + q] * norm;
+    for (int p = 0; p < 3; ++p) {
+      const real v = u[p] * C.out_scale;
       Mb[(size_t)(3 * i + p) * sz + 3 * j + q] = v;
       if (i != j) Mb[(size_t)(3 * j + q) * sz + 3 * i + p] = v;
     }
+  }
 }
 template <typename real>
 cudaError_t pc_block_assemble(const real* r, int count, int n_blb, real a, real eta,
                               bool wall, real* M, int* below, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  const real norm = (real)((real)1.0 / (8.0 * M_PI * (double)eta * (double)a));
+  const PairConsts<real> C = make_pair_consts<real>((double)a, (double)eta);
   dim3 grid((n_blb * n_blb + 255) / 256, count);
-  pc_block_assemble_kernel<real><<<grid, 256, 0, s>>>(r, n_blb, a, norm, wall ? 1 : 0, M, below);
+  if (wall)
+    pc_block_assemble_kernel<real, true><<<grid, 256, 0, s>>>(r, n_blb, C, M, below);
+  else
+    pc_block_assemble_kernel<real, false><<<grid, 256, 0, s>>>(r, n_blb, C, M, below);
   return cudaGetLastError();
 }
 
-// In-place Gauss-Jordan inverse without pivoting (safe for SPD), one CTA per matrix.
+// In-place Gauss-Jordan inverse WITH partial (row) pivoting, one CTA per matrix.  This is the path for
+// body blocks that are NOT positive definite (blobs inside the wall-overlap layer; the reference inverts
+// the same block with Eigen's pivoted Mob.inverse(), c_rigid_obj.cpp:475): at step k the row with the
+// largest |A[i][k]|, i >= k, is swapped into place; the column swaps that undo the permutation are
+// applied in reverse order at the end.  A zero or non-finite pivot raises the flag.
 template <typename real>
-__global__ void pc_block_invert_kernel(real* __restrict__ M, int sz, int* __restrict__ not_spd) {
+__global__ void pc_block_invert_kernel(real* __restrict__ M, int sz, int* __restrict__ singular) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* row = reinterpret_cast<real*>(smem_raw);
   real* col = row + sz;
+  int* perm = reinterpret_cast<int*>(col + sz);
+  __shared__ real s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_piv;
   real* A = M + (size_t)blockIdx.x * sz * sz;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = 0; k < sz; ++k) {
+    // pivot search in column k
+    real best = (real)-1;
+    int bi = k;
+    for (int i = k + threadIdx.x; i < sz; i += blockDim.x) {
+      const real v = fabs(A[(size_t)i * sz + k]);
+      if (v > best) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const real ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      real bv = s_val[0];
+      int bx = s_idx[0];
+      for (int w = 1; w < nw; ++w)
+        if (s_val[w] > bv || (s_val[w] == bv && s_idx[w] < bx)) { bv = s_val[w]; bx = s_idx[w]; }
+      if (!(bv > (real)0) || !isfinite(bv)) *singular = 1;
+      s_piv = bx;
+      perm[k] = bx;
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    if (pr != k) {
+      for (int j = threadIdx.x; j < sz; j += blockDim.x) {
+        const real t = A[(size_t)k * sz + j];
+        A[(size_t)k * sz + j] = A[(size_t)pr * sz + j];
+        A[(size_t)pr * sz + j] = t;
+      }
+      __syncthreads();
+    }
     for (int j = threadIdx.x; j < sz; j += blockDim.x) {
       row[j] = A[(size_t)k * sz + j];
       col[j] = A[(size_t)j * sz + k];
     }
     __syncthreads();
-    const real piv = row[k];
-    if (threadIdx.x == 0 && (piv == (real)0 || !isfinite(piv))) *not_spd = 1;  // singular
-    const real p = (real)1 / piv;
+    const real p = (real)1 / row[k];
     for (int i = wid; i < sz; i += nw) {
       real* Ai = A + (size_t)i * sz;
       if (i == k) {
@@ -447,11 +444,22 @@ __global__ void pc_block_invert_kernel(real* __restrict__ M, int sz, int* __rest
     }
     __syncthreads();
   }
+  for (int k = sz - 1; k >= 0; --k) {  // A^-1 = (P A)^-1 P: undo the row swaps as column swaps, last first
+    const int pr = perm[k];
+    if (pr != k) {
+      for (int i = threadIdx.x; i < sz; i += blockDim.x) {
+        const real t = A[(size_t)i * sz + k];
+        A[(size_t)i * sz + k] = A[(size_t)i * sz + pr];
+        A[(size_t)i * sz + pr] = t;
+      }
+      __syncthreads();
+    }
+  }
 }
 template <typename real>
 cudaError_t pc_block_invert(real* M, int count, int sz, int* not_spd, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
-  const size_t smem = 2 * (size_t)sz * sizeof(real);
+  const size_t smem = 2 * (size_t)sz * sizeof(real) + (size_t)sz * sizeof(int);
   const int threads = sz <= 128 ? 256 : 1024;
   cudaError_t e = cudaFuncSetAttribute(pc_block_invert_kernel<real>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -457,3 +457,41 @@ def test_cuda_path_against_the_live_reference_members(orc, wall, precision):
     check(rel_err(cb.get_config()[0], rb.get_config()[0]), tol_on)
     check(rel_err(cb.get_config()[1], rb.get_config()[1]), tol_on)
     check(rel_err(cb.get_blob_positions(), rb.positions()), 2 * tol_on)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_block_pc_on_indefinite_body_blocks(orc, precision):
+    """case_near_wall has blobs inside the wall-overlap layer (z < a): its body blocks are NOT positive
+    definite (min eigenvalue -1.2), so the block PC takes the pivoted Gauss-Jordan path instead of the
+    Cholesky factors.  The reference inverts the same blocks with Eigen's pivoted inverse()
+    (c_rigid_obj.cpp:475); its LLT of the 6x6 N blocks (:562) has no meaning for an indefinite N, so the
+    comparison is with the exact algebra: apply_PC = inverse of [Mt -K; -K^T 0] (test_PC, :569-587)."""
+    g = load_golden("case_near_wall")
+    a, eta = float(g["a"]), float(g["eta"])
+    cb = _solver(g, precision, block=True)
+    ndt = np.float64 if precision == "double" else np.float32
+    ref = orc.remove_mean(g["cfg"])
+    n_blb, nb = ref.shape[0], g["X"].shape[0]
+    sz = 3 * n_blb
+    r = np.asarray(cb.get_blob_positions(), dtype=np.float64)  # the positions the device placed
+    X = np.asarray(g["X"], dtype=ndt).astype(np.float64)
+    Kd = orc.K_dense(r, X, n_blb)
+    vec = np.asarray(g["vec"], dtype=ndt).astype(np.float64)
+    n3 = sz * nb
+    want = np.empty_like(vec)
+    conds, mins = [], []
+    for b in range(nb):
+        Mb = np.asarray(orc.dense_mobility(r.reshape(-1, 3)[b * n_blb:(b + 1) * n_blb], a, eta, True))
+        mins.append(np.linalg.eigvalsh(0.5 * (Mb + Mb.T)).min())
+        Kb = Kd[sz * b:sz * (b + 1), 6 * b:6 * b + 6]
+        A = np.block([[Mb, -Kb], [-Kb.T, np.zeros((6, 6))]])
+        x = np.linalg.solve(A, np.concatenate([vec[sz * b:sz * (b + 1)], vec[n3 + 6 * b:n3 + 6 * b + 6]]))
+        want[sz * b:sz * (b + 1)] = x[:sz]
+        want[n3 + 6 * b:n3 + 6 * b + 6] = x[sz:]
+        conds.append(np.linalg.cond(A))
+    assert min(mins) < 0  # the point of the case: indefinite body blocks
+    out = cb.apply_PC(vec.astype(ndt))
+    err = rel_err(out, want)
+    print(f"[{precision}] block PC on indefinite blocks: error {err:.3e}, cond(per-body saddle matrix) up to {max(conds):.1e}")
+    check(err, 1e-12 if precision == "double" else 1e-4,
+          f"pivoted block PC vs exact per-body saddle inverse, cond {max(conds):.1e}")
