@@ -457,13 +457,32 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
             pb.ctx.L.rbl_bd_stats(pb.ctx.h, ctypes.byref(l1), ctypes.byref(l2))
             times.append(dt); iters.append(int(it)); lz.append([l1.value, l2.value]); rel.append(float(rr))
         products = (int(pb.ctx.L.rbl_product_count(pb.ctx.h)) - prod0) / max(1, args.bd_steps)
+        # one more step, NOT timed, with the profiling hooks on: where a step's wall clock goes
+        # (a stream sync ends every phase; CUDA events bracket every product kernel)
+        pb.ctx.call("rbl_profile_matvec", 1)
+        pb.ctx.matvec_profile(reset=True)
+        ph = (ctypes.c_double * 6)()
+        pb.ctx.call("rbl_bd_phase_ms", ph, 1)
+        noise = tuple(pb.slice_blobs(rng.standard_normal(n3)) for _ in range(3))
+        t0 = time.perf_counter()
+        pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60,
+                   max_iter=args.bd_gmres_max_iter, lanczos_tol=ltol, lanczos_max_iter=args.bd_lanczos_max_iter)
+        prof_s = time.perf_counter() - t0
+        kms, kn = pb.ctx.matvec_profile(reset=True)
+        pb.ctx.call("rbl_bd_phase_ms", ph, 1)
+        pb.ctx.call("rbl_profile_matvec", 0)
+        profile_step = {"seconds": prof_s, "product_kernel_seconds": kms * kn * 1e-3, "product_kernel_launches": int(kn),
+                        "phase_seconds": dict(zip(["inputs_noise", "lanczos", "rfd", "midpoint", "gmres_incl_pc_build", "evolve_output"],
+                                                  [float(v) * 1e-3 for v in ph])),
+                        "note": "rank 0, untimed extra step with a stream sync after every phase"}
         X, _ = pb.get_config()
         out[precision] = {"seconds_per_step": float(np.mean(times)), "seconds_per_step_min": float(np.min(times)),
                           "seconds_per_step_max": float(np.max(times)), "seconds_each_step": [float(t) for t in times],
                           "gmres_iterations": iters, "lanczos_iterations": lz,
                           "gmres_tol": tol, "lanczos_tol": ltol, "gmres_max_iter": args.bd_gmres_max_iter,
                           "lanczos_max_iter": args.bd_lanczos_max_iter, "relres": rel, "mobility_products_per_step": products,
-                          "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U))}
+                          "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U)),
+                          "profile_step": profile_step}
         pb.close()
     return out
 

@@ -131,6 +131,36 @@ int rbl_set_noise_preconditioner(rbl_ctx* ctx, int mode);
  * body blocks, inverse_err = |G L x - x| / |x| for a fixed pseudo-random x; active = 0 if the
  * context fell back to the plain recurrence.  Rank-local. */
 int rbl_noise_selfcheck(rbl_ctx* ctx, double* factor_err, double* inverse_err, int* active);
+/* ---- random finite differences (unbound members of the reference, :743-863), noise supplied ------
+ * The reference draws W inside each function from a wall-clock seeded generator (:730-741); here the
+ * caller passes it, so every function is deterministic and can be compared with the reference's own
+ * code given the same noise (tests/test_gpu_rfd.py).  delta <= 0 selects the reference's value: 1e-4
+ * for M_RFD / KTinv_RFD (:745,771; 4e-3 in a float context, see rbl_set_rfd_delta), 1e-3 for the
+ * *_from_U forms (:820,844).  n = blobs of the context, n_bod = its bodies.
+ *   rbl_M_RFD          out[3n]    = (M(q+) - M(q-)) W / delta,  q+- = q +- (delta/2) K^-1 W     (:769-796)
+ *   rbl_M_RFD_from_U   out[3n]    = the same with q+- = q +- (delta/2) U, U[6 n_bod]             (:818-840)
+ *   rbl_KT_RFD_from_U  out[6nbod] = (K(q+)^T - K(q-)^T) W / delta, W[3n]                         (:842-863)
+ *   rbl_KTinv_RFD      out[6nbod] = K^T (Kinv(q+)^T - Kinv(q-)^T) W / delta, q+- = q +- (delta/2) W, W[6 n_bod] (:743-767)
+ *   rbl_M_RFD_cfgs     r_plus, r_minus [3n] = blob positions of q +- (delta/2) U                 (:798-816)
+ *   rbl_update_X_Q_out X_out[3 n_bod], Q_out[4 n_bod] = q displaced by U (a displacement), state untouched (:712-728)
+ *   rbl_evolve_RFD     installs q displaced by U and rebuilds K; a built preconditioner is kept   (:880-893)
+ * rbl_M_RFD / rbl_M_RFD_from_U are collective on a partitioned suspension; the others are rank-local. */
+int rbl_M_RFD(rbl_ctx* ctx, const void* W, double delta, void* out);
+int rbl_M_RFD_from_U(rbl_ctx* ctx, const void* U, const void* W, double delta, void* out);
+int rbl_KT_RFD_from_U(rbl_ctx* ctx, const void* U, const void* W, double delta, void* out);
+int rbl_KTinv_RFD(rbl_ctx* ctx, const void* W6, double delta, void* out);
+int rbl_M_RFD_cfgs(rbl_ctx* ctx, const void* U, double delta, void* r_plus, void* r_minus);
+int rbl_update_X_Q_out(rbl_ctx* ctx, const void* U, void* X_out, void* Q_out);
+int rbl_evolve_RFD(rbl_ctx* ctx, const void* U);
+/* RFD step of rbl_bd_step and default of rbl_M_RFD / rbl_KTinv_RFD.  0 restores the defaults: 1e-4 in a
+ * double context (the reference's value), 4e-3 in a float context -- a centred difference quotient in
+ * float is most accurate near eps^(1/3) x (length over which M varies ~ the body radius): rounding
+ * 3e-7 |M W| / delta against truncation ~ (delta/a)^2 / 6. */
+int rbl_set_rfd_delta(rbl_ctx* ctx, double delta);
+/* 1 (default, like the reference's split_rand = true, :150): two Brownian increments per step, c1 = 2 sqrt(kBT/dt),
+ * c2 = sqrt(kBT/dt), BI = c2 (M^{1/2}W1 - M^{1/2}W2) (:943-948).  0: one increment, c1 = c2 = sqrt(2 kBT/dt),
+ * BI = c2 M^{1/2}W1 (:949-953); rbl_bd_step then ignores W2 (may be NULL). */
+int rbl_set_split_rand(rbl_ctx* ctx, int enable);
 /* 1 (default): rbl_bd_step uses the paired Lanczos; 0: two separate single-vector runs */
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable);
 
@@ -253,6 +283,12 @@ int rbl_bd_stats(const rbl_ctx* ctx, int* lanczos_iters_1, int* lanczos_iters_2)
  * the launches since the last reset; enable/disable with rbl_profile_matvec */
 int rbl_profile_matvec(rbl_ctx* ctx, int enable);
 int rbl_matvec_profile(rbl_ctx* ctx, double* avg_ms, int64_t* launches, int reset);
+/* wall clock (ms, accumulated over the rbl_bd_step calls made while rbl_profile_matvec is on; each phase
+ * ends with a stream synchronisation, so never enable it in a timed run) of the six phases of a BD step:
+ * [0] inputs + noise, [1] Lanczos M^{1/2}W (c_rigid_obj.cpp:661-675), [2] random finite difference
+ * (:769-796), [3] midpoint configuration (:954-958), [4] GMRES incl. the preconditioner build,
+ * [5] evolve (:865-878) + output */
+int rbl_bd_phase_ms(rbl_ctx* ctx, double* out6, int reset);
 /* sustained FMA-pipe peak of this precision (TFLOP/s), the roofline denominator */
 int rbl_fma_peak(rbl_ctx* ctx, int iters, double* tflops);
 

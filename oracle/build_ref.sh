@@ -91,7 +91,10 @@ gen_members() { # $1 = real type, $2 = suffix
     awk '/^  SparseM Block_diag_invM\(\)/{on=1} /template <class AVector> void test_PC\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  Vector apply_PC\(const Vector &IN\)/{on=1} /^  DiagM make_damp_mat\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  Vector M_half_W\(\)/{on=1} /Dynamics\/time integration/{on=0} on{print}' "$REF_SRC"
+    awk '/^  Vector KTinv_RFD\(\)/{on=1} /^  Vector M_RFD\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  Vector M_RFD\(\)/{on=1} /template <class AVector> auto M_RFD_cfgs\(/{on=0} on{print}' "$REF_SRC"
+    awk '/template <class AVector> auto M_RFD_cfgs\(/{on=1} /^  void evolve_X_Q\(Vector &U\)/{on=0} on{print}' "$REF_SRC"
+    awk '/^  void evolve_X_Q_RFD\(/{on=1} /^  Vector Test_Mhalf\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  auto RHS_and_Midpoint\(/{on=1} /^  auto get_K\(\)/{on=0} on{print}' "$REF_SRC"
     awk '/^  Quat Q_from_Om\(/{on=1} /^  Vector rand_vector\(/{on=0} on{print}' "$REF_SRC"
     awk '/^  void evolve_X_Q\(Vector &U\)/{on=1} /^  void evolve_X_Q_RFD\(/{on=0} on{print}' "$REF_SRC"
@@ -153,6 +156,50 @@ extern "C" int refm_M_RFD_$2(void *h, const $1 *W, $1 *out) {
   b->injected_noise = {in_$2(W, 3L * b->N_bod * b->N_blb)}; b->noise_pos = 0;
   try { out_$2(b->M_RFD(), out); } catch (const std::runtime_error &) { return 2; }
   return 0;
+}
+// the other random finite differences (:743-767, :798-863) and the RFD-sized configuration updates
+// (:712-728, :880-893), noise injected where the reference draws it
+extern "C" int refm_KTinv_RFD_$2(void *h, const $1 *W6, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  b->injected_noise = {in_$2(W6, 6L * b->N_bod)}; b->noise_pos = 0;
+  try { out_$2(b->KTinv_RFD(), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+extern "C" int refm_M_RFD_from_U_$2(void *h, const $1 *U, const $1 *W, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  V_$2 u = in_$2(U, 6L * b->N_bod), w = in_$2(W, 3L * b->N_bod * b->N_blb);
+  try { out_$2(b->M_RFD_from_U(u, w), out); } catch (const std::runtime_error &) { return 2; }
+  return 0;
+}
+extern "C" int refm_KT_RFD_from_U_$2(void *h, const $1 *U, const $1 *W, $1 *out) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  V_$2 u = in_$2(U, 6L * b->N_bod), w = in_$2(W, 3L * b->N_bod * b->N_blb);
+  out_$2(b->KT_RFD_from_U(u, w), out);
+  return 0;
+}
+extern "C" int refm_M_RFD_cfgs_$2(void *h, const $1 *U, double delta, $1 *rp, $1 *rm) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  V_$2 u = in_$2(U, 6L * b->N_bod);
+  b->injected_noise = {V_$2(3L * b->N_bod * b->N_blb)}; b->noise_pos = 0;  // M_RFD_cfgs draws a W it never uses (:801)
+  auto t = b->M_RFD_cfgs(u, delta);
+  const std::vector<$1> &p = std::get<0>(t), &m = std::get<1>(t);
+  for (size_t i = 0; i < p.size(); ++i) { rp[i] = p[i]; rm[i] = m[i]; }
+  return 0;
+}
+extern "C" int refm_update_X_Q_out_$2(void *h, const $1 *U, $1 *X, $1 *Q) {
+  B_$2 *b = static_cast<B_$2 *>(h);
+  V_$2 u = in_$2(U, 6L * b->N_bod);
+  auto t = b->update_X_Q_out(u);  // (Qout [w x y z], Xout), row-major N_bod x 4 / N_bod x 3
+  const refm_$2::Matrix &Qo = std::get<0>(t), &Xo = std::get<1>(t);
+  for (int j = 0; j < b->N_bod; ++j) {
+    for (int d = 0; d < 4; ++d) Q[4 * j + d] = Qo(j, d);
+    for (int d = 0; d < 3; ++d) X[3 * j + d] = Xo(j, d);
+  }
+  return 0;
+}
+extern "C" int refm_set_split_rand_$2(void *h, int on) { static_cast<B_$2 *>(h)->split_rand = on != 0; return 0; }
+extern "C" int refm_evolve_RFD_$2(void *h, const $1 *U) {
+  B_$2 *b = static_cast<B_$2 *>(h); V_$2 u = in_$2(U, 6L * b->N_bod); b->evolve_X_Q_RFD(u); return 0;
 }
 extern "C" int refm_M_half_W_$2(void *h, const $1 *W, $1 *out) {
   B_$2 *b = static_cast<B_$2 *>(h);

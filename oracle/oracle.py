@@ -104,8 +104,13 @@ def ref_apply_M_lib():
             for name in ("positions", "evolve"):
                 getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp]
             getattr(L, f"refm_RHS_{sfx}").argtypes = [vp, vp, vp, vp, vp, vp, cd, vp]
-            for name in ("K_x_U", "KT_x_Lam", "Kinv_x_V", "KTinv_x_F", "apply_PC", "M_RFD", "M_half_W"):
+            for name in ("K_x_U", "KT_x_Lam", "Kinv_x_V", "KTinv_x_F", "apply_PC", "M_RFD", "M_half_W", "KTinv_RFD"):
                 getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp, vp]
+            for name in ("M_RFD_from_U", "KT_RFD_from_U", "update_X_Q_out"):
+                getattr(L, f"refm_{name}_{sfx}").argtypes = [vp, vp, vp, vp]
+            getattr(L, f"refm_M_RFD_cfgs_{sfx}").argtypes = [vp, vp, cd, vp, vp]
+            getattr(L, f"refm_evolve_RFD_{sfx}").argtypes = [vp, vp]
+            getattr(L, f"refm_set_split_rand_{sfx}").argtypes = [vp, ci]
         _REF_APPLY = L
     return _REF_APPLY
 
@@ -188,6 +193,49 @@ class RefBody:
     def M_RFD(self, W):
         """the reference's M_RFD (:769-796) with ITS rand_vector replaced by the given noise W"""
         return self._mv("M_RFD", W, 3 * self.n_bod * self.n_blb)
+
+    # the remaining random finite differences and RFD-sized configuration updates, noise injected
+    def KTinv_RFD(self, W6):
+        """KTinv_RFD (:743-767) with rand_vector(6 N_bod) = W6"""
+        return self._mv("KTinv_RFD", W6, 6 * self.n_bod)
+
+    def M_RFD_from_U(self, U, W):
+        """M_RFD_from_U (:818-840), delta = 1e-3"""
+        U, W = self._vec(U), self._vec(W)
+        out = np.empty_like(W)
+        self._call("M_RFD_from_U", U.ctypes.data, W.ctypes.data, out.ctypes.data)
+        return out
+
+    def KT_RFD_from_U(self, U, W):
+        """KT_RFD_from_U (:842-863), delta = 1e-3"""
+        U, W = self._vec(U), self._vec(W)
+        out = np.empty(6 * self.n_bod, self.dt_)
+        self._call("KT_RFD_from_U", U.ctypes.data, W.ctypes.data, out.ctypes.data)
+        return out
+
+    def M_RFD_cfgs(self, U, delta):
+        """M_RFD_cfgs (:798-816): blob positions of q +- (delta/2) U"""
+        U = self._vec(U)
+        n3 = 3 * self.n_bod * self.n_blb
+        rp, rm = np.empty(n3, self.dt_), np.empty(n3, self.dt_)
+        self._call("M_RFD_cfgs", U.ctypes.data, float(delta), rp.ctypes.data, rm.ctypes.data)
+        return rp.reshape(-1, 3), rm.reshape(-1, 3)
+
+    def update_X_Q_out(self, U):
+        """update_X_Q_out (:712-728): (X, Q [w x y z]) displaced by U, state untouched"""
+        U = self._vec(U)
+        X, Q = np.empty(3 * self.n_bod, self.dt_), np.empty(4 * self.n_bod, self.dt_)
+        self._call("update_X_Q_out", U.ctypes.data, X.ctypes.data, Q.ctypes.data)
+        return X.reshape(-1, 3), Q.reshape(-1, 4)
+
+    def set_split_rand(self, on):
+        """the class's split_rand member (:150); False selects the single-increment branch (:949-953)"""
+        self._call("set_split_rand", int(bool(on)))
+
+    def evolve_RFD(self, U):
+        """evolve_X_Q_RFD (:880-893)"""
+        U = self._vec(U)
+        self._call("evolve_RFD", U.ctypes.data)
 
     def M_half_W(self, W):
         """the reference's M_half_W (:661-675: chol(B M B) W) with the given noise W"""
@@ -656,7 +704,7 @@ def rfd_M(X, Q, ref_cfg, a, eta, wall, W, delta=1.0e-4):
 
 
 def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta=1.0e-4, noise="symmetric",
-            return_rhs=False):
+            return_rhs=False, split_rand=True):
     """The trapezoidal-slip midpoint step RHS_and_Midpoint sets up (c_rigid_obj.cpp:917-976),
     completed as intended (the reference computes the midpoint configuration but never installs
     it) and evaluated with dense float64 linear algebra:
@@ -666,9 +714,12 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
       [M -K; K^T 0][lam;U] = [slip - kBT RFD - BI ; F_ext] at the midpoint, evolve from q^n.
     Returns (U, X_new, Q_new); with return_rhs the assembled right-hand side and the midpoint
     configuration instead (rhs, X_mid, Q_mid).  noise: "symmetric" (sqrtm), "block_cholesky" (the
-    product path's default) or "cholesky" (the reference's M_half_W)."""
+    product path's default) or "cholesky" (the reference's M_half_W).  split_rand=False: the single-increment
+    branch (:949-953): c1 = c2 = sqrt(2 kBT/dt), BI = c2 M^{1/2}W1, W2 unused."""
     from scipy.linalg import sqrtm
 
+    if W2 is None:
+        W2 = np.zeros_like(np.asarray(W1, dtype=np.float64))
     ref = np.asarray(ref_cfg, dtype=np.float64).reshape(-1, 3)
     n_blb = ref.shape[0]
     X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
@@ -695,8 +746,12 @@ def bd_step(X, Q, ref_cfg, a, eta, dt, kBT, wall, F_ext, slip, W1, W2, Wr, delta
             S = np.real(sqrtm(M))
             mh1, mh2 = S @ W1, S @ W2
         rfd = rfd_M(X, Q, ref, a, eta, wall, Wr, delta)
-        c1, c2 = 2.0 * np.sqrt(kBT / dt), np.sqrt(kBT / dt)
-        rhs_slip -= kBT * rfd + c2 * (mh1 - mh2)
+        if split_rand:
+            c1, c2 = 2.0 * np.sqrt(kBT / dt), np.sqrt(kBT / dt)
+            rhs_slip -= kBT * rfd + c2 * (mh1 - mh2)
+        else:
+            c1 = c2 = np.sqrt(2.0 * kBT / dt)
+            rhs_slip -= kBT * rfd + c2 * mh1
         Xm, Qm = update_X_Q(X, Q, 0.5 * dt * Kinv_apply(c1 * mh1, r, X, Q, ref))
     rm = blob_positions(Xm, Qm, ref)
     Mm = np.asarray(dense_mobility(rm, a, eta, wall))

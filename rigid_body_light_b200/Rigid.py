@@ -189,6 +189,83 @@ class RigidBody:
         return self.cb.bd_step(F_ext.reshape(-1), slip, W1, W2, Wr, float(kBT), tol, restart, max_iter,
                                lanczos_tol, lanczos_max_iter)
 
+    # -- random finite differences: the reference's unbound members (c_rigid_obj.cpp:712-728,743-863,
+    #    880-893) through the C ABI (include/rbl.h), noise supplied by the caller -----------------
+    def _abi(self, name, *args):
+        import ctypes
+
+        from . import _lib
+
+        L = _lib.load()
+        st = getattr(L, name)(ctypes.c_void_p(self.cb.handle()), *args)
+        if st != 0:
+            raise RuntimeError(L.rbl_last_error(ctypes.c_void_p(self.cb.handle())).decode())
+
+    def _real(self):
+        return np.float64 if self.precision == "double" else np.float32
+
+    def _vec(self, x, n, name, what):
+        x = np.asarray(x)
+        self._need(x, n, name, what)
+        return np.ascontiguousarray(x.reshape(-1), dtype=self._real())
+
+    def M_RFD(self, W, delta=0.0, U=None):
+        """(M(q+) - M(q-)) W / delta with q+- = q +- (delta/2) K^-1 W (M_RFD, :769-796), or with
+        q+- = q +- (delta/2) U when ``U`` is given (M_RFD_from_U, :818-840).  delta <= 0: the reference's."""
+        W = self._vec(W, 3 * self.total_blobs, "W", "3*N_blobs")
+        out = np.empty_like(W)
+        if U is None:
+            self._abi("rbl_M_RFD", W.ctypes.data, float(delta), out.ctypes.data)
+        else:
+            U = self._vec(U, 6 * self.N_bodies, "U", "6*N_bodies")
+            self._abi("rbl_M_RFD_from_U", U.ctypes.data, W.ctypes.data, float(delta), out.ctypes.data)
+        return out
+
+    def KT_RFD(self, U, W, delta=0.0):
+        """(K(q+)^T - K(q-)^T) W / delta, q+- = q +- (delta/2) U (KT_RFD_from_U, :842-863)."""
+        U = self._vec(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        W = self._vec(W, 3 * self.total_blobs, "W", "3*N_blobs")
+        out = np.empty(6 * self.N_bodies, dtype=self._real())
+        self._abi("rbl_KT_RFD_from_U", U.ctypes.data, W.ctypes.data, float(delta), out.ctypes.data)
+        return out
+
+    def KTinv_RFD(self, W6, delta=0.0):
+        """K^T (Kinv(q+)^T - Kinv(q-)^T) W / delta, q+- = q +- (delta/2) W (KTinv_RFD, :743-767)."""
+        W6 = self._vec(W6, 6 * self.N_bodies, "W", "6*N_bodies")
+        out = np.empty_like(W6)
+        self._abi("rbl_KTinv_RFD", W6.ctypes.data, float(delta), out.ctypes.data)
+        return out
+
+    def M_RFD_cfgs(self, U, delta):
+        """Blob positions of q +- (delta/2) U (M_RFD_cfgs, :798-816): (r_plus, r_minus), each (N_blobs, 3)."""
+        U = self._vec(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        rp = np.empty(3 * self.total_blobs, dtype=self._real())
+        rm = np.empty_like(rp)
+        self._abi("rbl_M_RFD_cfgs", U.ctypes.data, float(delta), rp.ctypes.data, rm.ctypes.data)
+        return rp.reshape(-1, 3), rm.reshape(-1, 3)
+
+    def displaced_config(self, U):
+        """(X, Q) displaced by the displacement U, state untouched (update_X_Q_out, :712-728)."""
+        U = self._vec(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        X = np.empty(3 * self.N_bodies, dtype=self._real())
+        Q = np.empty(4 * self.N_bodies, dtype=self._real())
+        self._abi("rbl_update_X_Q_out", U.ctypes.data, X.ctypes.data, Q.ctypes.data)
+        return X.reshape(-1, 3), Q.reshape(-1, 4)
+
+    def evolve_rigid_bodies_RFD(self, U):
+        """Install the configuration displaced by U (a displacement) and rebuild K; a built preconditioner
+        is kept (evolve_X_Q_RFD, :880-893)."""
+        U = self._vec(U, 6 * self.N_bodies, "U", "6*N_bodies")
+        self._abi("rbl_evolve_RFD", U.ctypes.data)
+
+    def set_rfd_delta(self, delta):
+        """RFD step of ``bd_step`` / default of ``M_RFD``; 0 restores 1e-4 (double) / 4e-3 (float)."""
+        self._abi("rbl_set_rfd_delta", float(delta))
+
+    def set_split_rand(self, enable):
+        """True (default): two Brownian increments per step (:943-948); False: one (:949-953)."""
+        self._abi("rbl_set_split_rand", int(bool(enable)))
+
     # -- size checks (RuntimeError like Rigid.py:117-135) -------------------------------
     def _need(self, vec, n, name, what):
         if vec.size != n:

@@ -95,6 +95,16 @@ SYMBOLS = {
     "rbl_sym_variant_info": (_i, [_vp, _i, _pi, _pi]),
     "rbl_set_sym_variant": (_i, [_vp, _i]),
     "rbl_sym_variant_chunk": (_i, [_vp, _i]),
+    "rbl_bd_phase_ms": (_i, [_vp, _pd, _i]),
+    "rbl_M_RFD": (_i, [_vp, _vp, _d, _vp]),
+    "rbl_M_RFD_from_U": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "rbl_KT_RFD_from_U": (_i, [_vp, _vp, _vp, _d, _vp]),
+    "rbl_KTinv_RFD": (_i, [_vp, _vp, _d, _vp]),
+    "rbl_M_RFD_cfgs": (_i, [_vp, _vp, _d, _vp, _vp]),
+    "rbl_update_X_Q_out": (_i, [_vp, _vp, _vp, _vp]),
+    "rbl_evolve_RFD": (_i, [_vp, _vp]),
+    "rbl_set_rfd_delta": (_i, [_vp, _d]),
+    "rbl_set_split_rand": (_i, [_vp, _i]),
     "rbl_launch_count": (_i64, [_vp]),
     "rbl_product_count": (_i64, [_vp]),
     "rbl_bd_stats": (_i, [_vp, _pi, _pi]),

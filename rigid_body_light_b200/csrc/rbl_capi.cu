@@ -5,6 +5,7 @@
 // X_n/Q_n, the K data (here: cached blob positions) and the lazily built preconditioner
 // -- but resident in HBM.  Host-pointer entry points stage through device buffers and
 // call the same device path the rbl_dev_* entry points expose.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -89,6 +90,12 @@ struct rbl_ctx {
   virtual int bd_step_seeded(const void* F_ext, const void* slip, unsigned long long seed, unsigned long long step,
                              double kBT, double tol, int restart, int max_iter, double ltol, int lmax, void* U_out,
                              int* iters, double* relres) = 0;
+  virtual int M_RFD(const void* U6, const void* W, double delta, void* out) = 0;
+  virtual int KT_RFD(const void* U6, const void* W, double delta, void* out6) = 0;
+  virtual int KTinv_RFD(const void* W6, double delta, void* out6) = 0;
+  virtual int RFD_cfgs(const void* U6, double delta, void* r_plus, void* r_minus) = 0;
+  virtual int displaced_config(const void* U6, void* X_out, void* Q_out) = 0;
+  virtual int evolve_RFD(const void* U6) = 0;
   virtual int normals(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n, void* W1,
                       void* W2, void* Wr, bool dev) = 0;
   virtual int sync() = 0;
@@ -122,10 +129,15 @@ struct rbl_ctx {
   // 0: symmetric square root everywhere; 1 (default): block-Cholesky preconditioned noise inside
   // rbl_bd_step; 2: also in rbl_lanczos_sqrt / rbl_lanczos_sqrt2 (they then return L (G A G^T)^{1/2} W)
   int noise_mode = 1;
+  bool split_rand = true;    // BD step: two Brownian increments W1, W2 (c_rigid_obj.cpp:150,943-953); false: one
+  double rfd_delta = 0;      // <= 0: default of the precision (1e-4 double like :771, 4e-3 float)
   bool pair_lanczos = true;  // BD step: M^{1/2}W_1 and M^{1/2}W_2 in lockstep over the two-right-hand-side product
   int mode = 0;  // 0: symmetric kernel when targets == sources; 1: ordered kernel always
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  // wall-clock per phase of the last rbl_bd_step calls while profiling is on (ms, accumulated):
+  // 0 inputs+noise, 1 Lanczos, 2 RFD, 3 midpoint configuration, 4 GMRES (with the PC build), 5 evolve+output
+  double bd_phase_ms[6] = {0, 0, 0, 0, 0, 0};
   DevBuf flush_buf;
 };
 
@@ -180,6 +192,20 @@ struct Ctx final : rbl_ctx {
   DevBuf d_NL, d_NG, d_nt1, d_nt2, d_nu1, d_nu2;
   bool noise_set = false, noise_ok = false, noise_shared = false, noise_shared_ready = false;
   bool r_all_valid = false;
+  // Packed records and tile boxes are a function of the POSITIONS only: inside the Krylov drivers the
+  // configuration is fixed while the force vector changes every product, so a product on positions
+  // the records were already packed from only rewrites the three force words of each record
+  // (repack_forces) and skips both tile-box launches.  `gen` identifies a position set: cfg_gen for the
+  // context's own blob positions (d_r), r_all_gen for the all-gathered ones; 0 = unknown (always repack).
+  unsigned long long gen_counter = 0, cfg_gen = 0, r_all_gen = 0;
+  struct RecState {
+    unsigned long long gen = 0;
+    int n = 0, tile = 0;
+    const void* buf = nullptr;
+    bool matches(unsigned long long g, int n_, int tile_, const void* b) const {
+      return g != 0 && g == gen && n_ == n && tile_ == tile && b == buf;
+    }
+  } rec1_state, rec2_state;
 
   enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, FLAG_NOISE = 3, N_FLAGS = 4 };
 
@@ -303,6 +329,7 @@ struct Ctx final : rbl_ctx {
                                         d_flags.as<int>() + FLAG_SINGULAR, stream));
     r_valid = true;
     r_all_valid = false;
+    cfg_gen = ++gen_counter;
     noise_set = false;  // the per-body factors follow the blob positions
     return RBL_OK;
   }
@@ -409,6 +436,9 @@ struct Ctx final : rbl_ctx {
 
   // symmetric kernel: share `part` of `n_parts` of the unordered-pair work; out = partial product
   int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) override {
+    return apply_M_part_gen(F, r, n, part, n_parts, out, 0);
+  }
+  int apply_M_part_gen(const void* F, const void* r, int n, int part, int n_parts, void* out, unsigned long long gen) {
     if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
     if (n < 0 || n_parts < 1 || part < 0 || part >= n_parts) return fail(RBL_ERR_INVALID, "apply_M_part: bad share");
     if (n == 0) return RBL_OK;
@@ -420,10 +450,17 @@ struct Ctx final : rbl_ctx {
     CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
     CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
     CK(d_raw.ensure(3 * n_pad * sizeof(real)));
-    LAUNCH(1, rbl::pack_records<real>(static_cast<const real*>(r), static_cast<const real*>(F), n, (int)n_pad, wall,
-                                      (real)a, d_rec.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
-    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream));
-    LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream));
+    if (rec1_state.matches(gen, n, A.plan.tgt_tile, d_rec.p)) {
+      LAUNCH(1, rbl::repack_forces<real>(static_cast<const real*>(F), n, wall, (real)a, d_rec.as<real>(),
+                                         d_flags.as<int>() + FLAG_BELOW, stream));
+    } else {
+      LAUNCH(1, rbl::pack_records<real>(static_cast<const real*>(r), static_cast<const real*>(F), n, (int)n_pad, wall,
+                                        (real)a, d_rec.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+      LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream));
+      LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream));
+      rec1_state = {gen, n, A.plan.tgt_tile, d_rec.p};
+      rec2_state.gen = 0;  // the two kernels share the tile-box buffers
+    }
     A.rec = d_rec.as<real>();
     A.box_src = d_box_src.as<float>();
     A.box_tgt = d_box_tgt.as<float>();
@@ -456,7 +493,7 @@ struct Ctx final : rbl_ctx {
     if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
     if (n < 0 || t0 < 0 || nt < 0 || t0 + nt > n) return fail(RBL_ERR_INVALID, "apply_M: bad target range");
     if (n == 0 || nt == 0) return RBL_OK;
-    if (mode == 0 && t0 == 0 && nt == n) return dev_apply_M_part(F, r, n, 0, 1, out);
+    if (mode == 0 && t0 == 0 && nt == n) return apply_M_part_gen(F, r, n, 0, 1, out, 0);
     const int v = pick_variant(nt);
     rbl::MatvecArgs<real> A;
     CK(rbl::matvec_plan<real>(v, wall, n, t0, nt, sm_count, &A.plan));
@@ -465,6 +502,7 @@ struct Ctx final : rbl_ctx {
     CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
     CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
     CK(d_scratch.ensure(2 * (size_t)A.plan.grid * 3 * A.plan.tgt_tile * sizeof(real)));
+    rec1_state.gen = rec2_state.gen = 0;  // this path repacks the shared record and box buffers
     LAUNCH(1, rbl::pack_records<real>(static_cast<const real*>(r), static_cast<const real*>(F), n, (int)n_pad, wall,
                                       (real)a, d_rec.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
     LAUNCH(1, rbl::tile_boxes<real>(d_rec.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream));
@@ -538,7 +576,10 @@ struct Ctx final : rbl_ctx {
   // reduce-scatter of the partial products (each rank keeps the sum of its own rows).
   int prod_M(const real* F_local, const real* r_local, bool r_is_config, real* out_local) {
     const int nl = (int)N();
-    if (!comm) return dev_apply_M(F_local, r_local, nl, 0, nl, out_local);
+    if (!comm) {
+      if (mode == 0) return apply_M_part_gen(F_local, r_local, nl, 0, 1, out_local, r_is_config ? cfg_gen : 0);
+      return dev_apply_M(F_local, r_local, nl, 0, nl, out_local);
+    }
     const size_t n3_all = 3 * (size_t)comm->n_all;
     const void* before = d_r_all.p;
     CK(d_r_all.ensure(2 * n3_all * sizeof(real)));  // [configuration ; scratch positions (RFD)]
@@ -550,27 +591,30 @@ struct Ctx final : rbl_ctx {
       if (!r_all_valid) {
         NK(comm->allgatherv<real>(r_local, r_all, 3, stream));
         r_all_valid = true;
+        r_all_gen = ++gen_counter;
       }
     } else {
       r_all += n3_all;
       NK(comm->allgatherv<real>(r_local, r_all, 3, stream));
     }
     NK(comm->allgatherv<real>(F_local, d_lam_all.as<real>(), 3, stream));
-    RET(dev_apply_M_part(d_lam_all.p, r_all, (int)comm->n_all, comm->rank, comm->world, d_mbuf.p));
+    RET(apply_M_part_gen(d_lam_all.p, r_all, (int)comm->n_all, comm->rank, comm->world, d_mbuf.p,
+                         r_is_config ? r_all_gen : 0));
     NK(comm->reduce_scatterv<real>(d_mbuf.as<real>(), out_local, 3, stream));
     return RBL_OK;
   }
-  // d_dots[0..m) = <V_i, w> summed over the ranks
-  int gdots(const real* V, size_t ld, int m, const real* w, size_t n) {
-    LAUNCH(2, rbl::multi_dot<real>(V, ld, m, w, n, d_partial.as<real>(), d_dots.as<real>(), stream));
-    if (comm) NK(comm->allreduce_sum<real>(d_dots.as<real>(), (size_t)m, stream));
+  // d_dots[slot .. slot+m) = <V_i, w> summed over the ranks (results stay on the device; the Krylov
+  // drivers read every scalar of an iteration back with ONE copy, read_slots)
+  int gdots(const real* V, size_t ld, int m, const real* w, size_t n, int slot = 0) {
+    LAUNCH(2, rbl::multi_dot<real>(V, ld, m, w, n, d_partial.as<real>(), d_dots.as<real>() + slot, stream));
+    if (comm) NK(comm->allreduce_sum<real>(d_dots.as<real>() + slot, (size_t)m, stream));
     return RBL_OK;
   }
 
 
   // ---- two right-hand sides per pass (rpy_matvec_sym2_kernel) ----------------------------------
   int dev_apply_M2_part(const void* F1, const void* F2, const void* r, int n, int part, int n_parts, void* out1,
-                        void* out2) {
+                        void* out2, unsigned long long gen = 0) {
     if (!params_set) return fail(RBL_ERR_STATE, "apply_M before setParameters");
     if (n < 0 || n_parts < 1 || part < 0 || part >= n_parts) return fail(RBL_ERR_INVALID, "apply_M2_part: bad share");
     if (n == 0) return RBL_OK;
@@ -582,10 +626,17 @@ struct Ctx final : rbl_ctx {
     CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
     CK(d_box_tgt.ensure(6 * (size_t)A.plan.n_tgt_tiles * sizeof(float)));
     CK(d_raw2.ensure(2 * 3 * n_pad * sizeof(real)));
-    LAUNCH(1, rbl::pack_records2<real>(static_cast<const real*>(r), static_cast<const real*>(F1), static_cast<const real*>(F2),
-                                       n, (int)n_pad, wall, (real)a, d_rec2.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
-    LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream, rbl::kRec2Reals));
-    LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream, rbl::kRec2Reals));
+    if (rec2_state.matches(gen, n, A.plan.tgt_tile, d_rec2.p)) {
+      LAUNCH(1, rbl::repack_forces2<real>(static_cast<const real*>(F1), static_cast<const real*>(F2), n, wall, (real)a,
+                                          d_rec2.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+    } else {
+      LAUNCH(1, rbl::pack_records2<real>(static_cast<const real*>(r), static_cast<const real*>(F1), static_cast<const real*>(F2),
+                                         n, (int)n_pad, wall, (real)a, d_rec2.as<real>(), d_flags.as<int>() + FLAG_BELOW, stream));
+      LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, (int)n_pad, rbl::kSrcTile, d_box_src.as<float>(), stream, rbl::kRec2Reals));
+      LAUNCH(1, rbl::tile_boxes<real>(d_rec2.as<real>(), 0, n, A.plan.tgt_tile, d_box_tgt.as<float>(), stream, rbl::kRec2Reals));
+      rec2_state = {gen, n, A.plan.tgt_tile, d_rec2.p};
+      rec1_state.gen = 0;  // the two kernels share the tile-box buffers
+    }
     A.rec = d_rec2.as<real>();
     A.box_src = d_box_src.as<float>();
     A.box_tgt = d_box_tgt.as<float>();
@@ -607,7 +658,7 @@ struct Ctx final : rbl_ctx {
   // out_k_local = rows of this rank of B M B F_k (k = 1, 2) at the cached configuration
   int prod_M2(const real* F1_local, const real* F2_local, real* out1_local, real* out2_local) {
     const int nl = (int)N();
-    if (!comm) return dev_apply_M2_part(F1_local, F2_local, d_r.p, nl, 0, 1, out1_local, out2_local);
+    if (!comm) return dev_apply_M2_part(F1_local, F2_local, d_r.p, nl, 0, 1, out1_local, out2_local, cfg_gen);
     const size_t n3_all = 3 * (size_t)comm->n_all;
     const void* before = d_r_all.p;
     CK(d_r_all.ensure(2 * n3_all * sizeof(real)));
@@ -617,12 +668,14 @@ struct Ctx final : rbl_ctx {
     if (!r_all_valid) {
       NK(comm->allgatherv<real>(d_r.as<real>(), d_r_all.as<real>(), 3, stream));
       r_all_valid = true;
+      r_all_gen = ++gen_counter;
     }
     real* lam = d_lam_all.as<real>();
     real* mb = d_mbuf.as<real>();
     NK(comm->allgatherv<real>(F1_local, lam, 3, stream));
     NK(comm->allgatherv<real>(F2_local, lam + n3_all, 3, stream));
-    RET(dev_apply_M2_part(lam, lam + n3_all, d_r_all.p, (int)comm->n_all, comm->rank, comm->world, mb, mb + n3_all));
+    RET(dev_apply_M2_part(lam, lam + n3_all, d_r_all.p, (int)comm->n_all, comm->rank, comm->world, mb, mb + n3_all,
+                          r_all_gen));
     NK(comm->reduce_scatterv<real>(mb, out1_local, 3, stream));
     NK(comm->reduce_scatterv<real>(mb + n3_all, out2_local, 3, stream));
     return RBL_OK;
@@ -920,11 +973,12 @@ struct Ctx final : rbl_ctx {
     CK(d_tmp.ensure(n * sizeof(real)));
     CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
     CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
-    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(3 * (m + 2)) * sizeof(real)));
     real* V = d_V.as<real>();
     real* w = d_w.as<real>();
     real* z = d_z.as<real>();
     real* tmp = d_tmp.as<real>();
+    const int slot2 = m + 2, slotn = 2 * (m + 2);  // second Gram-Schmidt pass, squared norm
     CK(cudaMemsetAsync(xs, 0, n * sizeof(real), stream));
     double bnorm = 0;
     RET(dev_norm(b, n, &bnorm));
@@ -961,18 +1015,19 @@ struct Ctx final : rbl_ctx {
         LAUNCH(1, rbl::flip_tail<real>(V + (size_t)j * n, n_head, n, tmp, stream));
         RET(dev_pc(tmp, z));
         RET(dev_saddle(z, w));
-        // classical Gram-Schmidt, twice (one device->host read per pass)
+        // classical Gram-Schmidt, twice; coefficients, the norm and the normalisation of v_{j+1} stay
+        // on the device: ONE device->host read per iteration (for the Givens update and the stopping test)
         std::fill(H.begin() + (size_t)j * (m + 1), H.begin() + (size_t)(j + 1) * (m + 1), 0.0);
-        for (int pass = 0; pass < 2; ++pass) {
-          RET(gdots(V, n, j + 1, w, n));
-          LAUNCH(1, rbl::multi_axpy<real>(V, n, j + 1, d_dots.as<real>(), (real)-1, w, n, stream));
-          RET(read_scalars(d_dots.as<real>(), j + 1, hcol));
-          for (int i = 0; i <= j; ++i) H[(size_t)j * (m + 1) + i] += hcol[i];
-        }
-        double hn = 0;
-        RET(dev_norm(w, n, &hn));
+        RET(gdots(V, n, j + 1, w, n, 0));
+        LAUNCH(1, rbl::multi_axpy<real>(V, n, j + 1, d_dots.as<real>(), (real)-1, w, n, stream));
+        RET(gdots(V, n, j + 1, w, n, slot2));
+        LAUNCH(1, rbl::multi_axpy<real>(V, n, j + 1, d_dots.as<real>() + slot2, (real)-1, w, n, stream));
+        RET(gdots(w, n, 1, w, n, slotn));
+        LAUNCH(1, rbl::scale_by_inv_sqrt<real>(w, d_dots.as<real>() + slotn, V + (size_t)(j + 1) * n, n, stream));
+        RET(read_scalars(d_dots.as<real>(), slotn + 1, hcol));
+        for (int i = 0; i <= j; ++i) H[(size_t)j * (m + 1) + i] = hcol[i] + hcol[slot2 + i];
+        const double hn = std::sqrt(std::max(hcol[slotn], 0.0));
         H[(size_t)j * (m + 1) + j + 1] = hn;
-        if (hn > 0) LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / hn), V + (size_t)(j + 1) * n, n, false, stream));
         // Givens
         double* h = &H[(size_t)j * (m + 1)];
         for (int i = 0; i < j; ++i) {
@@ -1075,7 +1130,7 @@ struct Ctx final : rbl_ctx {
     CK(d_w.ensure(n * sizeof(real)));
     CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
     CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
-    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(3 * (m + 4)) * sizeof(real)));
     real* V = d_V.as<real>();
     real* w = d_w.as<real>();
     LAUNCH(1, rbl::scale_copy<real>(dW, (real)1, w, n, false, stream));
@@ -1099,15 +1154,17 @@ struct Ctx final : rbl_ctx {
         RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
       }
       if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-beta[k - 1]), w, n, true, stream));
-      RET(gdots(V + (size_t)k * n, n, 1, w, n));
-      RET(read_scalars(d_dots.as<real>(), 1, s));
+      // alpha_k, the full reorthogonalisation (keeps the basis orthonormal in fp32 too), beta_k^2 and the
+      // normalised v_{k+1} are all computed on the device: ONE device->host read per iteration
+      RET(gdots(V + (size_t)k * n, n, 1, w, n, 0));
+      LAUNCH(1, rbl::multi_axpy<real>(V + (size_t)k * n, n, 1, d_dots.as<real>(), (real)-1, w, n, stream));
+      RET(gdots(V, n, k + 1, w, n, 2));
+      LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>() + 2, (real)-1, w, n, stream));
+      RET(gdots(w, n, 1, w, n, 1));
+      LAUNCH(1, rbl::scale_by_inv_sqrt<real>(w, d_dots.as<real>() + 1, V + (size_t)(k + 1) * n, n, stream));
+      RET(read_scalars(d_dots.as<real>(), 2, s));
       alpha.push_back(s[0]);
-      LAUNCH(1, rbl::scale_copy<real>(V + (size_t)k * n, (real)(-s[0]), w, n, true, stream));
-      // full reorthogonalisation (keeps the basis orthonormal in fp32 too)
-      RET(gdots(V, n, k + 1, w, n));
-      LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>(), (real)-1, w, n, stream));
-      double bn = 0;
-      RET(dev_norm(w, n, &bn));
+      const double bn = std::sqrt(std::max(s[1], 0.0));
       ++k;
       // y = ||W|| T_k^{1/2} e_1
       std::vector<double> T((size_t)k * k, 0.0), Z;
@@ -1131,8 +1188,7 @@ struct Ctx final : rbl_ctx {
       y_prev = y;
       const bool converged = k > 1 && std::sqrt(diff) <= tol * std::sqrt(nrm);
       if (converged || bn <= 1e-14 * wnorm || k == m) break;
-      beta.push_back(bn);
-      LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / bn), V + (size_t)k * n, n, false, stream));
+      beta.push_back(bn);  // v_k = w / beta is already in place
     }
     std::vector<real> coef(k);
     for (int i = 0; i < k; ++i) coef[i] = (real)y[i];
@@ -1341,7 +1397,8 @@ struct Ctx final : rbl_ctx {
     CK(d_w2.ensure(n * sizeof(real)));
     CK(d_partial.ensure((size_t)(m + 2) * rbl::kDotBlocks * sizeof(real)));
     CK(d_coef.ensure((size_t)(m + 2) * sizeof(real)));
-    CK(d_dots.ensure((size_t)(m + 2) * sizeof(real)));
+    CK(d_dots.ensure((size_t)(3 * (m + 4)) * sizeof(real)));
+    const int slot_stride = m + 4;  // per recurrence: [alpha, beta^2, reorthogonalisation coefficients ...]
     struct Rec {
       real* V; real* w; const real* W; real* out;
       std::vector<double> alpha, beta, y_prev, y;
@@ -1374,20 +1431,30 @@ struct Ctx final : rbl_ctx {
       } else {
         RET(prod_M2(v0, v1, R[0].w, R[1].w));
       }
-      for (auto& q : R) {
+      // device side of both recurrences first (alpha, reorthogonalisation, beta^2, normalised next
+      // basis vector), then ONE device->host read for the two of them
+      for (int r = 0; r < 2; ++r) {
+        auto& q = R[r];
         if (q.done) continue;
-        const int k = q.k;
+        const int k = q.k, base = r * slot_stride;
         real* V = q.V;
         real* w = q.w;
+        real* dd = d_dots.as<real>() + base;
         if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-q.beta[k - 1]), w, n, true, stream));
-        RET(gdots(V + (size_t)k * n, n, 1, w, n));
-        RET(read_scalars(d_dots.as<real>(), 1, s));
-        q.alpha.push_back(s[0]);
-        LAUNCH(1, rbl::scale_copy<real>(V + (size_t)k * n, (real)(-s[0]), w, n, true, stream));
-        RET(gdots(V, n, k + 1, w, n));
-        LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, d_dots.as<real>(), (real)-1, w, n, stream));
-        double bn = 0;
-        RET(dev_norm(w, n, &bn));
+        RET(gdots(V + (size_t)k * n, n, 1, w, n, base));
+        LAUNCH(1, rbl::multi_axpy<real>(V + (size_t)k * n, n, 1, dd, (real)-1, w, n, stream));
+        RET(gdots(V, n, k + 1, w, n, base + 2));
+        LAUNCH(1, rbl::multi_axpy<real>(V, n, k + 1, dd + 2, (real)-1, w, n, stream));
+        RET(gdots(w, n, 1, w, n, base + 1));
+        LAUNCH(1, rbl::scale_by_inv_sqrt<real>(w, dd + 1, V + (size_t)(k + 1) * n, n, stream));
+      }
+      RET(read_scalars(d_dots.as<real>(), slot_stride + 2, s));
+      for (int r = 0; r < 2; ++r) {
+        auto& q = R[r];
+        if (q.done) continue;
+        const int k = q.k;
+        q.alpha.push_back(s[r * slot_stride]);
+        const double bn = std::sqrt(std::max(s[r * slot_stride + 1], 0.0));
         q.k = k + 1;
         lanczos_coeffs(q.alpha, q.beta, q.k, q.wnorm, q.y);
         double diff = 0, nrm = 0;
@@ -1402,8 +1469,7 @@ struct Ctx final : rbl_ctx {
           q.done = true;
           continue;
         }
-        q.beta.push_back(bn);
-        LAUNCH(1, rbl::scale_copy<real>(w, (real)(1.0 / bn), V + (size_t)q.k * n, n, false, stream));
+        q.beta.push_back(bn);  // v_k = w / beta is already in place
       }
     }
     for (int r = 0; r < 2; ++r) {
@@ -1428,11 +1494,148 @@ struct Ctx final : rbl_ctx {
     LAUNCH(1, rbl::ktk_inv_apply<real>(d_S.as<real>(), n_bod, n_blb, out6, stream));
     return RBL_OK;
   }
+  // ---- random finite differences (c_rigid_obj.cpp:743-863), deterministic given the noise -------
+  // delta: the reference hard-wires 1e-4 (M_RFD, KTinv_RFD) and 1e-3 (the *_from_U forms) in whatever
+  // precision it was compiled for.  In float a centred difference quotient of M(q) W is best near
+  // eps^(1/3) * (length scale of M's variation ~ body radius 1) ~ 4e-3: rounding 3e-7 |M W| / delta
+  // against truncation (delta / a)^2 / 6; that is the float default.  rbl_set_rfd_delta overrides both.
+  double default_delta() const { return rfd_delta > 0 ? rfd_delta : (sizeof(real) == 8 ? 1.0e-4 : 4.0e-3); }
+  int rfd_buffers() {
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod;
+    for (DevBuf* b : {&d_rp, &d_t1, &d_t2, &d_rfd, &d_wr}) CK(b->ensure(n3 * sizeof(real)));
+    CK(d_uom.ensure(n6 * sizeof(real)));
+    CK(d_Xp.ensure(3 * (size_t)n_bod * sizeof(real)));
+    CK(d_Qp.ensure(4 * (size_t)n_bod * sizeof(real)));
+    return RBL_OK;
+  }
+  // (X', Q') = configuration displaced by scale * U (update_X_Q, :691-710) and its blob positions
+  int displace(const real* U6, double scale, real* rp) {
+    LAUNCH(1, rbl::integrate<real>(U6, (real)scale, n_bod, d_X.as<real>(), d_Q.as<real>(), d_Xp.as<real>(),
+                                   d_Qp.as<real>(), stream));
+    if (rp)
+      LAUNCH(1, rbl::place_blobs<real>(d_Xp.as<real>(), d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb, rp, stream));
+    return RBL_OK;
+  }
+  // out = (M(q+) - M(q-)) W / delta with q+- = q +- (delta/2) U   (M_RFD_from_U :818-840; M_RFD :769-796 with
+  // U = K^-1 W).  All pointers on the device; collective in partitioned mode.
+  int dev_M_RFD(const real* U6, const real* W, double delta, real* out) {
+    const size_t n3 = 3 * (size_t)N();
+    real* Mpm[2] = {d_t1.as<real>(), d_t2.as<real>()};
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      RET(displace(U6, (sgn ? -0.5 : 0.5) * delta, d_rp.as<real>()));
+      RET(prod_M(W, d_rp.as<real>(), false, Mpm[sgn]));
+    }
+    LAUNCH(1, rbl::scale_copy<real>(d_t1.as<real>(), (real)(1.0 / delta), out, n3, false, stream));
+    LAUNCH(1, rbl::scale_copy<real>(d_t2.as<real>(), (real)(-1.0 / delta), out, n3, true, stream));
+    return RBL_OK;
+  }
+  int M_RFD(const void* U6, const void* W, double delta, void* out) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!W || !out) return fail(RBL_ERR_INVALID, "M_RFD: W and out are required");
+    RET(need_K());
+    RET(rfd_buffers());
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod;
+    if (!(delta > 0)) delta = U6 ? (rfd_delta > 0 ? rfd_delta : 1.0e-3) : default_delta();  // :771 / :820
+    RET(h2d(d_wr.p, W, n3 * sizeof(real)));
+    if (U6) RET(h2d(d_uom.p, U6, n6 * sizeof(real)));
+    else RET(kinv_dev(d_wr.as<real>(), d_uom.as<real>()));  // UOM = Kinv * W  (:776)
+    RET(dev_M_RFD(d_uom.as<real>(), d_wr.as<real>(), delta, d_rfd.as<real>()));
+    RET(d2h(out, d_rfd.p, n3 * sizeof(real)));
+    return csync();
+  }
+  // out = (K(q+)^T - K(q-)^T) W / delta   (KT_RFD_from_U, :842-863)
+  int KT_RFD(const void* U6, const void* W, double delta, void* out6) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!U6 || !W || !out6) return fail(RBL_ERR_INVALID, "KT_RFD_from_U: U, W and out are required");
+    RET(need_K());
+    RET(rfd_buffers());
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod;
+    if (!(delta > 0)) delta = rfd_delta > 0 ? rfd_delta : 1.0e-3;  // :844
+    CK(d_in0.ensure(2 * n6 * sizeof(real)));
+    RET(h2d(d_wr.p, W, n3 * sizeof(real)));
+    RET(h2d(d_uom.p, U6, n6 * sizeof(real)));
+    real* pm = d_in0.as<real>();
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      RET(displace(d_uom.as<real>(), (sgn ? -0.5 : 0.5) * delta, d_rp.as<real>()));
+      LAUNCH(1, rbl::kt_dot<real>(d_wr.as<real>(), d_rp.as<real>(), d_Xp.as<real>(), n_bod, n_blb, pm + sgn * n6, stream));
+    }
+    LAUNCH(1, rbl::scale_copy<real>(pm, (real)(1.0 / delta), pm, n6, false, stream));
+    LAUNCH(1, rbl::scale_copy<real>(pm + n6, (real)(-1.0 / delta), pm, n6, true, stream));
+    RET(d2h(out6, pm, n6 * sizeof(real)));
+    return sync();
+  }
+  // out = K^T (Kinv(q+)^T - Kinv(q-)^T) W / delta with q+- = q +- (delta/2) W   (KTinv_RFD, :743-767)
+  int KTinv_RFD(const void* W6, double delta, void* out6) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!W6 || !out6) return fail(RBL_ERR_INVALID, "KTinv_RFD: W and out are required");
+    RET(need_K());
+    RET(rfd_buffers());
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod;
+    if (!(delta > 0)) delta = default_delta();  // :745
+    CK(d_in0.ensure(2 * n6 * sizeof(real)));
+    CK(d_in1.ensure(9 * (size_t)n_bod * sizeof(real)));
+    RET(h2d(d_uom.p, W6, n6 * sizeof(real)));
+    real* tmp6 = d_in0.as<real>();
+    real* Sp = d_in1.as<real>();
+    real* v[2] = {d_t1.as<real>(), d_t2.as<real>()};
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      RET(displace(d_uom.as<real>(), (sgn ? -0.5 : 0.5) * delta, d_rp.as<real>()));
+      LAUNCH(1, rbl::ktk_inv_blocks<real>(d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb, Sp, d_flags.as<int>() + FLAG_SINGULAR, stream));
+      CK(cudaMemcpyAsync(tmp6, d_uom.p, n6 * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      LAUNCH(1, rbl::ktk_inv_apply<real>(Sp, n_bod, n_blb, tmp6, stream));   // (K^T K)^-1 W
+      LAUNCH(1, rbl::k_dot<real>(tmp6, d_rp.as<real>(), d_Xp.as<real>(), n_bod, n_blb, (real)1, nullptr, v[sgn], stream));  // Kinv^T W
+    }
+    LAUNCH(1, rbl::scale_copy<real>(v[0], (real)(1.0 / delta), d_rfd.as<real>(), n3, false, stream));
+    LAUNCH(1, rbl::scale_copy<real>(v[1], (real)(-1.0 / delta), d_rfd.as<real>(), n3, true, stream));
+    LAUNCH(1, rbl::kt_dot<real>(d_rfd.as<real>(), d_r.as<real>(), d_X.as<real>(), n_bod, n_blb, tmp6 + n6, stream));  // KT * out (:766)
+    RET(d2h(out6, tmp6 + n6, n6 * sizeof(real)));
+    return sync();
+  }
+  // blob positions of q +- (delta/2) U   (M_RFD_cfgs, :798-816)
+  int RFD_cfgs(const void* U6, double delta, void* r_plus, void* r_minus) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!U6 || !r_plus || !r_minus || !(delta > 0)) return fail(RBL_ERR_INVALID, "M_RFD_cfgs: U, delta > 0 and two outputs are required");
+    RET(rfd_buffers());
+    const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod;
+    RET(h2d(d_uom.p, U6, n6 * sizeof(real)));
+    RET(displace(d_uom.as<real>(), 0.5 * delta, d_t1.as<real>()));
+    RET(displace(d_uom.as<real>(), -0.5 * delta, d_t2.as<real>()));
+    RET(d2h(r_plus, d_t1.p, n3 * sizeof(real)));
+    RET(d2h(r_minus, d_t2.p, n3 * sizeof(real)));
+    return sync();
+  }
+  // (X, Q) displaced by U (units of displacement), state untouched   (update_X_Q_out, :712-728)
+  int displaced_config(const void* U6, void* X_out, void* Q_out) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!U6 || !X_out || !Q_out) return fail(RBL_ERR_INVALID, "update_X_Q_out: U and two outputs are required");
+    RET(rfd_buffers());
+    RET(h2d(d_uom.p, U6, 6 * (size_t)n_bod * sizeof(real)));
+    RET(displace(d_uom.as<real>(), 1.0, nullptr));
+    RET(d2h(X_out, d_Xp.p, 3 * (size_t)n_bod * sizeof(real)));
+    RET(d2h(Q_out, d_Qp.p, 4 * (size_t)n_bod * sizeof(real)));
+    return sync();
+  }
+  // install the configuration displaced by U and rebuild K; a built preconditioner is KEPT, stale on
+  // purpose (evolve_X_Q_RFD, :880-893: the displacement is an RFD-sized one)
+  int evolve_RFD(const void* U6) override {
+    if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
+    if (!U6) return fail(RBL_ERR_INVALID, "evolve_X_Q_RFD: U is required");
+    RET(rfd_buffers());
+    RET(h2d(d_uom.p, U6, 6 * (size_t)n_bod * sizeof(real)));
+    LAUNCH(1, rbl::integrate<real>(d_uom.as<real>(), (real)1, n_bod, d_X.as<real>(), d_Q.as<real>(), d_X.as<real>(), d_Q.as<real>(), stream));
+    const bool keep = pc_set;
+    RET(set_K_mats());
+    pc_set = keep;
+    return sync();
+  }
+
   int bd_step(const void* F_ext, const void* slip, const void* W1, const void* W2, const void* Wr, double kBT_,
               double tol, int restart, int max_iter, double ltol, int lmax, void* U_out, int* iters,
               double* relres) override {
-    const bool brownian = kBT_ > 0 && W1 && W2 && Wr;
-    if (kBT_ > 0 && !brownian) return fail(RBL_ERR_INVALID, "bd_step: kBT > 0 needs the three noise vectors W1, W2, Wr");
+    const bool brownian = kBT_ > 0 && W1 && (W2 || !split_rand) && Wr;
+    if (kBT_ > 0 && !brownian)
+      return fail(RBL_ERR_INVALID, split_rand ? "bd_step: kBT > 0 needs the three noise vectors W1, W2, Wr"
+                                              : "bd_step: kBT > 0 needs the noise vectors W1 and Wr");
     return bd_step_core(F_ext, slip, W1, W2, Wr, false, 0, 0, kBT_, tol, restart, max_iter, ltol, lmax, U_out, iters, relres);
   }
   int bd_step_seeded(const void* F_ext, const void* slip, unsigned long long seed, unsigned long long step, double kBT_,
@@ -1463,7 +1666,15 @@ struct Ctx final : rbl_ctx {
                    double ltol, int lmax, void* U_out, int* iters, double* relres) {
     if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
     if (!F_ext || !U_out) return fail(RBL_ERR_INVALID, "bd_step: F_ext and U_out are required");
-    const bool brownian = kBT_ > 0 && (rng || (W1 && W2 && Wr));
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](int phase) {  // profiling only: a stream sync per phase, never in a timed run
+      if (!profile) return;
+      cudaStreamSynchronize(stream);
+      const auto now = std::chrono::steady_clock::now();
+      bd_phase_ms[phase] += std::chrono::duration<double, std::milli>(now - t_last).count();
+      t_last = now;
+    };
+    const bool brownian = kBT_ > 0 && (rng || (W1 && (W2 || !split_rand) && Wr));
     if (brownian && !(dt > 0)) return fail(RBL_ERR_INVALID, "bd_step: dt must be positive");
     RET(need_K());
     const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod, n = n3 + n6;
@@ -1488,12 +1699,17 @@ struct Ctx final : rbl_ctx {
         LAUNCH(1, rbl::normal_triplet<real>(seed, step, first_element(), n3, w1, w2, noise, stream));
       } else {
         RET(h2d(w1, W1, n3 * sizeof(real)));
-        RET(h2d(w2, W2, n3 * sizeof(real)));
+        if (split_rand) RET(h2d(w2, W2, n3 * sizeof(real)));
         RET(h2d(noise, Wr, n3 * sizeof(real)));
       }
       int it = 0;
+      mark(0);
       // Brownian increments at q^n  (M_half_W, :661-675, via Lanczos)
-      if (pair_lanczos) {
+      if (!split_rand) {  // one Brownian increment (:949-953)
+        RET(dev_lanczos(w1, d_mh1.as<real>(), ltol, lmax, &it, noise_mode >= 1));
+        last_lanczos[0] = it;
+        last_lanczos[1] = 0;
+      } else if (pair_lanczos) {
         RET(dev_lanczos2(w1, w2, d_mh1.as<real>(), d_mh2.as<real>(), ltol, lmax, last_lanczos, noise_mode >= 1));
       } else {
         RET(dev_lanczos(w1, d_mh1.as<real>(), ltol, lmax, &it, noise_mode >= 1));
@@ -1501,26 +1717,21 @@ struct Ctx final : rbl_ctx {
         RET(dev_lanczos(w2, d_mh2.as<real>(), ltol, lmax, &it, noise_mode >= 1));
         last_lanczos[1] = it;
       }
+      mark(1);
       // random finite difference  (M_RFD, :769-796)
-      const double delta = sizeof(real) == 8 ? 1.0e-4 : 4.0e-3;
       RET(kinv_dev(noise, d_uom.as<real>()));
-      real* Mpm[2] = {d_t1.as<real>(), d_t2.as<real>()};
-      for (int sgn = 0; sgn < 2; ++sgn) {
-        LAUNCH(1, rbl::integrate<real>(d_uom.as<real>(), (real)((sgn ? -0.5 : 0.5) * delta), n_bod, d_X.as<real>(),
-                                       d_Q.as<real>(), d_Xp.as<real>(), d_Qp.as<real>(), stream));
-        LAUNCH(1, rbl::place_blobs<real>(d_Xp.as<real>(), d_Qp.as<real>(), d_ref.as<real>(), n_bod, n_blb,
-                                         d_rp.as<real>(), stream));
-        RET(prod_M(noise, d_rp.as<real>(), false, Mpm[sgn]));
-      }
-      LAUNCH(1, rbl::scale_copy<real>(d_t1.as<real>(), (real)(1.0 / delta), d_rfd.as<real>(), n3, false, stream));
-      LAUNCH(1, rbl::scale_copy<real>(d_t2.as<real>(), (real)(-1.0 / delta), d_rfd.as<real>(), n3, true, stream));
+      RET(dev_M_RFD(d_uom.as<real>(), noise, default_delta(), d_rfd.as<real>()));
+      mark(2);
       // (no K^T finite difference in the force row: with q+- = q +- (delta/2) K^-1 W_r its expectation
       // (d_k K^T) K^-T e_k vanishes identically -- tests/test_oracle_bd_drift.py)
       // RHS slip -= kBT * RFD + c2 (M^{1/2}W1 - M^{1/2}W2)   (:945-948,963)
-      const double c1 = 2.0 * std::sqrt(kBT_ / dt), c2 = std::sqrt(kBT_ / dt);
+      // split_rand: c1 = 2 sqrt(kBT/dt), c2 = sqrt(kBT/dt), BI = c2 (M^{1/2}W1 - M^{1/2}W2)  (:943-948);
+      // single increment: c1 = c2 = sqrt(2 kBT/dt), BI = c2 M^{1/2}W1  (:949-953)
+      const double c1 = split_rand ? 2.0 * std::sqrt(kBT_ / dt) : std::sqrt(2.0 * kBT_ / dt);
+      const double c2 = split_rand ? std::sqrt(kBT_ / dt) : std::sqrt(2.0 * kBT_ / dt);
       LAUNCH(1, rbl::scale_copy<real>(d_rfd.as<real>(), (real)(-kBT_), rhs, n3, true, stream));
       LAUNCH(1, rbl::scale_copy<real>(d_mh1.as<real>(), (real)(-c2), rhs, n3, true, stream));
-      LAUNCH(1, rbl::scale_copy<real>(d_mh2.as<real>(), (real)(c2), rhs, n3, true, stream));
+      if (split_rand) LAUNCH(1, rbl::scale_copy<real>(d_mh2.as<real>(), (real)(c2), rhs, n3, true, stream));
       // midpoint configuration q' = q + (dt/2) K^-1 (c1 M^{1/2}W1)   (:954-958), installed
       RET(kinv_dev(d_mh1.as<real>(), d_uom.as<real>()));
       CK(cudaMemcpyAsync(d_Xs.p, d_X.p, 3 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
@@ -1529,8 +1740,10 @@ struct Ctx final : rbl_ctx {
                                      d_X.as<real>(), d_Q.as<real>(), stream));
       RET(set_K_mats());
       pc_set = false;
+      mark(3);
     }
     int st = dev_gmres(rhs, sol, tol, restart, max_iter, iters, relres);
+    mark(4);
     if (brownian) {  // back to q^n whatever the solver said
       CK(cudaMemcpyAsync(d_X.p, d_Xs.p, 3 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
       CK(cudaMemcpyAsync(d_Q.p, d_Qs.p, 4 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
@@ -1544,7 +1757,9 @@ struct Ctx final : rbl_ctx {
     RET(set_K_mats());
     pc_set = false;
     RET(d2h(U_out, sol + n3, n6 * sizeof(real)));
-    return csync();
+    const int st_end = csync();
+    mark(5);
+    return st_end;
   }
 
   // ---- measurement ----------------------------------------------------------------------------
@@ -1764,6 +1979,34 @@ int rbl_noise_selfcheck(rbl_ctx* ctx, double* factor_err, double* inverse_err, i
   if (active) *active = a;
   return s;
 }
+int rbl_M_RFD(rbl_ctx* ctx, const void* W, double delta, void* out) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->M_RFD(nullptr, W, delta, out);
+}
+int rbl_M_RFD_from_U(rbl_ctx* ctx, const void* U, const void* W, double delta, void* out) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  if (!U) return ctx->fail(RBL_ERR_INVALID, "M_RFD_from_U: U is required");
+  return ctx->M_RFD(U, W, delta, out);
+}
+int rbl_KT_RFD_from_U(rbl_ctx* ctx, const void* U, const void* W, double delta, void* out) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->KT_RFD(U, W, delta, out);
+}
+int rbl_KTinv_RFD(rbl_ctx* ctx, const void* W6, double delta, void* out) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->KTinv_RFD(W6, delta, out);
+}
+int rbl_M_RFD_cfgs(rbl_ctx* ctx, const void* U, double delta, void* r_plus, void* r_minus) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->RFD_cfgs(U, delta, r_plus, r_minus);
+}
+int rbl_update_X_Q_out(rbl_ctx* ctx, const void* U, void* X_out, void* Q_out) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->displaced_config(U, X_out, Q_out);
+}
+int rbl_evolve_RFD(rbl_ctx* ctx, const void* U) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->evolve_RFD(U); }
+int rbl_set_rfd_delta(rbl_ctx* ctx, double delta) { CTX_OR_FAIL(ctx); ctx->rfd_delta = delta > 0 ? delta : 0; return RBL_OK; }
+int rbl_set_split_rand(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->split_rand = enable != 0; return RBL_OK; }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }
 int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* T, int* threads) {
@@ -1895,6 +2138,13 @@ int rbl_bd_stats(const rbl_ctx* ctx, int* lanczos_iters_1, int* lanczos_iters_2)
   return RBL_OK;
 }
 int rbl_profile_matvec(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->profile = enable != 0; return RBL_OK; }
+int rbl_bd_phase_ms(rbl_ctx* ctx, double* out6, int reset) {
+  CTX_OR_FAIL(ctx);
+  if (!out6) return RBL_ERR_INVALID;
+  for (int i = 0; i < 6; ++i) out6[i] = ctx->bd_phase_ms[i];
+  if (reset) for (int i = 0; i < 6; ++i) ctx->bd_phase_ms[i] = 0;
+  return RBL_OK;
+}
 int rbl_matvec_profile(rbl_ctx* ctx, double* avg_ms, int64_t* launches, int reset) {
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
   int s = cuda_status(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");

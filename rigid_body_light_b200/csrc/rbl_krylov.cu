@@ -83,6 +83,20 @@ cudaError_t scale_copy(const real* x, real a, real* y, size_t n, bool accumulate
 }
 
 template <typename real>
+__global__ void scale_by_inv_sqrt_kernel(const real* __restrict__ x, const real* __restrict__ s2, real* y, size_t n) {
+  const real v = *s2;
+  const real a = v > (real)0 ? (real)1 / sqrt(v) : (real)0;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    y[k] = a * x[k];
+}
+template <typename real>
+cudaError_t scale_by_inv_sqrt(const real* x, const real* s2, real* y, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  scale_by_inv_sqrt_kernel<real><<<592, 256, 0, s>>>(x, s2, y, n);
+  return cudaGetLastError();
+}
+
+template <typename real>
 __global__ void flip_tail_kernel(const real* __restrict__ x, size_t n_head, size_t n, real* y) {
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
        k += (size_t)gridDim.x * blockDim.x)
@@ -154,6 +168,7 @@ cudaError_t normal_triplet(unsigned long long seed, unsigned long long step, uns
                                         size_t, cudaStream_t);                                  \
   template cudaError_t scale_copy<real>(const real*, real, real*, size_t, bool, cudaStream_t);  \
   template cudaError_t flip_tail<real>(const real*, size_t, size_t, real*, cudaStream_t);       \
+  template cudaError_t scale_by_inv_sqrt<real>(const real*, const real*, real*, size_t, cudaStream_t); \
   template cudaError_t normal_triplet<real>(unsigned long long, unsigned long long,             \
                                             unsigned long long, size_t, real*, real*, real*,    \
                                             cudaStream_t);

@@ -20,6 +20,10 @@ cudaError_t multi_axpy(const real* V, size_t ld, int m, const real* coef, real s
 // y = a*x (+ y if accumulate)
 template <typename real>
 cudaError_t scale_copy(const real* x, real a, real* y, size_t n, bool accumulate, cudaStream_t s);
+// y = x / sqrt(*s2)  (s2 on the DEVICE: a squared norm; y = 0 if it is not positive) -- lets a Krylov
+// driver normalise the next basis vector without reading the norm back first
+template <typename real>
+cudaError_t scale_by_inv_sqrt(const real* x, const real* s2, real* y, size_t n, cudaStream_t s);
 // y[k] = x[k] for k < n_head, -x[k] after (the sign flip between apply_saddle's and
 // apply_PC's conventions)
 template <typename real>

@@ -124,14 +124,16 @@ __global__ void pack_records_kernel(const real* __restrict__ r, const real* __re
 
 template <typename real>
 __global__ void repack_forces_kernel(const real* __restrict__ F, int n, int wall, real a,
-                                     real inv_a, real* __restrict__ rec) {
+                                     real inv_a, real* __restrict__ rec, int* __restrict__ below) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   real* p = rec + (size_t)k * kRecReals;
-  real b = wall ? damp(p[2], a, inv_a) : (real)1;
+  const real z = p[2];
+  real b = wall ? damp(z, a, inv_a) : (real)1;
   p[3] = b * F[3 * (size_t)k];
   p[4] = b * F[3 * (size_t)k + 1];
   p[5] = b * F[3 * (size_t)k + 2];
+  if (wall && z < (real)0) *below = 1;  // raised on every product, like the reference (c_rigid_obj.cpp:95-97)
 }
 
 template <typename real>
@@ -144,12 +146,12 @@ cudaError_t pack_records(const real* r, const real* F, int n, int n_padded, bool
   return cudaGetLastError();
 }
 template <typename real>
-cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec,
+cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec, int* below,
                           cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   int threads = 256, blocks = (n + threads - 1) / threads;
   repack_forces_kernel<real><<<blocks, threads, 0, s>>>(F, n, wall ? 1 : 0, a, (real)1 / a,
-                                                        rec);
+                                                        rec, below);
   return cudaGetLastError();
 }
 
@@ -1086,6 +1088,31 @@ cudaError_t pack_records2(const real* r, const real* F1, const real* F2, int n, 
   return cudaGetLastError();
 }
 
+// positions unchanged since pack_records2: only the six force words of each record
+template <typename real>
+__global__ void repack_forces2_kernel(const real* __restrict__ F1, const real* __restrict__ F2, int n, int wall,
+                                      real a, real inv_a, real* __restrict__ rec, int* __restrict__ below) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  real* p = rec + (size_t)k * kRec2Reals;
+  const real z = p[2];
+  const real b = wall ? damp(z, a, inv_a) : (real)1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    p[3 + c] = b * F1[3 * (size_t)k + c];
+    p[6 + c] = b * F2[3 * (size_t)k + c];
+  }
+  if (wall && z < (real)0) *below = 1;
+}
+template <typename real>
+cudaError_t repack_forces2(const real* F1, const real* F2, int n, bool wall, real a, real* rec, int* below,
+                           cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int threads = 256, blocks = (n + threads - 1) / threads;
+  repack_forces2_kernel<real><<<blocks, threads, 0, s>>>(F1, F2, n, wall ? 1 : 0, a, (real)1 / a, rec, below);
+  return cudaGetLastError();
+}
+
 // diagonal tiles (they hold the self pairs): ordered general path, one right-hand side at a time
 template <typename real, bool WALL, int T>
 __device__ __forceinline__ void tile_compute2_ordered(const real* __restrict__ sb, const PairConsts<real>& C,
@@ -1537,8 +1564,9 @@ cudaError_t fma_peak_launch(int sm_count, int iters, real* sink, double* flops,
   template cudaError_t matvec_plan<real>(int, bool, int, int, int, int, MatvecPlan*);      \
   template cudaError_t pack_records<real>(const real*, const real*, int, int, bool, real,  \
                                           real*, int*, cudaStream_t);                      \
-  template cudaError_t repack_forces<real>(const real*, int, bool, real, real*,            \
+  template cudaError_t repack_forces<real>(const real*, int, bool, real, real*, int*,      \
                                            cudaStream_t);                                  \
+  template cudaError_t repack_forces2<real>(const real*, const real*, int, bool, real, real*, int*, cudaStream_t); \
   template cudaError_t tile_boxes<real>(const real*, int, int, int, float*, cudaStream_t, int); \
   template cudaError_t pack_records2<real>(const real*, const real*, const real*, int, int, bool, real, real*, int*, cudaStream_t); \
   template cudaError_t matvec_sym2_plan<real>(int, bool, int, int, int, int, SymPlan*);      \

@@ -72,7 +72,7 @@ cudaError_t pack_records(const real* r, const real* F, int n, int n_padded, bool
 
 // Only refreshes the force part of already packed records (positions unchanged).
 template <typename real>
-cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec,
+cudaError_t repack_forces(const real* F, int n, bool wall, real a, real* rec, int* below_wall_flag,
                           cudaStream_t s);
 
 // Axis-aligned boxes of consecutive groups of `tile` records starting at `first`.
@@ -154,6 +154,9 @@ struct Sym2Args {
 template <typename real>
 cudaError_t pack_records2(const real* r, const real* F1, const real* F2, int n, int n_padded, bool wall, real a,
                           real* rec, int* below_wall_flag, cudaStream_t s);
+template <typename real>
+cudaError_t repack_forces2(const real* F1, const real* F2, int n, bool wall, real a, real* rec,
+                           int* below_wall_flag, cudaStream_t s);
 template <typename real>
 int matvec_sym2_num_variants();
 template <typename real>

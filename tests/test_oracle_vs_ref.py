@@ -309,3 +309,10 @@ def test_bd_right_hand_side_against_the_reference_RHS_and_Midpoint(orc, name):
     uom = orc.Kinv_apply(2.0 * np.sqrt(kBT / dt) * (Lc @ W[0]), g["r"], g["X"], g["Qn"], rcfg)
     Xw, Qw = orc.update_X_Q(g["X"], g["Qn"], 0.5 * dt * uom)
     assert rel_err(Xm, Xw) < 1e-14 and rel_err(Qm, Qw) < 1e-14
+    # the single-increment branch (split_rand = false, :949-953): rand_vector is drawn for W1, then for M_RFD
+    rb.set_split_rand(False)
+    ref_rhs1 = rb.RHS_and_Midpoint(slip, F, W[0], W[2], W[2], kBT)  # injected order: W1, Wr (third unused)
+    rhs1, _, _ = orc.bd_step(g["X"], g["Qn"], rcfg, a, eta, dt, kBT, wall, F, slip, W[0], None, W[2], noise="cholesky",
+                             return_rhs=True, split_rand=False)
+    assert rel_err(rhs1[:n3], ref_rhs1[:n3]) < 1e-9
+    assert rel_err(rhs1[:n3], rhs[:n3]) > 1e-3  # a different right-hand side than the two-increment scheme
