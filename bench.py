@@ -428,10 +428,15 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
                        f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC, block-Cholesky preconditioned paired Lanczos noise",
            "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps,
            "warmup_steps": 1 if args.bd_warmup else 0}
-    for precision in precisions:
+    legs = [(p, 0) for p in precisions]
+    if "double" in precisions and world == 1 and args.bd_mixed:
+        legs += [("double", 1), ("double", 2)]  # mixed precision: single-GPU double contexts
+    for precision, mixed in legs:
         tol, ltol = (1e-4, 1e-4) if precision == "single" else (1e-8, 1e-6)
         pb = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=wall, block_PC=True,
                                   precision=precision, rank=rank, world=world, dist=dist, device=local_rank)
+        if mixed:
+            pb.set_mixed_precision(mixed)
         rng = np.random.default_rng(3)
         times, iters, lz, rel = [], [], [], []
         prod0 = 0
@@ -476,13 +481,15 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
                                                   [float(v) * 1e-3 for v in ph])),
                         "note": "rank 0, untimed extra step with a stream sync after every phase"}
         X, _ = pb.get_config()
-        out[precision] = {"seconds_per_step": float(np.mean(times)), "seconds_per_step_min": float(np.min(times)),
+        out[precision if not mixed else f"double_mixed{mixed}"] = {"seconds_per_step": float(np.mean(times)), "seconds_per_step_min": float(np.min(times)),
                           "seconds_per_step_max": float(np.max(times)), "seconds_each_step": [float(t) for t in times],
                           "gmres_iterations": iters, "lanczos_iterations": lz,
                           "gmres_tol": tol, "lanczos_tol": ltol, "gmres_max_iter": args.bd_gmres_max_iter,
                           "lanczos_max_iter": args.bd_lanczos_max_iter, "relres": rel, "mobility_products_per_step": products,
                           "min_body_height_after": float(X[:, 2].min()), "U_norm_local": float(np.linalg.norm(U)),
-                          "profile_step": profile_step}
+                          "profile_step": profile_step,
+                          "mixed_precision": {0: None, 1: "float GMRES corrections, double-residual refinement (same relres <= tol)",
+                                              2: "mode 1 + float mobility products inside the Lanczos noise"}[mixed]}
         pb.close()
     return out
 
@@ -594,6 +601,7 @@ def main():
     ap.add_argument("--bd-steps", type=int, default=3, help="timed full BD steps after the matvec bench (0 = skip)")
     ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--bd-warmup", type=int, default=1, help="0: time the very first BD step (allocations included)")
+    ap.add_argument("--bd-mixed", type=int, default=1, help="also time the double BD step with mixed precision modes 1 and 2 (N=1)")
     ap.add_argument("--bd-gmres-max-iter", type=int, default=200)
     ap.add_argument("--bd-lanczos-max-iter", type=int, default=80)
     args = ap.parse_args()

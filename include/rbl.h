@@ -157,6 +157,15 @@ int rbl_evolve_RFD(rbl_ctx* ctx, const void* U);
  * float is most accurate near eps^(1/3) x (length over which M varies ~ the body radius): rounding
  * 3e-7 |M W| / delta against truncation ~ (delta/a)^2 / 6. */
 int rbl_set_rfd_delta(rbl_ctx* ctx, double delta);
+/* Mixed precision for DOUBLE contexts on one GPU (ignored on a partitioned suspension).  The context keeps a
+ * float mirror of itself (same parameters, flags, configuration; same stream):
+ *   0 (default) everything in double;
+ *   1 rbl_gmres / the solve of rbl_bd_step: float GMRES corrections inside an iterative refinement whose
+ *     residual b - apply_saddle(x) is evaluated in DOUBLE; stops on the same ||b - A x|| / ||b|| <= tol;
+ *   2 additionally the mobility products inside the Lanczos square roots run in float (vectors, recurrence
+ *     and block-Cholesky factors stay double): the increment is the square root of the float-rounded
+ *     operator, M (1 + O(1e-7)) -- below any Lanczos tolerance >= 1e-6, NOT bitwise the double increment. */
+int rbl_set_mixed_precision(rbl_ctx* ctx, int mode);
 /* 1 (default, like the reference's split_rand = true, :150): two Brownian increments per step, c1 = 2 sqrt(kBT/dt),
  * c2 = sqrt(kBT/dt), BI = c2 (M^{1/2}W1 - M^{1/2}W2) (:943-948).  0: one increment, c1 = c2 = sqrt(2 kBT/dt),
  * BI = c2 M^{1/2}W1 (:949-953); rbl_bd_step then ignores W2 (may be NULL). */

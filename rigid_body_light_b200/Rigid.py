@@ -262,6 +262,11 @@ class RigidBody:
         """RFD step of ``bd_step`` / default of ``M_RFD``; 0 restores 1e-4 (double) / 4e-3 (float)."""
         self._abi("rbl_set_rfd_delta", float(delta))
 
+    def set_mixed_precision(self, mode):
+        """double contexts: 0 all double; 1 float GMRES corrections inside a double-residual refinement;
+        2 also float mobility products inside the Lanczos noise (include/rbl.h rbl_set_mixed_precision)."""
+        self._abi("rbl_set_mixed_precision", int(mode))
+
     def set_split_rand(self, enable):
         """True (default): two Brownian increments per step (:943-948); False: one (:949-953)."""
         self._abi("rbl_set_split_rand", int(bool(enable)))

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rbl.h"
@@ -98,6 +99,7 @@ struct rbl_ctx {
   virtual int evolve_RFD(const void* U6) = 0;
   virtual int normals(unsigned long long seed, unsigned long long step, unsigned long long first, size_t n, void* W1,
                       void* W2, void* Wr, bool dev) = 0;
+  virtual int set_mixed(int mode) = 0;
   virtual int sync() = 0;
   virtual int fma_peak(int iters, double* tflops) = 0;
   virtual int num_variants() const = 0;
@@ -162,6 +164,9 @@ struct rbl_ctx {
 
 // ---------------------------------------------------------------------------------------
 template <typename real>
+struct Ctx;
+
+template <typename real>
 struct Ctx final : rbl_ctx {
   // parameters (setParameters, c_rigid_obj.cpp:183-195)
   double a = 0, dt = 0, kBT = 0, eta = 0;
@@ -207,9 +212,23 @@ struct Ctx final : rbl_ctx {
     }
   } rec1_state, rec2_state;
 
+  // mixed precision (double contexts, single GPU): a float mirror of this context on the same stream.
+  //  1: GMRES solves run in float inside an iterative refinement whose residual is the DOUBLE operator
+  //     (same stopping rule ||b - A x|| / ||b|| <= tol on the double residual);
+  //  2: additionally the mobility products of the Lanczos noise run in float (the vectors, the
+  //     recurrence and the block-Cholesky factors stay double): the increment is (M~)^{1/2} W for the
+  //     float-rounded operator M~ = M (1 + O(1e-7)), below the Lanczos tolerances in use (>= 1e-6).
+  int mixed = 0;
+  Ctx<float>* shadow = nullptr;
+  unsigned long long shadow_gen = 0;
+  std::vector<double> ref_host;  // mean-removed reference configuration, for the mirror
+  DevBuf d_c32a, d_c32b, d_c32c, d_c32d, d_mr, d_me;
+  int mixed_outer = 0;           // refinement cycles of the last mixed solve
+
   enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, FLAG_NOISE = 3, N_FLAGS = 4 };
 
   ~Ctx() override {
+    delete shadow;
     for (auto& pr : prof_events) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
@@ -278,6 +297,9 @@ struct Ctx final : rbl_ctx {
       for (int d = 0; d < 3; ++d) ref[3 * k + d] -= mean[d];
     CK(d_ref.ensure(ref.size() * sizeof(real)));
     RET(h2d(d_ref.p, ref.data(), ref.size() * sizeof(real)));
+    ref_host.assign(ref.begin(), ref.end());
+    delete shadow;  // the mirror follows the parameters: rebuilt at its next use
+    shadow = nullptr;
     CK(cudaStreamSynchronize(stream));
     params_set = true;
     r_valid = false;
@@ -945,13 +967,157 @@ struct Ctx final : rbl_ctx {
     return RBL_OK;
   }
 
+  // ---- mixed precision -------------------------------------------------------------------------------
+  int set_mixed(int mode) override {
+    if (mode < 0 || mode > 2) return fail(RBL_ERR_INVALID, "mixed precision mode must be 0, 1 or 2");
+    if (mode != 0 && sizeof(real) != 8) return fail(RBL_ERR_INVALID, "mixed precision applies to double contexts");
+    mixed = mode;
+    return RBL_OK;
+  }
+  bool use_mixed(int level) const { return sizeof(real) == 8 && mixed >= level && !comm; }
+  // bring the float mirror to this context's parameters, flags and CURRENT configuration
+  int sync_shadow() {
+    if constexpr (std::is_same<real, double>::value) {
+      RET(need_K());
+      if (!shadow) {
+        auto* sh = new Ctx<float>();
+        sh->precision = RBL_F32; sh->device = device; sh->sm_count = sm_count;
+        int st = sh->init();
+        if (st != RBL_OK) { err = sh->err; delete sh; return st; }
+        cudaStreamSynchronize(sh->stream);
+        cudaStreamDestroy(sh->stream);
+        sh->stream = stream;
+        sh->own_stream = false;
+        std::vector<float> rf(ref_host.begin(), ref_host.end());
+        st = sh->set_parameters(a, dt, kBT, eta, rf.data(), n_blb);
+        if (st != RBL_OK) { err = sh->err; delete sh; return st; }
+        shadow = sh;
+        shadow_gen = 0;
+      }
+      shadow->set_flags(block_pc ? 1 : 0, wall ? 1 : 0);
+      shadow->noise_mode = 0;
+      if (shadow_gen != cfg_gen || shadow->n_bod != n_bod) {
+        shadow->n_bod = n_bod;
+        CK(shadow->d_X.ensure(3 * (size_t)n_bod * sizeof(float)));
+        CK(shadow->d_Q.ensure(4 * (size_t)n_bod * sizeof(float)));
+        LAUNCH(1, (rbl::cast_scale<double, float>(d_X.template as<double>(), 1.0, shadow->d_X.template as<float>(), 3 * (size_t)n_bod, false, stream)));
+        LAUNCH(1, (rbl::cast_scale<double, float>(d_Q.template as<double>(), 1.0, shadow->d_Q.template as<float>(), 4 * (size_t)n_bod, false, stream)));
+        shadow->cfg_set = true;
+        int st = shadow->set_K_mats();
+        if (st != RBL_OK) return fail(st, shadow->err);
+        shadow->pc_set = false;
+        shadow_gen = cfg_gen;
+      }
+    }
+    return RBL_OK;
+  }
+  // x = A^-1 b to ||b - A x|| <= tol ||b|| (DOUBLE residual): float GMRES corrections inside an
+  // iterative refinement.  A cycle that fails to halve the residual hands over to the double solver.
+  int dev_gmres_mixed(const real* b, real* xs, double tol, int restart, int max_iter, int* iters, double* relres) {
+    if constexpr (std::is_same<real, double>::value) {
+      RET(sync_shadow());
+      const size_t n = sys_size();
+      CK(d_c32a.ensure(n * sizeof(float)));
+      CK(d_c32b.ensure(n * sizeof(float)));
+      CK(d_mr.ensure(n * sizeof(real)));
+      CK(d_me.ensure(n * sizeof(real)));
+      CK(d_partial.ensure((size_t)4 * rbl::kDotBlocks * sizeof(real)));
+      CK(d_dots.ensure((size_t)8 * sizeof(real)));
+      real* r = d_mr.template as<real>();
+      real* Ax = d_me.template as<real>();
+      float* r32 = d_c32a.template as<float>();
+      float* e32 = d_c32b.template as<float>();
+      CK(cudaMemsetAsync(xs, 0, n * sizeof(real), stream));
+      LAUNCH(1, rbl::scale_copy<real>(b, (real)1, r, n, false, stream));
+      double bnorm = 0;
+      RET(dev_norm(b, n, &bnorm));
+      *iters = 0;
+      *relres = 0;
+      mixed_outer = 0;
+      if (bnorm == 0) return RBL_OK;
+      double res = bnorm;
+      int total = 0;
+      for (int outer = 0; outer < 12 && total < max_iter; ++outer) {
+        ++mixed_outer;
+        const double need = tol * bnorm / res;                        // reduction still missing
+        const double inner_tol = std::min(1e-3, std::max(0.3 * need, 2e-6));
+        LAUNCH(1, (rbl::cast_scale<double, float>(r, 1.0 / res, r32, n, false, stream)));
+        int it = 0;
+        double rr = 0;
+        int st = shadow->dev_gmres(r32, e32, inner_tol, restart, max_iter - total, &it, &rr);
+        if (st != RBL_OK) return fail(st, shadow->err);
+        total += it;
+        LAUNCH(1, (rbl::cast_scale<float, double>(e32, res, xs, n, true, stream)));
+        RET(dev_saddle(xs, Ax));
+        LAUNCH(1, rbl::scale_copy<real>(b, (real)1, r, n, false, stream));
+        LAUNCH(1, rbl::scale_copy<real>(Ax, (real)-1, r, n, true, stream));
+        double nres = 0;
+        RET(dev_norm(r, n, &nres));
+        const bool stalled = nres > 0.5 * res;
+        res = nres;
+        if (res / bnorm <= tol) break;
+        if (stalled) {  // float corrections no longer help: finish in double on the residual equation
+          int it2 = 0;
+          double rr2 = 0;
+          RET(dev_gmres(r, Ax, std::min(0.5, tol * bnorm / res), restart, std::max(1, max_iter - total), &it2, &rr2));
+          total += it2;
+          LAUNCH(1, rbl::scale_copy<real>(Ax, (real)1, xs, n, true, stream));
+          res = rr2 * res;
+          break;
+        }
+      }
+      *iters = total;
+      *relres = res / bnorm;
+      return RBL_OK;
+    } else {
+      return dev_gmres(b, xs, tol, restart, max_iter, iters, relres);
+    }
+  }
+  // the two products of a paired Lanczos iteration through the float mirror (mode 2)
+  int prod_M2_mirror(const real* F1, const real* F2, real* out1, real* out2) {
+    if constexpr (std::is_same<real, double>::value) {
+      RET(sync_shadow());
+      const size_t n3 = 3 * (size_t)N();
+      for (DevBuf* bf : {&d_c32a, &d_c32b, &d_c32c, &d_c32d}) CK(bf->ensure(std::max(n3, sys_size()) * sizeof(float)));
+      LAUNCH(1, (rbl::cast_scale<double, float>(F1, 1.0, d_c32a.template as<float>(), n3, false, stream)));
+      LAUNCH(1, (rbl::cast_scale<double, float>(F2, 1.0, d_c32b.template as<float>(), n3, false, stream)));
+      int st = shadow->prod_M2(d_c32a.template as<float>(), d_c32b.template as<float>(), d_c32c.template as<float>(),
+                               d_c32d.template as<float>());
+      if (st != RBL_OK) return fail(st, shadow->err);
+      products += 2;
+      LAUNCH(1, (rbl::cast_scale<float, double>(d_c32c.template as<float>(), 1.0, out1, n3, false, stream)));
+      LAUNCH(1, (rbl::cast_scale<float, double>(d_c32d.template as<float>(), 1.0, out2, n3, false, stream)));
+      return RBL_OK;
+    } else {
+      return prod_M2(F1, F2, out1, out2);
+    }
+  }
+  int prod_M_mirror(const real* F, real* out) {
+    if constexpr (std::is_same<real, double>::value) {
+      RET(sync_shadow());
+      const size_t n3 = 3 * (size_t)N();
+      for (DevBuf* bf : {&d_c32a, &d_c32c}) CK(bf->ensure(std::max(n3, sys_size()) * sizeof(float)));
+      LAUNCH(1, (rbl::cast_scale<double, float>(F, 1.0, d_c32a.template as<float>(), n3, false, stream)));
+      int st = shadow->prod_M(d_c32a.template as<float>(), shadow->d_r.template as<float>(), true, d_c32c.template as<float>());
+      if (st != RBL_OK) return fail(st, shadow->err);
+      ++products;
+      LAUNCH(1, (rbl::cast_scale<float, double>(d_c32c.template as<float>(), 1.0, out, n3, false, stream)));
+      return RBL_OK;
+    } else {
+      return prod_M(F, d_r.template as<real>(), true, out);
+    }
+  }
+
   int gmres(const void* rhs, void* x, double tol, int restart, int max_iter, int* iters, double* relres) override {
     if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
     const size_t n = sys_size();
     CK(d_in1.ensure(n * sizeof(real)));   // rhs
     CK(d_out0.ensure(n * sizeof(real)));  // x
     RET(h2d(d_in1.p, rhs, n * sizeof(real)));
-    RET(dev_gmres(d_in1.as<real>(), d_out0.as<real>(), tol, restart, max_iter, iters, relres));
+    if (use_mixed(1))
+      RET(dev_gmres_mixed(d_in1.as<real>(), d_out0.as<real>(), tol, restart, max_iter, iters, relres));
+    else
+      RET(dev_gmres(d_in1.as<real>(), d_out0.as<real>(), tol, restart, max_iter, iters, relres));
     RET(d2h(x, d_out0.p, n * sizeof(real)));
     return csync();
   }
@@ -1148,10 +1314,12 @@ struct Ctx final : rbl_ctx {
       // w = M v_k - beta_{k-1} v_{k-1}
       if (pc) {  // w = G A G^T v_k
         RET(noise_GT(V + (size_t)k * n, d_nt1.as<real>()));
-        RET(prod_M(d_nt1.as<real>(), d_r.as<real>(), true, d_nu1.as<real>()));
+        if (use_mixed(2)) RET(prod_M_mirror(d_nt1.as<real>(), d_nu1.as<real>()));
+        else RET(prod_M(d_nt1.as<real>(), d_r.as<real>(), true, d_nu1.as<real>()));
         RET(noise_G(d_nu1.as<real>(), w));
       } else {
-        RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
+        if (use_mixed(2)) RET(prod_M_mirror(V + (size_t)k * n, w));
+        else RET(prod_M(V + (size_t)k * n, d_r.as<real>(), true, w));
       }
       if (k > 0) LAUNCH(1, rbl::scale_copy<real>(V + (size_t)(k - 1) * n, (real)(-beta[k - 1]), w, n, true, stream));
       // alpha_k, the full reorthogonalisation (keeps the basis orthonormal in fp32 too), beta_k^2 and the
@@ -1425,11 +1593,13 @@ struct Ctx final : rbl_ctx {
       if (pc) {  // w = G A G^T v
         RET(noise_GT(v0, d_nt1.as<real>()));
         RET(noise_GT(v1, d_nt2.as<real>()));
-        RET(prod_M2(d_nt1.as<real>(), d_nt2.as<real>(), d_nu1.as<real>(), d_nu2.as<real>()));
+        if (use_mixed(2)) RET(prod_M2_mirror(d_nt1.as<real>(), d_nt2.as<real>(), d_nu1.as<real>(), d_nu2.as<real>()));
+        else RET(prod_M2(d_nt1.as<real>(), d_nt2.as<real>(), d_nu1.as<real>(), d_nu2.as<real>()));
         RET(noise_G(d_nu1.as<real>(), R[0].w));
         RET(noise_G(d_nu2.as<real>(), R[1].w));
       } else {
-        RET(prod_M2(v0, v1, R[0].w, R[1].w));
+        if (use_mixed(2)) RET(prod_M2_mirror(v0, v1, R[0].w, R[1].w));
+        else RET(prod_M2(v0, v1, R[0].w, R[1].w));
       }
       // device side of both recurrences first (alpha, reorthogonalisation, beta^2, normalised next
       // basis vector), then ONE device->host read for the two of them
@@ -1742,7 +1912,8 @@ struct Ctx final : rbl_ctx {
       pc_set = false;
       mark(3);
     }
-    int st = dev_gmres(rhs, sol, tol, restart, max_iter, iters, relres);
+    int st = use_mixed(1) ? dev_gmres_mixed(rhs, sol, tol, restart, max_iter, iters, relres)
+                          : dev_gmres(rhs, sol, tol, restart, max_iter, iters, relres);
     mark(4);
     if (brownian) {  // back to q^n whatever the solver said
       CK(cudaMemcpyAsync(d_X.p, d_Xs.p, 3 * (size_t)n_bod * sizeof(real), cudaMemcpyDeviceToDevice, stream));
@@ -2006,6 +2177,7 @@ int rbl_update_X_Q_out(rbl_ctx* ctx, const void* U, void* X_out, void* Q_out) {
 }
 int rbl_evolve_RFD(rbl_ctx* ctx, const void* U) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->evolve_RFD(U); }
 int rbl_set_rfd_delta(rbl_ctx* ctx, double delta) { CTX_OR_FAIL(ctx); ctx->rfd_delta = delta > 0 ? delta : 0; return RBL_OK; }
+int rbl_set_mixed_precision(rbl_ctx* ctx, int mode) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->set_mixed(mode); }
 int rbl_set_split_rand(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->split_rand = enable != 0; return RBL_OK; }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }

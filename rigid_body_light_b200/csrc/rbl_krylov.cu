@@ -96,6 +96,22 @@ cudaError_t scale_by_inv_sqrt(const real* x, const real* s2, real* y, size_t n, 
   return cudaGetLastError();
 }
 
+template <typename From, typename To>
+__global__ void cast_scale_kernel(const From* __restrict__ x, double a, To* y, size_t n, int accumulate) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const double v = a * (double)x[k];
+    y[k] = accumulate ? (To)((double)y[k] + v) : (To)v;
+  }
+}
+template <typename From, typename To>
+cudaError_t cast_scale(const From* x, double a, To* y, size_t n, bool accumulate, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  cast_scale_kernel<From, To><<<592, 256, 0, s>>>(x, a, y, n, accumulate ? 1 : 0);
+  return cudaGetLastError();
+}
+template cudaError_t cast_scale<double, float>(const double*, double, float*, size_t, bool, cudaStream_t);
+template cudaError_t cast_scale<float, double>(const float*, double, double*, size_t, bool, cudaStream_t);
+
 template <typename real>
 __global__ void flip_tail_kernel(const real* __restrict__ x, size_t n_head, size_t n, real* y) {
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;

@@ -24,6 +24,10 @@ cudaError_t scale_copy(const real* x, real a, real* y, size_t n, bool accumulate
 // driver normalise the next basis vector without reading the norm back first
 template <typename real>
 cudaError_t scale_by_inv_sqrt(const real* x, const real* s2, real* y, size_t n, cudaStream_t s);
+// y = (To)(a * x) (+ y if accumulate) between precisions (mixed-precision refinement: the float mirror
+// of a double context)
+template <typename From, typename To>
+cudaError_t cast_scale(const From* x, double a, To* y, size_t n, bool accumulate, cudaStream_t s);
 // y[k] = x[k] for k < n_head, -x[k] after (the sign flip between apply_saddle's and
 // apply_PC's conventions)
 template <typename real>

@@ -265,6 +265,10 @@ class PartitionedRigidBody:
         self.dist.all_gather_object(parts, np.asarray(x_local))
         return join_system(parts, self.ranges)
 
+    def set_mixed_precision(self, mode):
+        """see Rigid.RigidBody.set_mixed_precision (single-GPU double contexts; ignored when partitioned)"""
+        self.ctx.call("rbl_set_mixed_precision", int(mode))
+
     def get_blob_positions(self):
         """Positions of THIS rank's blobs, (N_local, 3) (multi_body_pos, c_rigid_obj.cpp:295-300)."""
         r = np.empty(3 * self.total_blobs, dtype=self.real)
