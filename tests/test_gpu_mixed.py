@@ -49,11 +49,11 @@ def test_mixed_bd_step(name):
         U, it, rr = cb.bd_step(F, **kw)
         assert rr <= 1e-10, (mode, rr)
         out[mode] = (U, cb.get_config())
-    check(rel_err(out[1][0], out[0][0]), 1e-8, "BD step U, mixed mode 1 vs all-double")
+    check(rel_err(out[1][0], out[0][0]), 2e-9, "BD step U, mixed mode 1 vs all-double")  # observed 1.4e-10
     check(rel_err(out[1][1][0], out[0][1][0]), 1e-10, "X after the step, mixed mode 1 vs all-double")
     e2 = rel_err(out[2][0], out[0][0])
     print(f"[{name}] mode 2 (float products inside Lanczos): U differs from the all-double step by {e2:.2e}")
-    check(e2, 2e-5, "BD step U, mixed mode 2 vs all-double: float-rounded operator under the square root")
+    check(e2, 3e-6, "BD step U, mixed mode 2 vs all-double: float-rounded operator under the square root")
 
 
 def test_mixed_mode_is_refused_for_float_contexts():
