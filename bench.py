@@ -297,7 +297,7 @@ def run_ours(args):
             ctx.call("rbl_pinned_alloc", nbytes, ctypes.byref(ho))
             x_host = np.ascontiguousarray(x_local_np.astype(ndt))  # keep alive across the memmove
             ctypes.memmove(hx, x_host.ctypes.data, nbytes)
-            for _ in range(max(1, args.warmup)):
+            for _ in range(args.e2e_warmup):
                 ctx.call("rbl_apply_saddle", hx, ho)
             barrier()
             t0 = time.perf_counter()
@@ -311,7 +311,7 @@ def run_ours(args):
         else:
             hx = torch.from_numpy(x_local_np.astype(ndt)).pin_memory()
             ho = torch.empty_like(hx).pin_memory()
-            for _ in range(max(1, args.warmup)):
+            for _ in range(args.e2e_warmup):
                 x_local.copy_(hx, non_blocking=True); op.apply(x_local, out_local); ho.copy_(out_local, non_blocking=True)
             barrier()
             t0 = time.perf_counter()
@@ -462,24 +462,26 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
             pb.ctx.L.rbl_bd_stats(pb.ctx.h, ctypes.byref(l1), ctypes.byref(l2))
             times.append(dt); iters.append(int(it)); lz.append([l1.value, l2.value]); rel.append(float(rr))
         products = (int(pb.ctx.L.rbl_product_count(pb.ctx.h)) - prod0) / max(1, args.bd_steps)
-        # one more step, NOT timed, with the profiling hooks on: where a step's wall clock goes
-        # (a stream sync ends every phase; CUDA events bracket every product kernel)
-        pb.ctx.call("rbl_profile_matvec", 1)
-        pb.ctx.matvec_profile(reset=True)
-        ph = (ctypes.c_double * 6)()
-        pb.ctx.call("rbl_bd_phase_ms", ph, 1)
-        noise = tuple(pb.slice_blobs(rng.standard_normal(n3)) for _ in range(3))
-        t0 = time.perf_counter()
-        pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60,
-                   max_iter=args.bd_gmres_max_iter, lanczos_tol=ltol, lanczos_max_iter=args.bd_lanczos_max_iter)
-        prof_s = time.perf_counter() - t0
-        kms, kn = pb.ctx.matvec_profile(reset=True)
-        pb.ctx.call("rbl_bd_phase_ms", ph, 1)
-        pb.ctx.call("rbl_profile_matvec", 0)
-        profile_step = {"seconds": prof_s, "product_kernel_seconds": kms * kn * 1e-3, "product_kernel_launches": int(kn),
-                        "phase_seconds": dict(zip(["inputs_noise", "lanczos", "rfd", "midpoint", "gmres_incl_pc_build", "evolve_output"],
-                                                  [float(v) * 1e-3 for v in ph])),
-                        "note": "rank 0, untimed extra step with a stream sync after every phase"}
+        profile_step = None
+        if args.bd_profile_step:
+            # one more step, NOT timed, with the profiling hooks on: where a step's wall clock goes
+            # (a stream sync ends every phase; CUDA events bracket every product kernel)
+            pb.ctx.call("rbl_profile_matvec", 1)
+            pb.ctx.matvec_profile(reset=True)
+            ph = (ctypes.c_double * 6)()
+            pb.ctx.call("rbl_bd_phase_ms", ph, 1)
+            noise = tuple(pb.slice_blobs(rng.standard_normal(n3)) for _ in range(3))
+            t0 = time.perf_counter()
+            pb.bd_step(pb.slice_bodies(F_ext), kBT=0.0041, noise_local=noise, tol=tol, restart=60,
+                       max_iter=args.bd_gmres_max_iter, lanczos_tol=ltol, lanczos_max_iter=args.bd_lanczos_max_iter)
+            prof_s = time.perf_counter() - t0
+            kms, kn = pb.ctx.matvec_profile(reset=True)
+            pb.ctx.call("rbl_bd_phase_ms", ph, 1)
+            pb.ctx.call("rbl_profile_matvec", 0)
+            profile_step = {"seconds": prof_s, "product_kernel_seconds": kms * kn * 1e-3, "product_kernel_launches": int(kn),
+                            "phase_seconds": dict(zip(["inputs_noise", "lanczos", "rfd", "midpoint", "gmres_incl_pc_build", "evolve_output"],
+                                                      [float(v) * 1e-3 for v in ph])),
+                            "note": "rank 0, untimed extra step with a stream sync after every phase"}
         X, _ = pb.get_config()
         out[precision if not mixed else f"double_mixed{mixed}"] = {"seconds_per_step": float(np.mean(times)), "seconds_per_step_min": float(np.min(times)),
                           "seconds_per_step_max": float(np.max(times)), "seconds_each_step": [float(t) for t in times],
@@ -601,11 +603,15 @@ def main():
     ap.add_argument("--bd-steps", type=int, default=3, help="timed full BD steps after the matvec bench (0 = skip)")
     ap.add_argument("--bd-workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--bd-warmup", type=int, default=1, help="0: time the very first BD step (allocations included)")
+    ap.add_argument("--e2e-warmup", type=int, default=-1, help="warm-up steps of the host-buffer leg (default: --warmup; the "
+                    "kernels are warm from the device-resident leg, so 1 is enough for the seconds-long cfg5 products)")
+    ap.add_argument("--bd-profile-step", type=int, default=1, help="0: skip the extra, untimed, profiled BD step")
     ap.add_argument("--bd-mixed", type=int, default=1, help="also time the double BD step with mixed precision modes 1 and 2 (N=1)")
     ap.add_argument("--bd-gmres-max-iter", type=int, default=200)
     ap.add_argument("--bd-lanczos-max-iter", type=int, default=80)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.e2e_warmup = max(1, args.warmup if args.e2e_warmup < 0 else args.e2e_warmup)
     if args.impl == "reference":
         run_reference(args)
     else:
