@@ -277,7 +277,18 @@ int rbl_set_matvec_mode(rbl_ctx* ctx, int mode);
 int rbl_num_sym_variants(const rbl_ctx* ctx);
 int rbl_sym_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);
 int rbl_set_sym_variant(rbl_ctx* ctx, int idx); /* -1 = automatic */
-/* sources per warp-private reaction-reduction chunk of symmetric variant idx (0: warp butterfly) */
+/* Experiment knob.  The unordered-pair tile triangle is cut into shares of equal chunk COUNT (per CTA, and per
+ * GPU on a partitioned suspension).  w in (0, 1) cuts by COST instead, a diagonal unit -- the ordered loop on
+ * the tiles that hold the self pairs -- weighing w of a symmetric one (by instruction count 0.77 with the wall,
+ * 0.80 in free space).  Measured at cfg2: no gain beyond noise (profiles/r02_part_balance.md), hence the default
+ * w <= 0 or 1: equal counts.  Results do not depend on w beyond summation order. */
+int rbl_set_split_weight(rbl_ctx* ctx, double w);
+/* The cut points themselves (host arithmetic only, no device): bounds[0..grid] = 32-source-chunk indices that
+ * delimit the `grid` CTAs of share `part` of `n_parts` for n_blobs blobs and a target tile of tgt_tile blobs
+ * (a multiple of 256); *total_chunks = chunks of the whole triangle. */
+int rbl_plan_cost_bounds(int n_blobs, int tgt_tile, int grid, int part, int n_parts, double w, long long* bounds,
+                         long long* total_chunks);
+/* sources per warp-private reaction-reduction chunk of symmetric variant idx */
 int rbl_sym_variant_chunk(const rbl_ctx* ctx, int idx);
 int rbl_num_sym2_variants(const rbl_ctx* ctx);
 int rbl_sym2_variant_info(const rbl_ctx* ctx, int idx, int* targets_per_thread, int* threads);

@@ -105,6 +105,8 @@ SYMBOLS = {
     "rbl_evolve_RFD": (_i, [_vp, _vp]),
     "rbl_set_rfd_delta": (_i, [_vp, _d]),
     "rbl_set_split_rand": (_i, [_vp, _i]),
+    "rbl_set_split_weight": (_i, [_vp, _d]),
+    "rbl_plan_cost_bounds": (_i, [_i, _i, _i, _i, _i, _d, _pi64, _pi64]),
     "rbl_set_mixed_precision": (_i, [_vp, _i]),
     "rbl_launch_count": (_i64, [_vp]),
     "rbl_product_count": (_i64, [_vp]),

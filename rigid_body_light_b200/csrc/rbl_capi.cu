@@ -131,6 +131,7 @@ struct rbl_ctx {
   // 0: symmetric square root everywhere; 1 (default): block-Cholesky preconditioned noise inside
   // rbl_bd_step; 2: also in rbl_lanczos_sqrt / rbl_lanczos_sqrt2 (they then return L (G A G^T)^{1/2} W)
   int noise_mode = 1;
+  double split_weight = 0;   // cost of a diagonal unit relative to a symmetric one; <= 0: per-mode estimate, 1: equal counts
   bool split_rand = true;    // BD step: two Brownian increments W1, W2 (c_rigid_obj.cpp:150,943-953); false: one
   double rfd_delta = 0;      // <= 0: default of the precision (1e-4 double like :771, 4e-3 float)
   bool pair_lanczos = true;  // BD step: M^{1/2}W_1 and M^{1/2}W_2 in lockstep over the two-right-hand-side product
@@ -211,6 +212,40 @@ struct Ctx final : rbl_ctx {
       return g != 0 && g == gen && n_ == n && tile_ == tile && b == buf;
     }
   } rec1_state, rec2_state;
+  // equal-cost cut points of the unit triangle (sym_cost_bounds), cached per (n, variant, share)
+  struct BoundsCache {
+    std::vector<long long> host;
+    DevBuf dev;
+    long long key[6] = {-1, -1, -1, -1, -1, -1};
+  } bounds1, bounds2;
+  // Default: equal COUNTS (w = 1).  By instruction count a diagonal unit costs 0.77 (wall: 72 / 93) or
+  // 0.80 (free space: 27 / 33) of a symmetric one, but cutting by that cost changed neither the kernel
+  // time nor the spread between the shares of an 8-way partition beyond run-to-run noise at cfg2
+  // (profiles/r02_part_balance.md: the spread follows the near-tile pattern of the geometry and the
+  // per-launch ramp, not the diagonal units), so the knob stays an experiment (rbl_set_split_weight).
+  double diag_weight() const { return split_weight > 0 ? split_weight : 1.0; }
+  int cost_bounds(BoundsCache& bc, rbl::SymPlan* plan, int variant, int part, int n_parts, const long long** out) {
+    const double w = diag_weight();
+    if (w == 1.0) {  // equal counts: the kernels cut [u0, u1) themselves
+      *out = nullptr;
+      return RBL_OK;
+    }
+    const long long key[6] = {plan->n, variant, part, n_parts, plan->grid, (long long)(w * 1e6)};
+    bool same = bc.dev.p != nullptr;
+    for (int i = 0; i < 6; ++i) same = same && bc.key[i] == key[i];
+    if (!same) {
+      bc.host.assign((size_t)plan->grid + 1, 0);
+      rbl::sym_cost_bounds(plan, part, n_parts, w, bc.host.data());
+      CK(bc.dev.ensure(bc.host.size() * sizeof(long long)));
+      CK(cudaMemcpyAsync(bc.dev.p, bc.host.data(), bc.host.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
+      for (int i = 0; i < 6; ++i) bc.key[i] = key[i];
+    } else {
+      plan->u0 = bc.host.front();
+      plan->u1 = bc.host.back();
+    }
+    *out = bc.dev.template as<long long>();
+    return RBL_OK;
+  }
 
   // mixed precision (double contexts, single GPU): a float mirror of this context on the same stream.
   //  1: GMRES solves run in float inside an iterative refinement whose residual is the DOUBLE operator
@@ -467,6 +502,7 @@ struct Ctx final : rbl_ctx {
     const int v = pick_sym_variant(n);
     rbl::SymArgs<real> A;
     CK(rbl::matvec_sym_plan<real>(v, wall, n, part, n_parts, sm_count, &A.plan));
+    RET(cost_bounds(bounds1, &A.plan, v, part, n_parts, &A.bounds));
     const size_t n_pad = (size_t)A.plan.n_src_tiles * rbl::kSrcTile;
     CK(d_rec.ensure(n_pad * rbl::kRecReals * sizeof(real)));
     CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
@@ -643,6 +679,7 @@ struct Ctx final : rbl_ctx {
     const int v = sym2_variant >= 0 ? sym2_variant : rbl::matvec_sym2_default_variant<real>(wall, n);
     rbl::Sym2Args<real> A;
     CK(rbl::matvec_sym2_plan<real>(v, wall, n, part, n_parts, sm_count, &A.plan));
+    RET(cost_bounds(bounds2, &A.plan, v, part, n_parts, &A.bounds));
     const size_t n_pad = (size_t)A.plan.n_src_tiles * rbl::kSrcTile;
     CK(d_rec2.ensure(n_pad * rbl::kRec2Reals * sizeof(real)));
     CK(d_box_src.ensure(6 * (size_t)A.plan.n_src_tiles * sizeof(float)));
@@ -2178,6 +2215,25 @@ int rbl_update_X_Q_out(rbl_ctx* ctx, const void* U, void* X_out, void* Q_out) {
 int rbl_evolve_RFD(rbl_ctx* ctx, const void* U) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->evolve_RFD(U); }
 int rbl_set_rfd_delta(rbl_ctx* ctx, double delta) { CTX_OR_FAIL(ctx); ctx->rfd_delta = delta > 0 ? delta : 0; return RBL_OK; }
 int rbl_set_mixed_precision(rbl_ctx* ctx, int mode) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->set_mixed(mode); }
+int rbl_plan_cost_bounds(int n_blobs, int tgt_tile, int grid, int part, int n_parts, double w, long long* bounds,
+                         long long* total_chunks) {
+  if (n_blobs <= 0 || tgt_tile <= 0 || tgt_tile % rbl::kSrcTile != 0 || grid < 1 || n_parts < 1 || part < 0 ||
+      part >= n_parts || !bounds)
+    return RBL_ERR_INVALID;
+  rbl::SymPlan plan{};
+  plan.n = n_blobs;
+  plan.n_src_tiles = (n_blobs + rbl::kSrcTile - 1) / rbl::kSrcTile;
+  plan.tgt_tile = tgt_tile;
+  plan.diag = tgt_tile / rbl::kSrcTile;
+  plan.n_tgt_tiles = (n_blobs + tgt_tile - 1) / tgt_tile;
+  const long long I = plan.n_tgt_tiles;
+  plan.units = I * plan.n_src_tiles - (long long)plan.diag * (I * (I - 1) / 2);
+  plan.grid = grid;
+  rbl::sym_cost_bounds(&plan, part, n_parts, w, bounds);
+  if (total_chunks) *total_chunks = plan.units * (rbl::kSrcTile / 32);
+  return RBL_OK;
+}
+int rbl_set_split_weight(rbl_ctx* ctx, double w) { CTX_OR_FAIL(ctx); ctx->split_weight = w > 0 ? w : 0; return RBL_OK; }
 int rbl_set_split_rand(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->split_rand = enable != 0; return RBL_OK; }
 int rbl_set_lanczos_pairing(rbl_ctx* ctx, int enable) { CTX_OR_FAIL(ctx); ctx->pair_lanczos = enable != 0; return RBL_OK; }
 int rbl_num_sym2_variants(const rbl_ctx* ctx) { return ctx ? ctx->num_sym2_variants() : 0; }

@@ -572,85 +572,17 @@ __device__ __forceinline__ void load_full_rec(const double* p, double& x, double
   x = a.x; y = a.y; z = b.x; fx = b.y; fy = c.x; fz = c.y; nz4 = -d.y;
 }
 
-template <typename real>
-__device__ __forceinline__ real warp_sum(real v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// one staged source tile against the thread's T targets, both directions.  Sources are taken
-// two at a time (jj and jj + 16): the first butterfly stage exchanges the two sources'
-// partial sums between the half-warps (transposed reduction), the remaining four stages run
-// on 3 values instead of 6, and the totals land in lane jj (first source) and lane jj + 16
-// (second source).  After 32 sources every lane holds the warp-total reaction of source
-// (j0 + lane) and adds it to the global accumulators (coalesced RED.ADD).
-template <typename real, bool WALL, bool NEAR, int T>
-__device__ __forceinline__ void tile_compute_sym(const real* __restrict__ sb, const PairConsts<real>& C,
-                                                 const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
-                                                 const real (&fxi)[T], const real (&fyi)[T], const real (&fzi)[T],
-                                                 const real (&nz4i)[T], real (&ux)[T], real (&uy)[T],
-                                                 real (&uz)[T], real* __restrict__ raw_tile, int jb, int je) {
-  constexpr bool kTwoLevel = sizeof(real) == 4;  // fp32: per-tile accumulators (see tile_compute)
-  const int lane = threadIdx.x & 31;
-  const bool upper = (lane & 16) != 0;
-  real lx[T], ly[T], lz[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    lx[t] = kTwoLevel ? (real)0 : ux[t];
-    ly[t] = kTwoLevel ? (real)0 : uy[t];
-    lz[t] = kTwoLevel ? (real)0 : uz[t];
-  }
-  for (int j0 = jb; j0 < je; j0 += 32) {
-    real rx = 0, ry = 0, rz = 0;
-#pragma unroll 1
-    for (int jj = 0; jj < 16; ++jj) {
-      real xa, ya, za, fxa, fya, fza, nz4a, xb, yb, zb, fxb, fyb, fzb, nz4b;
-      load_full_rec(sb + (size_t)(j0 + jj) * kRecReals, xa, ya, za, fxa, fya, fza, nz4a);
-      load_full_rec(sb + (size_t)(j0 + jj + 16) * kRecReals, xb, yb, zb, fxb, fyb, fzb, nz4b);
-      real ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xa, ya, za, fxa, fya,
-                                   fza, nz4a, lx[t], ly[t], lz[t], ax, ay, az);
-        pair_sym<real, WALL, NEAR>(C, xi[t], yi[t], zi[t], fxi[t], fyi[t], fzi[t], nz4i[t], xb, yb, zb, fxb, fyb,
-                                   fzb, nz4b, lx[t], ly[t], lz[t], bx, by, bz);
-      }
-      // stage 1: lower half-warp keeps source a, upper keeps source b
-      real kx = upper ? bx : ax, ky = upper ? by : ay, kz = upper ? bz : az;
-      const real sx = upper ? ax : bx, sy = upper ? ay : by, sz = upper ? az : bz;
-      kx += __shfl_xor_sync(0xffffffffu, sx, 16);
-      ky += __shfl_xor_sync(0xffffffffu, sy, 16);
-      kz += __shfl_xor_sync(0xffffffffu, sz, 16);
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        kx += __shfl_xor_sync(0xffffffffu, kx, o);
-        ky += __shfl_xor_sync(0xffffffffu, ky, o);
-        kz += __shfl_xor_sync(0xffffffffu, kz, o);
-      }
-      if ((lane & 15) == jj) { rx = kx; ry = ky; rz = kz; }
-    }
-    real* o = raw_tile + 3 * (size_t)(j0 + lane);
-    atomicAdd(o, rx);
-    atomicAdd(o + 1, ry);
-    atomicAdd(o + 2, rz);
-  }
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    ux[t] = kTwoLevel ? ux[t] + lx[t] : lx[t];
-    uy[t] = kTwoLevel ? uy[t] + ly[t] : ly[t];
-    uz[t] = kTwoLevel ? uz[t] + lz[t] : lz[t];
-  }
-}
-
 // ---- reaction sums through a warp-private shared-memory tile ---------------------------------
-// The butterfly above costs ~19.5 issue slots per source and warp (5 shuffle stages x 3 values).
+// A warp butterfly per source costs ~19.5 issue slots per source and warp (5 shuffle stages x 3 values).
 // Here every lane parks its partial reaction on source j (summed over its T targets) in row
 // (j, component) of a warp-private tile, and after RC sources the tile is read back TRANSPOSED:
 // 32 / RC lanes per source, each sums RC consecutive lane-partials with 128-bit loads and adds its
-// share to the global accumulator (RED.ADD).  3 STS per source + (3 RC/4 LDS.128 + 3 (RC-1) adds
-// + 3 RED) per RC sources  ~=  7 issue slots per source and warp, and the sum order inside the
-// warp is fixed.  Row stride: 3 * stride words = 12 (mod 32) makes the transposed 128-bit reads of
+// share; the 32 / RC partial sums of a source are combined with log2(32 / RC) shuffles and ONE lane per
+// source adds the total to the global accumulator (RED.ADD).  3 STS per source + (3 RC/4 LDS.128 +
+// 3 (RC-1) adds + 3 RED) per RC sources  ~=  7 issue slots per source and warp, and the sum order inside
+// the warp is fixed.  The global accumulators are stored component-major (x[N] y[N] z[N]), so one RED
+// instruction of RC lanes touches RC consecutive words (2 sectors for RC = 16) instead of RC words with
+// stride 3 (6 sectors): the L2 atomic units see a third of the sector operations.  Row stride: 3 * stride words = 12 (mod 32) makes the transposed 128-bit reads of
 // a quarter-warp hit 8 distinct 4-bank groups; the writes are lane-contiguous.
 template <typename real>
 struct RedLayout;
@@ -695,7 +627,7 @@ __device__ __forceinline__ void tile_compute_symt(const real* __restrict__ sb, c
                                                   const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
                                                   const real (&fxi)[T], const real (&fyi)[T], const real (&fzi)[T],
                                                   const real (&nz4i)[T], real (&lx)[T], real (&ly)[T],
-                                                  real (&lz)[T], real* __restrict__ raw_tile,
+                                                  real (&lz)[T], real* __restrict__ raw_tile, size_t raw_ld,
                                                   real* __restrict__ red, int jb, int je) {
   static_assert(RC == 8 || RC == 16 || RC == 32, "reduction chunk");
   constexpr int STR = RedLayout<real>::kStride;
@@ -723,11 +655,19 @@ __device__ __forceinline__ void tile_compute_symt(const real* __restrict__ sb, c
       wb[0] = bx; wb[STR] = by; wb[2 * STR] = bz;
     }
     __syncwarp();
-    const real sx = row_sum<RC>(rd), sy = row_sum<RC>(rd + STR), sz = row_sum<RC>(rd + 2 * STR);
-    real* o = raw_tile + 3 * (size_t)(j0 + src);
-    atomicAdd(o, sx);
-    atomicAdd(o + 1, sy);
-    atomicAdd(o + 2, sz);
+    real sx = row_sum<RC>(rd), sy = row_sum<RC>(rd + STR), sz = row_sum<RC>(rd + 2 * STR);
+#pragma unroll
+    for (int o = RC; o < 32; o <<= 1) {  // the 32 / RC lanes of a source
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (part == 0) {
+      real* o = raw_tile + (j0 + src);
+      atomicAdd(o, sx);
+      atomicAdd(o + raw_ld, sy);
+      atomicAdd(o + 2 * raw_ld, sz);
+    }
     __syncwarp();
   }
 }
@@ -739,10 +679,65 @@ __device__ __host__ __forceinline__ long long sym_row_offset(long long I, int ns
   return I * ns - (long long)diag * (I * (I - 1) / 2);
 }
 
-// RC = 0: reaction sums by the warp butterfly (tile_compute_sym); RC = 8/16/32: through the
-// warp-private shared-memory tile (tile_compute_symt).  Target sums are flushed into the global
+// Reaction sums go through the warp-private shared-memory tile (tile_compute_symt, RC sources per
+// chunk).  Target sums are flushed into the global
 // accumulators (RED.ADD) after every tile unit -- that IS the second summation level of the fp32
 // path, and it frees the 3T registers a running sum per target would hold.
+// source tile of the unit at position `pos` of row I: J = I D (the diagonal units), I D + 1, ..., ns - 1.
+// (Walking odd rows from the far end, so that CTAs on neighbouring rows do not add reaction sums to the
+// same accumulators in lockstep, was measured: no effect beyond run-to-run noise, profiles/r02_part_balance.md.)
+__device__ __host__ __forceinline__ int sym_tile_of(int I, int pos, int ns, int D) {
+  (void)ns;
+  return I * D + pos;
+}
+
+void sym_cost_bounds(SymPlan* plan, int part, int n_parts, double w_diag, long long* bounds) {
+  const int ns = plan->n_src_tiles, D = plan->diag, ntt = plan->n_tgt_tiles, grid = plan->grid;
+  if (!(w_diag > 0.0)) w_diag = 1.0;
+  auto row_units = [&](int I, int* nd) {
+    const int len = ns - I * D;
+    *nd = len < D ? len : D;
+    return len;
+  };
+  double total = 0.0;
+  for (int I = 0; I < ntt; ++I) {
+    int nd;
+    const int len = row_units(I, &nd);
+    total += kSymChunks * (nd * w_diag + (len - nd));
+  }
+  const long long pieces = (long long)n_parts * grid;
+  int I = 0;
+  double before = 0.0;  // cost of the rows above I
+  for (int c = 0; c <= grid; ++c) {
+    const long long q = (long long)part * grid + c;
+    long long f;
+    if (q >= pieces) {
+      f = plan->units * kSymChunks;
+    } else {
+      const double target = total * ((double)q / (double)pieces);
+      for (;;) {
+        int nd;
+        const int len = row_units(I, &nd);
+        const double rc = kSymChunks * (nd * w_diag + (len - nd));
+        if (I + 1 < ntt && before + rc <= target) { before += rc; ++I; } else break;
+      }
+      int nd;
+      const int len = row_units(I, &nd);
+      const double rem = target - before;
+      const double diag_cost = kSymChunks * nd * w_diag;
+      long long in_row = rem < diag_cost ? (long long)(rem / w_diag) : (long long)kSymChunks * nd + (long long)(rem - diag_cost);
+      const long long row_chunks = (long long)kSymChunks * len;
+      if (in_row > row_chunks) in_row = row_chunks;
+      if (in_row < 0) in_row = 0;
+      f = sym_row_offset(I, ns, D) * kSymChunks + in_row;
+    }
+    bounds[c] = f;
+    if (c > 0 && bounds[c] < bounds[c - 1]) bounds[c] = bounds[c - 1];
+  }
+  plan->u0 = bounds[0];
+  plan->u1 = bounds[grid];
+}
+
 template <typename real, int T, int NT, int RC>
 __host__ __device__ constexpr size_t sym_smem_bytes() {
   return (2 * (size_t)kSrcTile * kRecReals + (size_t)(NT / 32) * red_tile_reals<real, RC>()) * sizeof(real);
@@ -763,8 +758,8 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
   // work is cut at the granularity of 32-source chunks (kSymChunks per tile unit) so that the
   // shares of different CTAs -- and of different GPUs -- differ by at most one chunk
   const long long span = A.plan.u1 - A.plan.u0;
-  const long long f0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
-  const long long f1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
+  const long long f0 = A.bounds ? A.bounds[blockIdx.x] : A.plan.u0 + span * blockIdx.x / gridDim.x;
+  const long long f1 = A.bounds ? A.bounds[blockIdx.x + 1] : A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
   if (f0 >= f1) return;
   const long long g0 = f0 / kSymChunks, g_last = (f1 - 1) / kSymChunks, g1 = g_last + 1;
   const int jb_first = (int)(f0 - g0 * kSymChunks) * 32;
@@ -787,7 +782,9 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     }
     I = lo;
   }
-  int J = I * D + (int)(g0 - sym_row_offset(I, ns, D));  // source tile of the first unit
+  // position of the first unit inside its row
+  int pos = (int)(g0 - sym_row_offset(I, ns, D));
+  int J = sym_tile_of(I, pos, ns, D);
   if (tid == 0) {
     mbar_expect_tx(&mbar[0], kTileBytes);
     tma_load_1d(sbuf0, A.rec + (size_t)J * kSrcTile * kRecReals, kTileBytes, &mbar[0]);
@@ -796,19 +793,20 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
   real xi[T], yi[T], zi[T], fxi[T], fyi[T], fzi[T], nz4i[T];
   bool fresh = true;
   const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
+  const size_t raw_ld = (size_t)ns * kSrcTile;  // accumulators: x[raw_ld] y[raw_ld] z[raw_ld]
 
   for (long long g = g0; g < g1; ++g) {
     const int it = (int)(g - g0);
     const int buf = it & 1;
     const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-    const bool row_end = (J + 1 == ns);
+    const bool row_end = (pos + 1 == ns - I * D);
     const int jb = (g == g0) ? jb_first : 0;
     const int je = (g == g_last) ? je_last : kSrcTile;
     const real* cur = buf ? sbuf1 : sbuf0;
     real* nxt = buf ? sbuf0 : sbuf1;
 
     if (tid == 0 && g + 1 < g1) {
-      const int nJ = row_end ? (I + 1) * D : J + 1;
+      const int nJ = row_end ? sym_tile_of(I + 1, 0, ns, D) : sym_tile_of(I, pos + 1, ns, D);
       mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
       tma_load_1d(nxt, A.rec + (size_t)nJ * kSrcTile * kRecReals, kTileBytes, &mbar[buf ^ 1]);
     }
@@ -836,38 +834,32 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym_kernel(const SymArgs<real> 
     if (diagonal) {
       tile_compute<WALL, true, T>(cur, A.C, xi, yi, zi, ux, uy, uz, jb, je);
     } else {
-      real* raw_tile = A.raw + 3 * (size_t)J * kSrcTile;
-      if constexpr (RC == 0) {
-        if (far)
-          tile_compute_sym<real, WALL, false, T>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
-        else
-          tile_compute_sym<real, WALL, true, T>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, jb, je);
-      } else {
-        if (far)
-          tile_compute_symt<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, red, jb, je);
-        else
-          tile_compute_symt<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, red, jb, je);
-      }
+      real* raw_tile = A.raw + (size_t)J * kSrcTile;
+      if (far)
+        tile_compute_symt<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, raw_ld, red, jb, je);
+      else
+        tile_compute_symt<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, fxi, fyi, fzi, nz4i, ux, uy, uz, raw_tile, raw_ld, red, jb, je);
     }
     // flush this unit's target sums (per-tile accumulators: the first summation level)
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int li = I * TT + tid + t * NT;
-      if (li < A.plan.n) {
-        atomicAdd(A.raw + 3 * (size_t)li + 0, ux[t]);
-        atomicAdd(A.raw + 3 * (size_t)li + 1, uy[t]);
-        atomicAdd(A.raw + 3 * (size_t)li + 2, uz[t]);
+      if (li < A.plan.n) {  // component-major accumulators: a warp adds 32 consecutive words per instruction
+        atomicAdd(A.raw + li, ux[t]);
+        atomicAdd(A.raw + raw_ld + li, uy[t]);
+        atomicAdd(A.raw + 2 * raw_ld + li, uz[t]);
       }
     }
     __syncthreads();  // every thread is done with `cur` before it is refilled
 
     if (row_end) {
       ++I;
-      J = I * D;
+      pos = 0;
       fresh = true;
     } else {
-      ++J;
+      ++pos;
     }
+    J = sym_tile_of(I, pos, ns, D);
   }
 }
 
@@ -877,16 +869,17 @@ __global__ void rpy_sym_scale_kernel(const SymArgs<real> A) {
   if (i >= A.plan.n) return;
   real sc = A.C.out_scale;
   if (WALL) sc *= damp(A.rec[(size_t)i * kRecReals + 2], A.C.a, A.C.inv_a);
-  A.out[3 * (size_t)i + 0] = A.raw[3 * (size_t)i + 0] * sc;
-  A.out[3 * (size_t)i + 1] = A.raw[3 * (size_t)i + 1] * sc;
-  A.out[3 * (size_t)i + 2] = A.raw[3 * (size_t)i + 2] * sc;
+  const size_t ld = (size_t)A.plan.n_src_tiles * kSrcTile;
+  A.out[3 * (size_t)i + 0] = A.raw[i] * sc;
+  A.out[3 * (size_t)i + 1] = A.raw[ld + i] * sc;
+  A.out[3 * (size_t)i + 2] = A.raw[2 * ld + i] * sc;
 }
 
-// (T targets per thread, NT threads per CTA, RC reaction-reduction chunk; RC = 0: warp butterfly)
+// (T targets per thread, NT threads per CTA, RC sources per reaction-reduction chunk)
 #define RBL_F32_SYM_VARIANTS(X) \
-  X(6, 256, 16) X(4, 128, 16) X(4, 256, 16) X(5, 256, 16) X(4, 256, 0) X(2, 256, 8) X(1, 256, 8)
+  X(6, 256, 16) X(4, 128, 16) X(4, 256, 16) X(5, 256, 16) X(6, 256, 8) X(2, 256, 8) X(1, 256, 8)
 #define RBL_F64_SYM_VARIANTS(X) \
-  X(4, 256, 16) X(3, 256, 16) X(4, 128, 16) X(3, 256, 0) X(2, 128, 8) X(1, 256, 8)
+  X(4, 256, 16) X(3, 256, 16) X(4, 128, 16) X(3, 256, 8) X(2, 128, 8) X(1, 256, 8)
 
 template <>
 MatvecVariant matvec_sym_variant<float>(int idx) {
@@ -1133,63 +1126,6 @@ __device__ __forceinline__ void tile_compute2_ordered(const real* __restrict__ s
   }
 }
 
-template <typename real, bool WALL, bool NEAR, int T>
-__device__ __forceinline__ void tile_compute_sym2(const real* __restrict__ sb, const PairConsts<real>& C,
-                                                  const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
-                                                  const real (&nz4i)[T], const real (&fi)[T][2][3],
-                                                  real (&u)[T][2][3], real* __restrict__ raw1,
-                                                  real* __restrict__ raw2, int jb, int je) {
-  constexpr bool kTwoLevel = sizeof(real) == 4;
-  const int lane = threadIdx.x & 31;
-  const bool upper = (lane & 16) != 0;
-  real l[T][2][3];
-#pragma unroll
-  for (int t = 0; t < T; ++t)
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) l[t][k][c] = kTwoLevel ? (real)0 : u[t][k][c];
-  for (int j0 = jb; j0 < je; j0 += 32) {
-    real keep[2][3] = {{0, 0, 0}, {0, 0, 0}};
-#pragma unroll 1
-    for (int jj = 0; jj < 16; ++jj) {
-      Rec2<real> sa, sb2;
-      load_rec2(sb + (size_t)(j0 + jj) * kRec2Reals, sa);
-      load_rec2(sb + (size_t)(j0 + jj + 16) * kRec2Reals, sb2);
-      real ra[2][3] = {{0, 0, 0}, {0, 0, 0}}, rb[2][3] = {{0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sa.x, sa.y, sa.z, sa.f, sa.nz4, l[t], ra);
-        pair_symR<real, WALL, NEAR, 2>(C, xi[t], yi[t], zi[t], fi[t], nz4i[t], sb2.x, sb2.y, sb2.z, sb2.f, sb2.nz4, l[t], rb);
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          real kv = upper ? rb[k][c] : ra[k][c];
-          const real sv = upper ? ra[k][c] : rb[k][c];
-          kv += __shfl_xor_sync(0xffffffffu, sv, 16);
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) kv += __shfl_xor_sync(0xffffffffu, kv, o);
-          if ((lane & 15) == jj) keep[k][c] = kv;
-        }
-    }
-    real* o1 = raw1 + 3 * (size_t)(j0 + lane);
-    real* o2 = raw2 + 3 * (size_t)(j0 + lane);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      atomicAdd(o1 + c, keep[0][c]);
-      atomicAdd(o2 + c, keep[1][c]);
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < T; ++t)
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) u[t][k][c] = kTwoLevel ? u[t][k][c] + l[t][k][c] : l[t][k][c];
-}
-
 // Two right-hand sides through the warp-private reduction tile (see tile_compute_symt): 6 rows per
 // source (2 right-hand sides x 3 components), rows ordered component-major, row = (k*3 + c) * RC +
 // source, so that consecutive sources are one row stride apart (36 words = 4 mod 32 in fp32, 68
@@ -1204,7 +1140,8 @@ __device__ __forceinline__ void tile_compute_sym2t(const real* __restrict__ sb, 
                                                    const real (&xi)[T], const real (&yi)[T], const real (&zi)[T],
                                                    const real (&nz4i)[T], const real (&fi)[T][2][3],
                                                    real (&u)[T][2][3], real* __restrict__ raw1,
-                                                   real* __restrict__ raw2, real* __restrict__ red, int jb, int je) {
+                                                   real* __restrict__ raw2, size_t raw_ld, real* __restrict__ red,
+                                                   int jb, int je) {
   static_assert(RC == 8 || RC == 16 || RC == 32, "reduction chunk");
   constexpr int STR = RedLayout<real>::kStride;
   const int lane = threadIdx.x & 31;
@@ -1232,12 +1169,21 @@ __device__ __forceinline__ void tile_compute_sym2t(const real* __restrict__ sb, 
         }
     }
     __syncwarp();
-    real* o1 = raw1 + 3 * (size_t)(j0 + src);
-    real* o2 = raw2 + 3 * (size_t)(j0 + src);
+    real s6[6];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      atomicAdd(o1 + c, row_sum<RC>(rd + (size_t)(c * RC) * STR));
-      atomicAdd(o2 + c, row_sum<RC>(rd + (size_t)((3 + c) * RC) * STR));
+    for (int q = 0; q < 6; ++q) s6[q] = row_sum<RC>(rd + (size_t)(q * RC) * STR);
+#pragma unroll
+    for (int o = RC; o < 32; o <<= 1)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s6[q] += __shfl_xor_sync(0xffffffffu, s6[q], o);
+    if (part == 0) {
+      real* o1 = raw1 + (j0 + src);
+      real* o2 = raw2 + (j0 + src);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        atomicAdd(o1 + c * raw_ld, s6[c]);
+        atomicAdd(o2 + c * raw_ld, s6[3 + c]);
+      }
     }
     __syncwarp();
   }
@@ -1261,8 +1207,8 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
   const int tid = threadIdx.x;
   const int ns = A.plan.n_src_tiles, D = A.plan.diag, ntt = A.plan.n_tgt_tiles;
   const long long span = A.plan.u1 - A.plan.u0;
-  const long long f0 = A.plan.u0 + span * blockIdx.x / gridDim.x;
-  const long long f1 = A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
+  const long long f0 = A.bounds ? A.bounds[blockIdx.x] : A.plan.u0 + span * blockIdx.x / gridDim.x;
+  const long long f1 = A.bounds ? A.bounds[blockIdx.x + 1] : A.plan.u0 + span * (blockIdx.x + 1) / gridDim.x;
   if (f0 >= f1) return;
   const long long g0 = f0 / kSymChunks, g_last = (f1 - 1) / kSymChunks, g1 = g_last + 1;
   const int jb_first = (int)(f0 - g0 * kSymChunks) * 32;
@@ -1284,7 +1230,8 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
     }
     I = lo;
   }
-  int J = I * D + (int)(g0 - sym_row_offset(I, ns, D));
+  int pos = (int)(g0 - sym_row_offset(I, ns, D));
+  int J = sym_tile_of(I, pos, ns, D);
   if (tid == 0) {
     mbar_expect_tx(&mbar[0], kTileBytes);
     tma_load_1d(sbuf0, A.rec + (size_t)J * kSrcTile * kRec2Reals, kTileBytes, &mbar[0]);
@@ -1293,20 +1240,20 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
   real xi[T], yi[T], zi[T], nz4i[T], fi[T][2][3];
   bool fresh = true;
   const double near2 = (double)A.C.four_a2 * (1.0 + 1e-6);
-  const size_t raw_ld = 3 * (size_t)ns * kSrcTile;
+  const size_t raw_ld = (size_t)ns * kSrcTile;  // accumulators: [right-hand side][x y z][raw_ld]
 
   for (long long g = g0; g < g1; ++g) {
     const int it = (int)(g - g0);
     const int buf = it & 1;
     const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-    const bool row_end = (J + 1 == ns);
+    const bool row_end = (pos + 1 == ns - I * D);
     const int jb = (g == g0) ? jb_first : 0;
     const int je = (g == g_last) ? je_last : kSrcTile;
     real* cur = buf ? sbuf1 : sbuf0;
     real* nxt = buf ? sbuf0 : sbuf1;
 
     if (tid == 0 && g + 1 < g1) {
-      const int nJ = row_end ? (I + 1) * D : J + 1;
+      const int nJ = row_end ? sym_tile_of(I + 1, 0, ns, D) : sym_tile_of(I, pos + 1, ns, D);
       mbar_expect_tx(&mbar[buf ^ 1], kTileBytes);
       tma_load_1d(nxt, A.rec + (size_t)nJ * kSrcTile * kRec2Reals, kTileBytes, &mbar[buf ^ 1]);
     }
@@ -1343,19 +1290,12 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
     if (diagonal) {
       tile_compute2_ordered<real, WALL, T>(cur, A.C, xi, yi, zi, u, jb, je);
     } else {
-      real* raw1 = A.raw + 3 * (size_t)J * kSrcTile;
-      real* raw2 = raw1 + raw_ld;
-      if constexpr (RC == 0) {
-        if (far)
-          tile_compute_sym2<real, WALL, false, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
-        else
-          tile_compute_sym2<real, WALL, true, T>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, jb, je);
-      } else {
-        if (far)
-          tile_compute_sym2t<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, red, jb, je);
-        else
-          tile_compute_sym2t<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, red, jb, je);
-      }
+      real* raw1 = A.raw + (size_t)J * kSrcTile;  // [right-hand side][component][blob]
+      real* raw2 = raw1 + 3 * raw_ld;
+      if (far)
+        tile_compute_sym2t<real, WALL, false, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, raw_ld, red, jb, je);
+      else
+        tile_compute_sym2t<real, WALL, true, T, RC>(cur, A.C, xi, yi, zi, nz4i, fi, u, raw1, raw2, raw_ld, red, jb, je);
     }
     // flush this unit's target sums (the per-tile accumulators are the first summation level)
 #pragma unroll
@@ -1365,18 +1305,19 @@ __global__ void __launch_bounds__(NT) rpy_matvec_sym2_kernel(const Sym2Args<real
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) atomicAdd(A.raw + k * raw_ld + 3 * (size_t)li + c, u[t][k][c]);
+          for (int c = 0; c < 3; ++c) atomicAdd(A.raw + (size_t)(3 * k + c) * raw_ld + li, u[t][k][c]);
       }
     }
     __syncthreads();
 
     if (row_end) {
       ++I;
-      J = I * D;
+      pos = 0;
       fresh = true;
     } else {
-      ++J;
+      ++pos;
     }
+    J = sym_tile_of(I, pos, ns, D);
   }
 }
 
@@ -1386,16 +1327,16 @@ __global__ void rpy_sym2_scale_kernel(const Sym2Args<real> A) {
   if (i >= A.plan.n) return;
   real sc = A.C.out_scale;
   if (WALL) sc *= damp(A.rec[(size_t)i * kRec2Reals + 2], A.C.a, A.C.inv_a);
-  const size_t raw_ld = 3 * (size_t)A.plan.n_src_tiles * kSrcTile;
+  const size_t raw_ld = (size_t)A.plan.n_src_tiles * kSrcTile;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    A.out1[3 * (size_t)i + c] = A.raw[3 * (size_t)i + c] * sc;
-    A.out2[3 * (size_t)i + c] = A.raw[raw_ld + 3 * (size_t)i + c] * sc;
+    A.out1[3 * (size_t)i + c] = A.raw[(size_t)c * raw_ld + i] * sc;
+    A.out2[3 * (size_t)i + c] = A.raw[(size_t)(3 + c) * raw_ld + i] * sc;
   }
 }
 
-#define RBL_F32_SYM2_VARIANTS(X) X(3, 256, 8) X(4, 128, 8) X(4, 128, 0) X(2, 256, 8) X(1, 256, 8)
-#define RBL_F64_SYM2_VARIANTS(X) X(3, 256, 8) X(2, 256, 8) X(2, 256, 0) X(1, 256, 8)
+#define RBL_F32_SYM2_VARIANTS(X) X(3, 256, 8) X(4, 128, 8) X(4, 256, 8) X(2, 256, 8) X(1, 256, 8)
+#define RBL_F64_SYM2_VARIANTS(X) X(3, 256, 8) X(2, 256, 8) X(2, 128, 8) X(1, 256, 8)
 
 template <>
 int matvec_sym2_num_variants<float>() {

@@ -113,10 +113,19 @@ struct SymArgs {
   const float* box_tgt;
   real* raw;   // 3 * n_src_tiles * kSrcTile accumulators, zeroed by the launcher
   real* out;   // 3 * n
+  const long long* bounds;  // grid + 1 cut points of [u0, u1) (equal-COST shares, sym_cost_bounds); null: equal counts
   SymPlan plan;
   PairConsts<real> C;
   int wall;
 };
+
+// Equal-COST cuts of the unit triangle.  A diagonal unit (source tile inside the target tile) runs the
+// ordered loop on T x 256 ordered pairs and costs w_diag (< 1) of a symmetric unit, and short rows hold
+// relatively more of them: equal COUNTS would let the CTAs -- and, on a partitioned suspension, the GPUs
+// -- that own the end of the triangle finish ~1-2 % early.  Fills bounds[0..grid] with the cut points of
+// share `part` of `n_parts` (32-source chunk indices, non-decreasing) and sets plan->u0 / plan->u1 to
+// the share's ends.  Pure host arithmetic, O(rows + grid).
+void sym_cost_bounds(SymPlan* plan, int part, int n_parts, double w_diag, long long* bounds);
 
 template <typename real>
 int matvec_sym_num_variants();
@@ -146,6 +155,7 @@ struct Sym2Args {
   real* raw;         // 2 x (3 * n_src_tiles * kSrcTile) accumulators, zeroed by the launcher
   real* out1;        // 3 * n
   real* out2;        // 3 * n
+  const long long* bounds;  // see SymArgs
   SymPlan plan;
   PairConsts<real> C;
   int wall;
