@@ -362,9 +362,14 @@ struct Ctx final : rbl_ctx {
     CK(cudaStreamSynchronize(stream));
     cfg_set = true;
     r_valid = false;
-    // the reference keeps a built PC across setConfig (only evolve_X_Q resets PC_mat_Set,
-    // :877); it cannot survive a change of the number of bodies, so rebuild in that case
-    if (pc_set && pc_n_bod != n_bod) pc_set = false;
+    // DELIBERATE DEVIATION.  The reference keeps a built preconditioner across setConfig (only
+    // evolve_X_Q resets PC_mat_Set, :877): apply_PC then mixes the OLD invM / N_lu with the NEW K
+    // (:601-610).  Here the factors are device-resident and partly expressed through the current
+    // configuration (rotated shared free-space factor, K products in pc_finish), so a kept PC would be
+    // neither the reference's stale one nor a fresh one.  The preconditioner is therefore rebuilt at its
+    // next use: apply_PC after set_config is the preconditioner OF THAT CONFIGURATION (what a user of
+    // the reference gets by calling evolve / constructing anew).  tests/test_gpu_rigid.py pins this.
+    pc_set = false;
     return RBL_OK;
   }
 
@@ -628,6 +633,38 @@ struct Ctx final : rbl_ctx {
   }
   int csync() { return agree(sync()); }
 
+  // Partitioned mode: every allocation and plan a product needs, made BEFORE the first collective of a
+  // driver and agreed between the ranks (agree()), so that an out-of-memory or a failed plan on one rank
+  // surfaces as the same error everywhere instead of leaving the other ranks inside the next collective.
+  int reserve_comm_workspace(bool two_rhs) {
+    if (!comm) return RBL_OK;
+    const int n = (int)comm->n_all;
+    const size_t n3 = 3 * (size_t)n;
+    rbl::SymPlan plan;
+    CK(rbl::matvec_sym_plan<real>(pick_sym_variant(n), wall, n, comm->rank, comm->world, sm_count, &plan));
+    size_t n_pad = (size_t)plan.n_src_tiles * rbl::kSrcTile;
+    const void* before = d_r_all.p;
+    CK(d_r_all.ensure(2 * n3 * sizeof(real)));
+    if (d_r_all.p != before) r_all_valid = false;
+    CK(d_lam_all.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
+    CK(d_mbuf.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
+    CK(d_rec.ensure(n_pad * rbl::kRecReals * sizeof(real)));
+    CK(d_raw.ensure(3 * n_pad * sizeof(real)));
+    size_t tgt_tiles = (size_t)plan.n_tgt_tiles;
+    if (two_rhs) {
+      const int v2 = sym2_variant >= 0 ? sym2_variant : rbl::matvec_sym2_default_variant<real>(wall, n);
+      CK(rbl::matvec_sym2_plan<real>(v2, wall, n, comm->rank, comm->world, sm_count, &plan));
+      n_pad = (size_t)plan.n_src_tiles * rbl::kSrcTile;
+      CK(d_rec2.ensure(n_pad * rbl::kRec2Reals * sizeof(real)));
+      CK(d_raw2.ensure(2 * 3 * n_pad * sizeof(real)));
+      tgt_tiles = std::max(tgt_tiles, (size_t)plan.n_tgt_tiles);
+    }
+    CK(d_box_src.ensure(6 * (size_t)plan.n_src_tiles * sizeof(float)));
+    CK(d_box_tgt.ensure(6 * tgt_tiles * sizeof(float)));
+    return RBL_OK;
+  }
+  int agree_workspace(bool two_rhs) { return comm ? agree(reserve_comm_workspace(two_rhs)) : (int)RBL_OK; }
+
   // out_local = rows of this rank of  B M B F  where F_local / r_local are this rank's slices.
   // Single context: the plain product.  Partitioned: all-gather F (and the positions, unless they
   // are the cached configuration), this rank's share of the unordered-pair work over ALL blobs,
@@ -806,6 +843,15 @@ struct Ctx final : rbl_ctx {
     if (!cfg_set) return fail(RBL_ERR_STATE, "ERROR CONFIG NOT INITIALIZED YET!!");
     if (dev) return dev_saddle(static_cast<const real*>(x), static_cast<real*>(out));
     const size_t bytes = sys_size() * sizeof(real);
+    if (comm) {  // allocations agreed before the first collective
+      int st = reserve_comm_workspace(false);
+      if (st == RBL_OK && (d_in0.ensure(bytes) != cudaSuccess || d_out0.ensure(bytes) != cudaSuccess)) {
+        cudaGetLastError();
+        st = fail(RBL_ERR_NOMEM, "apply_saddle: out of device memory");
+      }
+      st = agree(st);
+      if (st != RBL_OK) return st;
+    }
     CK(d_in0.ensure(bytes));
     CK(d_out0.ensure(bytes));
     RET(h2d(d_in0.p, x, bytes));
@@ -1165,7 +1211,9 @@ struct Ctx final : rbl_ctx {
     if (restart < 1 || max_iter < 1) return fail(RBL_ERR_INVALID, "gmres: restart and max_iter must be >= 1");
     RET(need_K());
     if (!pc_set || comm) {  // lazily built like the reference (:591-596); every rank must agree it exists
-      const int st = agree(pc_set ? (int)RBL_OK : build_pc());
+      int st = reserve_comm_workspace(false);
+      if (st == RBL_OK && !pc_set) st = build_pc();
+      st = agree(st);
       if (st != RBL_OK) return st;
     }
     const size_t n = sys_size(), n_head = 3 * (size_t)N();
@@ -1325,6 +1373,7 @@ struct Ctx final : rbl_ctx {
     if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
     RET(need_K());
     bool pc = false;
+    RET(agree_workspace(false));
     RET(want_noise_pc(precondition, &pc));
     const size_t n = 3 * (size_t)N();
     const int nb = (int)N();
@@ -1593,6 +1642,7 @@ struct Ctx final : rbl_ctx {
     if (max_iter < 1) return fail(RBL_ERR_INVALID, "lanczos: max_iter must be >= 1");
     RET(need_K());
     bool pc = false;
+    RET(agree_workspace(true));
     RET(want_noise_pc(precondition, &pc));
     const size_t n = 3 * (size_t)N();
     const int m = max_iter;
@@ -1886,19 +1936,27 @@ struct Ctx final : rbl_ctx {
     RET(need_K());
     const size_t n3 = 3 * (size_t)N(), n6 = 6 * (size_t)n_bod, n = n3 + n6;
     const int nb = (int)N();
-    CK(d_rhs.ensure(n * sizeof(real)));
-    CK(d_sol.ensure(n * sizeof(real)));
+    {  // every buffer of the step, allocated and (partitioned mode) agreed before the first collective
+      int st_alloc = [&]() -> int {
+        CK(d_rhs.ensure(n * sizeof(real)));
+        CK(d_sol.ensure(n * sizeof(real)));
+        if (brownian) {
+          for (DevBuf* b : {&d_mh1, &d_mh2, &d_rfd, &d_noise, &d_rp, &d_t1, &d_t2, &d_wr}) CK(b->ensure(n3 * sizeof(real)));
+          CK(d_uom.ensure(n6 * sizeof(real)));
+          for (DevBuf* b : {&d_Xs, &d_Xp}) CK(b->ensure(3 * (size_t)n_bod * sizeof(real)));
+          for (DevBuf* b : {&d_Qs, &d_Qp}) CK(b->ensure(4 * (size_t)n_bod * sizeof(real)));
+        }
+        return reserve_comm_workspace(brownian && split_rand && pair_lanczos);
+      }();
+      if (comm) st_alloc = agree(st_alloc);
+      if (st_alloc != RBL_OK) return st_alloc;
+    }
     real* rhs = d_rhs.as<real>();
     real* sol = d_sol.as<real>();
     if (slip) RET(h2d(rhs, slip, n3 * sizeof(real)));
     else CK(cudaMemsetAsync(rhs, 0, n3 * sizeof(real), stream));
     RET(h2d(rhs + n3, F_ext, n6 * sizeof(real)));
     if (brownian) {
-      for (DevBuf* b : {&d_mh1, &d_mh2, &d_rfd, &d_noise, &d_rp, &d_t1, &d_t2}) CK(b->ensure(n3 * sizeof(real)));
-      CK(d_uom.ensure(n6 * sizeof(real)));
-      for (DevBuf* b : {&d_Xs, &d_Xp}) CK(b->ensure(3 * (size_t)n_bod * sizeof(real)));
-      for (DevBuf* b : {&d_Qs, &d_Qp}) CK(b->ensure(4 * (size_t)n_bod * sizeof(real)));
-      CK(d_wr.ensure(n3 * sizeof(real)));
       real* w1 = d_noise.as<real>();
       real* w2 = d_rfd.as<real>();  // d_rfd is free until the RFD below
       real* noise = d_wr.as<real>();  // W_r of the random finite difference

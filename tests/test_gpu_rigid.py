@@ -124,13 +124,27 @@ def test_evolve_matches_oracle_and_invalidates_pc(orc, precision):
     assert not np.array_equal(before, after)
 
 
-def test_set_config_keeps_a_built_pc_like_the_reference(orc):
-    """setConfig does not reset PC_mat_Set (only evolve_X_Q does, c_rigid_obj.cpp:877)."""
-    g = load_golden("case_touch_free")
-    cb = _solver(g, "double")
-    built = cb.apply_PC(g["vec"])
-    cb.set_config(g["X"] + 0.0, g["Q"])  # same configuration
-    assert np.array_equal(cb.apply_PC(g["vec"]), built)
+@pytest.mark.parametrize("block", [False, True])
+def test_set_config_rebuilds_the_pc_for_the_new_configuration(orc, block):
+    """The reference's setConfig leaves PC_mat_Set alone (only evolve_X_Q resets it, c_rigid_obj.cpp:877), so
+    its apply_PC then mixes the old invM / N_lu with the new K.  Deliberate deviation (rbl_capi.cu
+    set_config): the preconditioner is rebuilt, so apply_PC after set_config is the preconditioner of THAT
+    configuration -- same numbers as a solver constructed there, and as the oracle's fresh PC."""
+    g = load_golden("case_touch_wall")
+    cb = _solver(g, "double", block=block)
+    first = cb.apply_PC(g["vec"])
+    cb.set_config(g["X"] + 0.0, g["Q"])  # same configuration: same numbers
+    check(rel_err(cb.apply_PC(g["vec"]), first), 1e-15)
+    X2 = g["X"] + np.array([0.3, -0.2, 0.25])
+    Q2 = np.roll(g["Q"], 1, axis=0)
+    cb.set_config(X2, Q2)
+    moved = cb.apply_PC(g["vec"])
+    fresh = type(cb)(g["cfg"], X2, Q2, float(g["a"]), float(g["eta"]), float(g["dt"]), wall_PC=True, block_PC=block,
+                     precision="double").apply_PC(g["vec"])
+    assert np.array_equal(moved, fresh)
+    want = orc.PC(X2, orc.normalize_quats(Q2), orc.remove_mean(g["cfg"]), float(g["a"]), float(g["eta"]), True, block).apply(g["vec"])
+    check(rel_err(moved, want), TOL_PC["double"])
+    assert rel_err(moved, first) > 1e-3
 
 
 @pytest.mark.parametrize("block", [False, True])
