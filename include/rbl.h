@@ -61,7 +61,9 @@ int rbl_set_parameters(rbl_ctx* ctx, double a, double dt, double kBT, double eta
  * preconditioner and apply_M, like PC_wall in the reference. */
 int rbl_set_flags(rbl_ctx* ctx, int block_pc, int wall);
 /* setConfig (:201-233): X 3*n_bod, Q 4*n_bod as [w,x,y,z]; quaternions are normalised.
- * Like the reference it does NOT invalidate an already built preconditioner. */
+ * DEVIATION: the reference leaves PC_mat_Set alone here (only evolve_X_Q resets it, :877), so its next
+ * apply_PC mixes the old invM / N_lu with the new K.  Here the preconditioner is rebuilt at its next
+ * use: apply_PC after rbl_set_config is the preconditioner of that configuration. */
 int rbl_set_config(rbl_ctx* ctx, const void* X, const void* Q, int n_bod);
 /* getConfig (:235-255) */
 int rbl_get_config(rbl_ctx* ctx, void* X, void* Q);
@@ -81,7 +83,15 @@ int rbl_KT_dot(rbl_ctx* ctx, const void* lambda, void* out);
 int rbl_Kinv_dot(rbl_ctx* ctx, const void* V, void* out);
 int rbl_KTinv_dot(rbl_ctx* ctx, const void* F, void* out);
 /* apply_M (:641-659): U = M F, or B M B F with the wall; n_blobs is free (it need not
- * equal n_bod*n_blb, tests/test_interface.py:171-177). F, r, out: 3*n_blobs */
+ * equal n_bod*n_blb, tests/test_interface.py:171-177). F, r, out: 3*n_blobs.
+ * Reproducibility: the default (symmetric) product evaluates every unordered pair once and adds the
+ * two reactions with floating-point atomics (RED.ADD), so two runs agree to rounding (~1e-7 / 1e-16
+ * relative), not bit for bit; the sum order INSIDE a warp is fixed.  rbl_set_matvec_mode(ctx, 1) selects
+ * the ordered kernel, which is bit-reproducible (per-CTA partial sums added in CTA order, no atomics)
+ * at ~0.72x the speed -- the deterministic path for a bitwise-repeatable trajectory.
+ * DEVIATION: two DISTINCT blobs closer than 1e-12 a abort the reference ("TWO BLOBS ARE OVERLAPPING",
+ * exit(), :53-58); here such a pair is evaluated with the overlap formula at r -> 0 (the self-mobility
+ * block), finite and continuous, and no error is raised. */
 int rbl_apply_M(rbl_ctx* ctx, const void* F, const void* r, int n_blobs, void* out);
 /* apply_PC (:589-616): in/out 3*N + 6*n_bod, exact inverse of [Mt -K; -K^T 0] */
 int rbl_apply_PC(rbl_ctx* ctx, const void* in, void* out);

@@ -105,21 +105,34 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// r_{b,k} = R(q_b) ref_k + X_b   (get_r_vecs / single_body_pos / multi_body_pos, c_rigid_obj.cpp:257-300).
+// One CTA per body, one thread per OUTPUT ELEMENT: the body's 3 n_blb reals are contiguous in r, so the
+// stores of a warp are 32 consecutive words (the thread-per-blob form wrote 12 partial sectors per store
+// instruction, 3x the L1->L2 sector traffic, and spent ~95 instructions per blob on a per-thread
+// quaternion-to-rotation and an integer division by n_blb: it was issue-bound at 72 % busy, not HBM-bound,
+// profiles/r02_on_kernels_ncu.md).  The rotation matrix is computed once per CTA into shared memory.
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, int n_bod, int n_blb,
-                                   real* __restrict__ r) {
-  // 32-bit index arithmetic on purpose: a 64-bit division per blob (a ~100-instruction library
-  // routine) made this kernel instruction-bound at 0.41 of the HBM peak; N < 2^31 is checked by the launcher
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (unsigned)n_bod * (unsigned)n_blb) return;
-  const unsigned b = i / (unsigned)n_blb, k = i - b * (unsigned)n_blb;
-  real R[9];
-  quat_to_rot(Q + 4 * (size_t)b, R);
-  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
-  r[3 * (size_t)i + 0] = R[0] * cx + R[1] * cy + R[2] * cz + X[3 * (size_t)b + 0];
-  r[3 * (size_t)i + 1] = R[3] * cx + R[4] * cy + R[5] * cz + X[3 * (size_t)b + 1];
-  r[3 * (size_t)i + 2] = R[6] * cx + R[7] * cy + R[8] * cz + X[3 * (size_t)b + 2];
+                                   const real* __restrict__ ref, int n_blb, real* __restrict__ r) {
+  __shared__ real RX[12];  // rows of R, then X_b
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    real R[9];
+    quat_to_rot(Q + 4 * (size_t)b, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) RX[i] = R[i];
+    RX[9] = X[3 * (size_t)b];
+    RX[10] = X[3 * (size_t)b + 1];
+    RX[11] = X[3 * (size_t)b + 2];
+  }
+  __syncthreads();
+  const int n3 = 3 * n_blb;
+  real* __restrict__ out = r + (size_t)b * n3;
+  for (int e = threadIdx.x; e < n3; e += blockDim.x) {
+    const int k = e / 3, c = e - 3 * k;  // division by a literal: a multiply and a shift
+    const real* row = RX + 3 * c;
+    out[e] = fma(row[0], ref[3 * k], fma(row[1], ref[3 * k + 1], fma(row[2], ref[3 * k + 2], RX[9 + c])));
+  }
 }
 template <typename real>
 cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod, int n_blb,
@@ -127,7 +140,9 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
-  place_blobs_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, Q, ref, n_bod, n_blb, r);
+  const int n3 = 3 * n_blb;
+  const int threads = n3 >= 256 ? 256 : ((n3 + 31) / 32) * 32;
+  place_blobs_kernel<real><<<n_bod, threads, 0, s>>>(X, Q, ref, n_blb, r);
   return cudaGetLastError();
 }
 

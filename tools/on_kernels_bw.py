@@ -52,6 +52,22 @@ def main():
             "apply_PC_diag (2 launches)": (lambda: ctx.call("rbl_dev_apply_PC", x.data_ptr(), outx.data_ptr()),
                                            (3 * 3 * n + (1 + 6 + 1 + 1) * 3 * n) * sz),
         }
+        # references on the SAME buffers: a write-only fill and a read+write copy (what the denominators mean)
+        for name, op, nbytes in (("reference: fill (write 3N)", lambda: out3.zero_(), 3 * n * sz),
+                                 ("reference: copy (read 3N, write 3N)", lambda: out3.copy_(lam), 2 * 3 * n * sz)):
+            for _ in range(3):
+                op()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                op()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(json.dumps({"kernel": name, "precision": precision, "blobs": n, "ms": ms, "algorithmic_bytes": nbytes,
+                              "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}),
+                  flush=True)
         for name, (fn, nbytes) in cases.items():
             for _ in range(3):
                 fn()
