@@ -106,32 +106,41 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
 }
 
 // r_{b,k} = R(q_b) ref_k + X_b   (get_r_vecs / single_body_pos / multi_body_pos, c_rigid_obj.cpp:257-300).
-// One CTA per body, one thread per OUTPUT ELEMENT: the body's 3 n_blb reals are contiguous in r, so the
-// stores of a warp are 32 consecutive words (the thread-per-blob form wrote 12 partial sectors per store
-// instruction, 3x the L1->L2 sector traffic, and spent ~95 instructions per blob on a per-thread
-// quaternion-to-rotation and an integer division by n_blb: it was issue-bound at 72 % busy, not HBM-bound,
-// profiles/r02_on_kernels_ncu.md).  The rotation matrix is computed once per CTA into shared memory.
+// One CTA per group of kPlaceBodies-at-most bodies, one thread per OUTPUT ELEMENT: a body's 3 n_blb reals
+// are contiguous in r, so the stores of a warp are 32 consecutive words (the thread-per-blob form wrote 12
+// partial sectors per store instruction, 3x the L1->L2 sector traffic, and spent ~95 instructions per blob
+// on a per-thread quaternion-to-rotation and an integer division by n_blb: 72 % issue-busy, 9 % of DRAM
+// throughput, profiles/r02_on_kernels_ncu.md).  The rotation matrices of the group are computed by the
+// first threads of the CTA into shared memory, all at once: one dependent-load latency per ~6000 outputs
+// (one CTA per body was launch/latency bound: 68 CTAs per SM, each waiting ~1.5 us for its quaternion).
+constexpr int kPlaceBodies = 64;
 template <typename real>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, int n_blb, real* __restrict__ r) {
-  __shared__ real RX[12];  // rows of R, then X_b
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
+                                   const real* __restrict__ ref, int n_bod, int n_blb, int per_cta,
+                                   real* __restrict__ r) {
+  __shared__ real RX[kPlaceBodies][12];  // rows of R, then X_b
+  const int b0 = blockIdx.x * per_cta;
+  const int nb = min(per_cta, n_bod - b0);
+  if ((int)threadIdx.x < nb) {
+    const int b = b0 + threadIdx.x;
     real R[9];
     quat_to_rot(Q + 4 * (size_t)b, R);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) RX[i] = R[i];
-    RX[9] = X[3 * (size_t)b];
-    RX[10] = X[3 * (size_t)b + 1];
-    RX[11] = X[3 * (size_t)b + 2];
+    for (int i = 0; i < 9; ++i) RX[threadIdx.x][i] = R[i];
+    RX[threadIdx.x][9] = X[3 * (size_t)b];
+    RX[threadIdx.x][10] = X[3 * (size_t)b + 1];
+    RX[threadIdx.x][11] = X[3 * (size_t)b + 2];
   }
   __syncthreads();
   const int n3 = 3 * n_blb;
-  real* __restrict__ out = r + (size_t)b * n3;
-  for (int e = threadIdx.x; e < n3; e += blockDim.x) {
-    const int k = e / 3, c = e - 3 * k;  // division by a literal: a multiply and a shift
-    const real* row = RX + 3 * c;
-    out[e] = fma(row[0], ref[3 * k], fma(row[1], ref[3 * k + 1], fma(row[2], ref[3 * k + 2], RX[9 + c])));
+  for (int bl = 0; bl < nb; ++bl) {
+    real* __restrict__ out = r + (size_t)(b0 + bl) * n3;
+    const real* rx = RX[bl];
+    for (int e = threadIdx.x; e < n3; e += blockDim.x) {
+      const int k = e / 3, c = e - 3 * k;  // division by a literal: a multiply and a shift
+      const real* row = rx + 3 * c;
+      out[e] = fma(row[0], ref[3 * k], fma(row[1], ref[3 * k + 1], fma(row[2], ref[3 * k + 2], rx[9 + c])));
+    }
   }
 }
 template <typename real>
@@ -141,8 +150,13 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
   const int n3 = 3 * n_blb;
-  const int threads = n3 >= 256 ? 256 : ((n3 + 31) / 32) * 32;
-  place_blobs_kernel<real><<<n_bod, threads, 0, s>>>(X, Q, ref, n_blb, r);
+  const int threads = n3 >= 256 ? 256 : std::max(64, ((n3 + 31) / 32) * 32);
+  int per_cta = std::max(1, std::min(kPlaceBodies, 6144 / n3));  // ~6000 outputs per CTA
+  per_cta = std::min(per_cta, threads);
+  // keep at least ~4 CTAs per SM in flight for small suspensions
+  while (per_cta > 1 && (n_bod + per_cta - 1) / per_cta < 592) per_cta = (per_cta + 1) / 2;
+  const int blocks = (n_bod + per_cta - 1) / per_cta;
+  place_blobs_kernel<real><<<blocks, threads, 0, s>>>(X, Q, ref, n_bod, n_blb, per_cta, r);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,14 @@ def cfg1(args):
         res = np.linalg.norm(cb.apply_saddle(x) - rhs) / np.linalg.norm(rhs)
         out["gpu_block_pc" if block else "gpu_diag_pc"] = {"seconds": dt, "iterations": int(iters), "relres": float(relres),
                                                              "true_residual": float(res)}
+    cbm = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=True, precision="double")
+    cbm.set_mixed_precision(1)  # float GMRES corrections, double residual (same stopping rule)
+    cbm.gmres(rhs, tol=1e-8, restart=60, max_iter=300)
+    t0 = time.perf_counter()
+    xm, iters, relres = cbm.gmres(rhs, tol=1e-8, restart=60, max_iter=300)
+    dt = time.perf_counter() - t0
+    out["gpu_block_pc_mixed_precision"] = {"seconds": dt, "float_iterations": int(iters), "relres": float(relres),
+                                           "true_residual": float(np.linalg.norm(cb.apply_saddle(xm) - rhs) / np.linalg.norm(rhs))}
     if args.cpu:
         from scipy.sparse.linalg import LinearOperator, gmres
 
