@@ -43,7 +43,8 @@ def main():
     rhs = np.concatenate([np.zeros(n3), rng.standard_normal(n6)])
     W = [rng.standard_normal(n3) for _ in range(3)]
     F_ext = np.tile(np.array([0, 0, -1.0, 0, 0, 0]), n_bodies)
-    # tolerances ~10x the errors observed on B200 (printed below; a single context sums in another order)
+    # tolerances ~10x the worst errors observed on B200 at world sizes 1, 2, 3, 4 and 8 (profiles/
+    # r02_partitioned_tests_8gpu.log; every value is printed again below; a single context sums in another order)
     for precision, tol in (("double", 1e-12), ("single", 1e-5)):
         for block in (False, True):
             one = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=block, precision=precision)
@@ -70,14 +71,14 @@ def main():
             x, it, rr = part.gmres(part.slice_system(rhs), tol=gt, restart=40, max_iter=120)
             x1, it1, rr1 = one.gmres(rhs, tol=gt, restart=40, max_iter=120)
             assert rr <= gt and abs(it - it1) <= 2, ("gmres", precision, block, it, it1, rr)
-            chk(rel(part.gather_system(x), x1), 1e-10 if precision == "double" else 5e-5, "gmres x", precision, block)
+            chk(rel(part.gather_system(x), x1), 1e-12 if precision == "double" else 3e-5, "gmres x", precision, block)
             # Lanczos square root
             lt = 1e-9 if precision == "double" else 1e-5
             y, k = part.brownian_sqrt(part.slice_blobs(W[0]), tol=lt, max_iter=80)
             y1, k1 = one.brownian_sqrt(W[0], tol=lt, max_iter=80)
             parts = [None] * world
             dist.all_gather_object(parts, y)
-            chk(rel(np.concatenate(parts), y1), 1e-10 if precision == "double" else 1e-5, "lanczos", precision, k, k1)
+            chk(rel(np.concatenate(parts), y1), 1e-13 if precision == "double" else 5e-6, "lanczos", precision, k, k1)
             # full Brownian step: same noise, same step
             noise_l = tuple(part.slice_blobs(w) for w in W)
             U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, noise_local=noise_l, tol=gt, restart=40,
@@ -86,7 +87,7 @@ def main():
                                        lanczos_tol=lt, lanczos_max_iter=80)
             parts = [None] * world
             dist.all_gather_object(parts, U)
-            chk(rel(np.concatenate(parts), U1), 1e-10 if precision == "double" else 5e-5, "bd_step U", precision, block)
+            chk(rel(np.concatenate(parts), U1), 1e-12 if precision == "double" else 2e-5, "bd_step U", precision, block)
             # device-generated noise: same (seed, step) on every rank = the single-context step
             U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, seed=1234, step=7, tol=gt, restart=40,
                                      max_iter=120, lanczos_tol=lt, lanczos_max_iter=80)
@@ -94,11 +95,11 @@ def main():
                                        lanczos_tol=lt, lanczos_max_iter=80)
             parts = [None] * world
             dist.all_gather_object(parts, U)
-            chk(rel(np.concatenate(parts), U1), 1e-10 if precision == "double" else 5e-5, "seeded bd_step U", precision, block)
+            chk(rel(np.concatenate(parts), U1), 1e-12 if precision == "double" else 2e-5, "seeded bd_step U", precision, block)
             Xp, Qp = part.get_config()
             X1, Q1 = one.get_config()
-            chk(rel(Xp, X1[part.b0:part.b1]), 1e-12 if precision == "double" else 1e-7, "X after the step", precision, block)
-            chk(rel(Qp, Q1[part.b0:part.b1]), 1e-12 if precision == "double" else 1e-6, "Q after the step", precision, block)
+            chk(rel(Xp, X1[part.b0:part.b1]), 1e-14 if precision == "double" else 2e-7, "X after the step", precision, block)
+            chk(rel(Qp, Q1[part.b0:part.b1]), 1e-14 if precision == "double" else 5e-7, "Q after the step", precision, block)
             part.close()
     # a blob below the wall on ONE rank must surface as the same error on EVERY rank
     Xb = s["X"].copy()
