@@ -20,6 +20,13 @@ librbl), seconds per step.
 `roofline`: the product kernel alone (events recorded around every launch inside the timed
             region) against the FMA-pipe peak measured live by a microbenchmark.  The bound
             is FP32 (FP64) CUDA-core issue, not HBM and not tensor cores.
+`parity`  : after the timed region, at EVERY GPU count, sampled output rows of this run (first / last blob,
+            both sides of every rank boundary, seeded random rows; --parity-rows, default 64) against the CPU
+            oracle on the inputs the GPU saw; raises above 1e-5 (float) / 1e-12 (double).  The oracle is the
+            checker here, outside every timed region.
+`bd_step` : one warm-up + three timed full BD steps (min / mean / max), then one untimed profiled step
+            (wall clock per phase, summed product-kernel time); at N = 1 the double step also with mixed
+            precision modes 1 and 2 (include/rbl.h rbl_set_mixed_precision).
 `cpu_baseline` / --impl reference: the reference's own dense 3N x 3N assembly + GEMV
             (rotne_prager_tensor / make_damp_mat / apply_M, c_rigid_obj.cpp:413-459,618-659, compiled
             from the reference source into oracle/_ref/libref_apply_M.so; the oracle's port where that

@@ -2,6 +2,7 @@
 // See rbl_rigid.cuh for the reference members each kernel replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 
 #include "rbl_pair.cuh"
 #include "rbl_rigid.cuh"
@@ -106,41 +107,70 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
 }
 
 // r_{b,k} = R(q_b) ref_k + X_b   (get_r_vecs / single_body_pos / multi_body_pos, c_rigid_obj.cpp:257-300).
-// One CTA per group of kPlaceBodies-at-most bodies, one thread per OUTPUT ELEMENT: a body's 3 n_blb reals
-// are contiguous in r, so the stores of a warp are 32 consecutive words (the thread-per-blob form wrote 12
-// partial sectors per store instruction, 3x the L1->L2 sector traffic, and spent ~95 instructions per blob
-// on a per-thread quaternion-to-rotation and an integer division by n_blb: 72 % issue-busy, 9 % of DRAM
-// throughput, profiles/r02_on_kernels_ncu.md).  The rotation matrices of the group are computed by the
-// first threads of the CTA into shared memory, all at once: one dependent-load latency per ~6000 outputs
-// (one CTA per body was launch/latency bound: 68 CTAs per SM, each waiting ~1.5 us for its quaternion).
-constexpr int kPlaceBodies = 64;
+//
+// Every thread produces FOUR CONSECUTIVE reals of the flat output (one 128-bit store in fp32, two in fp64):
+// they belong to two consecutive blobs (k0, c0..2) and (k1, ...), whose positions are computed in full
+// (18 FMA) and the four wanted components selected.  History, all measured at 6.42 M blobs
+// (profiles/r02_on_kernels.md): the thread-per-blob form spent ~95 instructions per blob (per-thread
+// quaternion->rotation, integer division) and wrote 12 partial sectors per store instruction -- 72 %
+// issue-busy, 9 % of DRAM throughput, 27 us; a thread per output element with the rotation in shared
+// memory coalesced the stores but needed 7 memory instructions per element (3 LDS + 3 LDG + 1 STG) and sat
+// exactly on the LSU issue floor (1.82 cycles per memory instruction and SM: 26.4 us predicted, 26.2
+// measured).  This form needs ~11 memory instructions per 4 elements.
 template <typename real>
+__device__ __forceinline__ void place_one(const real* __restrict__ X, const real* __restrict__ Q,
+                                          const real* __restrict__ ref, unsigned b, unsigned k, real (&p)[3]) {
+  real R[9];
+  quat_to_rot(Q + 4 * (size_t)b, R);
+  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
+  p[0] = fma(R[0], cx, fma(R[1], cy, fma(R[2], cz, X[3 * (size_t)b + 0])));
+  p[1] = fma(R[3], cx, fma(R[4], cy, fma(R[5], cz, X[3 * (size_t)b + 1])));
+  p[2] = fma(R[6], cx, fma(R[7], cy, fma(R[8], cz, X[3 * (size_t)b + 2])));
+}
+__device__ __forceinline__ void store4(float* o, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(double* o, double a, double b, double c, double d) {
+  reinterpret_cast<double2*>(o)[0] = make_double2(a, b);
+  reinterpret_cast<double2*>(o)[1] = make_double2(c, d);
+}
+template <typename real, bool ALIGNED>
 __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, int n_bod, int n_blb, int per_cta,
+                                   const real* __restrict__ ref, unsigned n_blb, unsigned n_out,
                                    real* __restrict__ r) {
-  __shared__ real RX[kPlaceBodies][12];  // rows of R, then X_b
-  const int b0 = blockIdx.x * per_cta;
-  const int nb = min(per_cta, n_bod - b0);
-  if ((int)threadIdx.x < nb) {
-    const int b = b0 + threadIdx.x;
+  // 32-bit index arithmetic on purpose (a 64-bit division is a ~100-instruction routine); 3N < 2^31 is
+  // checked by the launcher
+  const unsigned e0 = 4u * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (e0 >= n_out) return;
+  const unsigned g0 = e0 / 3u, c0 = e0 - 3u * g0;      // global blob of the first element, its component
+  const unsigned b0 = g0 / n_blb, k0 = g0 - b0 * n_blb;
+  const unsigned last = n_out / 3u - 1u;
+  const unsigned g1 = g0 < last ? g0 + 1u : last;        // the next blob (clamped at the end of the array)
+  unsigned b1 = b0, k1 = k0 + 1u;
+  if (k1 == n_blb) { b1 = b0 + 1u; k1 = 0u; }
+  if (g1 == g0) { b1 = b0; k1 = k0; }
+  real p0[3], p1[3];
+  place_one(X, Q, ref, b0, k0, p0);
+  if (b1 == b0) {  // same body (the common case): one rotation matrix for both blobs
     real R[9];
-    quat_to_rot(Q + 4 * (size_t)b, R);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) RX[threadIdx.x][i] = R[i];
-    RX[threadIdx.x][9] = X[3 * (size_t)b];
-    RX[threadIdx.x][10] = X[3 * (size_t)b + 1];
-    RX[threadIdx.x][11] = X[3 * (size_t)b + 2];
+    quat_to_rot(Q + 4 * (size_t)b0, R);
+    const real cx = ref[3 * k1], cy = ref[3 * k1 + 1], cz = ref[3 * k1 + 2];
+    p1[0] = fma(R[0], cx, fma(R[1], cy, fma(R[2], cz, X[3 * (size_t)b0 + 0])));
+    p1[1] = fma(R[3], cx, fma(R[4], cy, fma(R[5], cz, X[3 * (size_t)b0 + 1])));
+    p1[2] = fma(R[6], cx, fma(R[7], cy, fma(R[8], cz, X[3 * (size_t)b0 + 2])));
+  } else {
+    place_one(X, Q, ref, b1, k1, p1);
   }
-  __syncthreads();
-  const int n3 = 3 * n_blb;
-  for (int bl = 0; bl < nb; ++bl) {
-    real* __restrict__ out = r + (size_t)(b0 + bl) * n3;
-    const real* rx = RX[bl];
-    for (int e = threadIdx.x; e < n3; e += blockDim.x) {
-      const int k = e / 3, c = e - 3 * k;  // division by a literal: a multiply and a shift
-      const real* row = rx + 3 * c;
-      out[e] = fma(row[0], ref[3 * k], fma(row[1], ref[3 * k + 1], fma(row[2], ref[3 * k + 2], rx[9 + c])));
-    }
+  // the four consecutive components starting at (g0, c0)
+  const real o0 = c0 == 0 ? p0[0] : (c0 == 1 ? p0[1] : p0[2]);
+  const real o1 = c0 == 0 ? p0[1] : (c0 == 1 ? p0[2] : p1[0]);
+  const real o2 = c0 == 0 ? p0[2] : (c0 == 1 ? p1[0] : p1[1]);
+  const real o3 = c0 == 0 ? p1[0] : (c0 == 1 ? p1[1] : p1[2]);
+  if (ALIGNED && e0 + 4u <= n_out) {
+    store4(r + e0, o0, o1, o2, o3);
+  } else {  // tail of the array (3N is not a multiple of 4), or an output pointer that is not 16-byte aligned
+    const real o[4] = {o0, o1, o2, o3};
+    for (unsigned j = 0; e0 + j < n_out; ++j) r[e0 + j] = o[j];
   }
 }
 template <typename real>
@@ -149,14 +179,12 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
-  const int n3 = 3 * n_blb;
-  const int threads = n3 >= 256 ? 256 : std::max(64, ((n3 + 31) / 32) * 32);
-  int per_cta = std::max(1, std::min(kPlaceBodies, 6144 / n3));  // ~6000 outputs per CTA
-  per_cta = std::min(per_cta, threads);
-  // keep at least ~4 CTAs per SM in flight for small suspensions
-  while (per_cta > 1 && (n_bod + per_cta - 1) / per_cta < 592) per_cta = (per_cta + 1) / 2;
-  const int blocks = (n_bod + per_cta - 1) / per_cta;
-  place_blobs_kernel<real><<<blocks, threads, 0, s>>>(X, Q, ref, n_bod, n_blb, per_cta, r);
+  const unsigned n_out = (unsigned)(3 * n);
+  const unsigned threads = 256, groups = (n_out + 3u) / 4u;
+  if (reinterpret_cast<uintptr_t>(r) % 16 == 0)
+    place_blobs_kernel<real, true><<<(groups + threads - 1) / threads, threads, 0, s>>>(X, Q, ref, (unsigned)n_blb, n_out, r);
+  else
+    place_blobs_kernel<real, false><<<(groups + threads - 1) / threads, threads, 0, s>>>(X, Q, ref, (unsigned)n_blb, n_out, r);
   return cudaGetLastError();
 }
 
