@@ -1,5 +1,6 @@
-"""Prints the metric table of a kernel from an .ncu-rep (developer tool for profiles/*.md).
-usage: python tools/ncu_table.py <report.ncu-rep>"""
+"""Prints the metric table of a kernel from an .ncu-rep, or from its `--page raw --csv` export
+(developer tool for profiles/*.md).
+usage: python tools/ncu_table.py <report.ncu-rep | raw.csv>"""
 import csv
 import subprocess
 import sys
@@ -22,7 +23,10 @@ WANT = ["gpu__time_duration.sum", "gpc__cycles_elapsed.avg.per_second", "launch_
 
 
 def main():
-    txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if sys.argv[1].endswith(".csv"):
+        txt = open(sys.argv[1]).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader([l for l in txt.splitlines() if not l.startswith("==")]))
     hdr, units, vals = rows[0], rows[1], rows[2]
     print("## `%s`\n" % vals[hdr.index("Kernel Name")])
