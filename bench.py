@@ -8,11 +8,13 @@ Workload (BASELINE.json configs[1], the configuration the metric is quoted on): 
 of shell_N_162 above a wall = 162 000 blobs; one STEP = one application of the saddle
 operator [M lam - K U ; K^T lam], i.e. one wall-corrected RPY mobility product B M B lam over
 N^2 = 2.6244e10 ordered blob pairs plus the K / K^T products.  Metric: ordered blob-pair
-interactions per second (whole job).  Strong scaling: bodies are partitioned over the ranks,
-lambda is all-gathered over NCCL each step, the pair work is split in equal shares and the
-partial products are reduce-scattered.  `bd_step`: BASELINE.json's second metric, one full
-fluctuating rigid BD step on configs[2]'s suspension partitioned over the ranks (NCCL inside
-librbl), seconds per step.
+interactions per second (whole job).  Strong scaling: bodies are partitioned over the ranks
+(rbl_comm_init: the collective saddle operator of the library), lambda is gathered each step, the pair
+work is split in equal shares and the partial products are reduce-scattered -- both exchanges by the
+library's own kernels over NVLink peer memory (csrc/rbl_peer.cuh), self-checked against the NCCL
+collectives before anything is timed and replaced by them where peer memory is unavailable (`exchange`).
+`bd_step`: BASELINE.json's second metric, one full fluctuating rigid BD step on configs[2]'s suspension
+partitioned over the ranks, seconds per step.
 
 `value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
 `e2e`     : the same step through the host-buffer C ABI (rbl_apply_saddle at N=1; pinned
@@ -209,7 +211,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from rigid_body_light_b200._lib import Context
-    from rigid_body_light_b200.sharding import CudaShard, ShardedSaddle, body_ranges, comm_breakdown, slice_system
+    from rigid_body_light_b200.sharding import CudaShard, PartitionedRigidBody, ShardedSaddle, body_ranges, slice_system
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,20 +253,64 @@ def run_ours(args):
     for precision in (["single", "double"] if args.dtype == "both" else [args.dtype]):
         tdt = torch.float32 if precision == "single" else torch.float64
         ndt = np.float32 if precision == "single" else np.float64
-        ctx = Context(precision, device=local_rank)
-        ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
-        ctx.set_flags(0, int(wall))
-        ctx.set_config(s["X"][lo:hi], s["Q"][lo:hi])
-        shard = CudaShard(ctx, (hi - lo) * n_blb, tdt)
+        pb = None
+        exchange = None
+        if world == 1:
+            ctx = Context(precision, device=local_rank)
+            ctx.set_parameters(s["a"], 0.01, 1.0, 1.0, ref)
+            ctx.set_flags(0, int(wall))
+            ctx.set_config(s["X"][lo:hi], s["Q"][lo:hi])
+        else:
+            # the collective saddle operator of the library (rbl_comm_init): the exchanges around the product are
+            # its own peer-memory kernels where every rank could map every other rank's buffer, NCCL otherwise
+            pb = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=wall, block_PC=False,
+                                      precision=precision, rank=rank, world=world, dist=dist, device=local_rank)
+            ctx = pb.ctx
+        shard = CudaShard(ctx, (hi - lo) * n_blb, tdt)  # (puts the context on torch's current stream)
         op = ShardedSaddle(shard, nb, n_blb, rank, world, dist if world > 1 else None)
         x_local = torch.from_numpy(x_local_np.astype(ndt)).cuda()
         out_local = torch.empty_like(x_local)
         op.refresh_positions()
         peak = max(ctx.fma_peak(20000) for _ in range(3))  # TFLOP/s, live, this GPU, this precision
 
+        if world == 1:
+            apply_op = lambda: op.apply(x_local, out_local)  # noqa: E731
+        else:
+            apply_op = lambda: pb.apply_saddle_dev(x_local.data_ptr(), out_local.data_ptr())  # noqa: E731
+            exchange = {"mode": pb.exchange, "why_not_peer": pb.exchange_why or None}
+            if pb.exchange == "peer":
+                # self-check before anything is timed: the same operator through both protocols; a failure of the
+                # peer exchange (error code, or a result that differs beyond rounding) leaves NCCL in charge
+                ok = 1.0
+                try:
+                    apply_op()
+                    ctx.call("rbl_sync")
+                    a_peer = out_local.clone()
+                    pb.set_exchange("nccl")
+                    apply_op()
+                    ctx.call("rbl_sync")
+                    den = float(torch.linalg.vector_norm(out_local.double()))
+                    dev = float(torch.linalg.vector_norm(a_peer.double() - out_local.double())) / max(den, 1e-300)
+                    exchange["selfcheck_rel_diff_vs_nccl"] = dev
+                    if not dev < (2e-6 if precision == "single" else 1e-13):
+                        ok = 0.0
+                except Exception as exc:  # noqa: BLE001
+                    exchange["selfcheck_error"] = str(exc)[:200]
+                    ok = 0.0
+                t = torch.tensor([ok], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if float(t.item()) > 0.5:
+                    pb.set_exchange("peer")
+                else:
+                    try:
+                        pb.set_exchange("nccl")
+                    except Exception:  # noqa: BLE001
+                        pass
+                exchange["mode"] = pb.exchange
+
         def step():
             ctx.call("rbl_flush_l2")  # inputs (5 MB) are smaller than the 126 MB L2: flush between steps
-            op.apply(x_local, out_local)
+            apply_op()
 
         for _ in range(args.warmup):
             step()
@@ -276,16 +322,20 @@ def run_ours(args):
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        op.timing = [] if world > 1 else None
+        if world > 1:
+            ctx.call("rbl_comm_profile", None, None, 1)  # clear
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
-        comm = comm_breakdown(op.timing) if world > 1 else None
-        op.timing = None
-        if comm is not None:
-            comm = [max_over_ranks(c) for c in comm]
+        comm = None
+        if world > 1:
+            import ctypes
+
+            ms3, cn = (ctypes.c_double * 3)(), ctypes.c_int()
+            ctx.call("rbl_comm_profile", ms3, ctypes.byref(cn), 1)
+            comm = [max_over_ranks(float(v)) for v in ms3]
         clocks = sampler.stop() if rank == 0 else None
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = ctx.launch_count() - launches0
@@ -319,13 +369,13 @@ def run_ours(args):
             hx = torch.from_numpy(x_local_np.astype(ndt)).pin_memory()
             ho = torch.empty_like(hx).pin_memory()
             for _ in range(args.e2e_warmup):
-                x_local.copy_(hx, non_blocking=True); op.apply(x_local, out_local); ho.copy_(out_local, non_blocking=True)
+                x_local.copy_(hx, non_blocking=True); apply_op(); ho.copy_(out_local, non_blocking=True)
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 ctx.call("rbl_flush_l2")
                 x_local.copy_(hx, non_blocking=True)
-                op.apply(x_local, out_local)
+                apply_op()
                 ho.copy_(out_local, non_blocking=True)
                 torch.cuda.synchronize()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
@@ -340,6 +390,8 @@ def run_ours(args):
                                  f"max |diff| {dd.max():.3e} at {int(dd.argmax())}")
         ctx.call("rbl_sync")
         parity = None
+        if world > 1:  # the all-gathered lambda the parity check reads (the library keeps its own copy inside)
+            op._allgather(x_local[: 3 * op.n_local], op.lam_all)
         if args.parity_rows > 0:
             parity = oracle_parity(precision, op, s, x_local_np, dev_out, ranges, rank, world, args.parity_rows,
                                    dist if world > 1 else None, torch)
@@ -372,11 +424,22 @@ def run_ours(args):
             "comm_ms_per_step": None if comm is None else {"allgather_lambda": comm[0], "product_incl_pack": comm[1],
                                                             "reduce_partials": comm[2],
                                                             "note": "CUDA events per step, max over ranks; a rank that "
-                                                                    "finishes its share early waits inside the collective"},
+                                                                    "finishes its share early waits inside the exchange"},
+            "exchange": exchange,
         }
-        ctx.close()
+        if pb is not None:
+            barrier()
+            pb.close()  # collective: the peer buffers are unmapped in step
+        else:
+            ctx.close()
         del op, shard, x_local, out_local
 
+    if world > 1 and any("selfcheck_error" in (r["exchange"] or {}) or
+                         ((r["exchange"] or {}).get("selfcheck_rel_diff_vs_nccl") is not None and (r["exchange"] or {}).get("mode") != "peer")
+                         for r in results.values()):
+        # the peer-memory exchange failed its self-check on this box (every rank saw the same verdict): the
+        # BD leg's contexts use the NCCL collectives too
+        os.environ["RBL_PEER_EXCHANGE"] = "0"
     bd = None
     if args.bd_steps > 0:
         bd = bd_step_leg(args, rank, world, dist if world > 1 else None, local_rank,
@@ -397,17 +460,18 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {nb} spheres of shell_N_{n_blb} "
                                    f"{'above a wall' if wall else 'in free space'} = {n_all} blobs; step = apply_saddle "
                                    f"(wall-corrected RPY matvec + K + K^T)",
-                       "pairs_per_step": pairs, "parallelism": f"x{world}: bodies in contiguous ranges; NCCL all-gather of lambda, equal shares of the "
-                                      f"unordered-pair tile triangle per rank, reduce-scatter of the partial products",
+                       "pairs_per_step": pairs, "parallelism": f"x{world}: bodies in contiguous ranges; lambda gathered and the partial products reduce-scattered "
+                                      f"by the library's own kernels over NVLink peer memory (NCCL collectives where "
+                                      f"that is unavailable: see `exchange`), equal shares of the unordered-pair tile triangle per rank",
                        "l2": "256 MiB memset between steps inside the timed region (inputs < L2)",
                        "seeds": {"geometry": 0, "quaternions": 1, "vectors": 2}},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "clocks": head["clocks"], "cpu_baseline": cpu, "comm_ms_per_step": head["comm_ms_per_step"],
-            "parity": head["parity"], "bd_step": bd,
+            "exchange": head["exchange"], "parity": head["parity"], "bd_step": bd,
         }
         if "double" in results and head_p == "single":
             d = results["double"]
-            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step", "parity")}
+            line["f64"] = {k: d[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks", "comm_ms_per_step", "exchange", "parity")}
         print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
@@ -434,7 +498,7 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
     out = {"workload": f"{args.bd_workload}: {nb} spheres of shell_N_{n_blb} {'above a wall' if wall else 'in free space'} "
                        f"= {nb * n_blb} blobs; kBT = 0.0041, dt = 0.01, gravity on every body, block-diagonal PC, block-Cholesky preconditioned paired Lanczos noise",
            "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps,
-           "warmup_steps": 1 if args.bd_warmup else 0}
+           "warmup_steps": 1 if args.bd_warmup else 0, "exchange": None}
     legs = [(p, 0) for p in precisions]
     if "double" in precisions and world == 1 and args.bd_mixed:
         legs += [("double", 1), ("double", 2)]  # mixed precision: single-GPU double contexts
@@ -444,6 +508,8 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
                                   precision=precision, rank=rank, world=world, dist=dist, device=local_rank)
         if mixed:
             pb.set_mixed_precision(mixed)
+        if world > 1:
+            out["exchange"] = pb.exchange
         rng = np.random.default_rng(3)
         times, iters, lz, rel = [], [], [], []
         prod0 = 0

@@ -251,11 +251,32 @@ int rbl_sync(rbl_ctx* ctx);
  * batched and all-reduced; status codes are max-reduced so every rank returns the same one.
  * K, K^T, the preconditioner and the integrator are rank-local (whole bodies per rank).
  * rbl_apply_M / rbl_dev_apply_M stay local, non-collective pure functions of their arguments.
- * NCCL is bound with dlopen("libnccl.so.2") at rbl_comm_init time; a single-GPU host never needs it. */
+ * NCCL is bound with dlopen("libnccl.so.2") at rbl_comm_init time; a single-GPU host never needs it.
+ *
+ * The two exchanges around every product.  rbl_comm_init also tries to set up a PEER-MEMORY exchange
+ * (csrc/rbl_peer.cuh): every rank exports one device buffer through CUDA IPC and maps every other
+ * rank's; the all-gather of the forces becomes NVLink stores into the peers' buffers plus an epoch
+ * hand-shake, the reduce-scatter becomes a hand-shake plus a kernel that sums this rank's rows of the
+ * world's partial products in RANK ORDER straight from the peers' memory (so, unlike ncclReduceScatter,
+ * the order of that sum is fixed).  It is on only if EVERY rank could set it up (one process per GPU on
+ * one node, peer access between the devices); otherwise, or after rbl_comm_set_exchange(ctx, 0), or with
+ * RBL_PEER_EXCHANGE=0 in the environment, the NCCL collectives above are used.  Waits inside the
+ * hand-shakes are bounded (RBL_PEER_TIMEOUT_S, default 30 s): a rank that never arrives turns into
+ * RBL_ERR_CUDA at the next synchronisation instead of a hung GPU.  Positions (once per configuration),
+ * dot products and status codes stay on NCCL. */
 /* rank 0: 128 bytes of ncclUniqueId for the host to broadcast (any transport) */
 int rbl_comm_unique_id(void* out128);
 /* blobs_per_rank: `world` entries (blobs, not bodies); entry `rank` must equal this context's N */
 int rbl_comm_init(rbl_ctx* ctx, const void* uid128, int rank, int world, const int* blobs_per_rank);
+/* 1: peer-memory exchange in use, 0: NCCL collectives; _why: what kept the peer exchange off ("" if on) */
+int rbl_comm_exchange(const rbl_ctx* ctx);
+const char* rbl_comm_exchange_why(const rbl_ctx* ctx);
+/* collective (every rank, same mode): 0 = NCCL collectives, 1 = peer memory (RBL_ERR_STATE if unavailable) */
+int rbl_comm_set_exchange(rbl_ctx* ctx, int mode);
+/* while rbl_profile_matvec is on, CUDA events bracket the phases of every partitioned product: ms3 = average
+ * milliseconds of {gather of the forces, pack + product + scale, reduce of the partial products}, n = products
+ * seen; reset != 0 clears */
+int rbl_comm_profile(rbl_ctx* ctx, double* ms3, int* n, int reset);
 int rbl_comm_world(const rbl_ctx* ctx); /* 1 without a communicator */
 int rbl_comm_rank(const rbl_ctx* ctx);
 /* the context's cudaStream_t (as void*); set_stream lets a host share its own stream */

@@ -74,6 +74,10 @@ SYMBOLS = {
     "rbl_sync": (_i, [_vp]),
     "rbl_comm_unique_id": (_i, [_vp]),
     "rbl_comm_init": (_i, [_vp, _vp, _i, _i, _pi]),
+    "rbl_comm_exchange": (_i, [_vp]),
+    "rbl_comm_exchange_why": (ctypes.c_char_p, [_vp]),
+    "rbl_comm_set_exchange": (_i, [_vp, _i]),
+    "rbl_comm_profile": (_i, [_vp, _pd, _pi, _i]),
     "rbl_comm_world": (_i, [_vp]),
     "rbl_comm_rank": (_i, [_vp]),
     "rbl_stream": (_vp, [_vp]),

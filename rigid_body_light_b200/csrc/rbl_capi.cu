@@ -5,6 +5,7 @@
 // X_n/Q_n, the K data (here: cached blob positions) and the lazily built preconditioner
 // -- but resident in HBM.  Host-pointer entry points stage through device buffers and
 // call the same device path the rbl_dev_* entry points expose.
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -110,6 +111,9 @@ struct rbl_ctx {
   virtual int dev_apply_M_part(const void* F, const void* r, int n, int part, int n_parts, void* out) = 0;
   virtual int saddle_finish(const void* Mlam, const void* lam, const void* U, void* out) = 0;
   virtual int comm_init(const void* uid128, int rank, int world, const int* blobs_per_rank) = 0;
+  virtual int comm_exchange(const char** why) const = 0;
+  virtual int comm_set_exchange(int mode) = 0;
+  virtual int comm_profile(double* ms3, int* n, int reset) = 0;
   virtual int dev_apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
   virtual int apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) = 0;
   virtual int lanczos2(const void* W1, const void* W2, void* out1, void* out2, double tol, int max_iter, int* iters2) = 0;
@@ -260,9 +264,12 @@ struct Ctx final : rbl_ctx {
   DevBuf d_c32a, d_c32b, d_c32c, d_c32d, d_mr, d_me;
   int mixed_outer = 0;           // refinement cycles of the last mixed solve
 
-  enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, FLAG_NOISE = 3, N_FLAGS = 4 };
+  enum { FLAG_BELOW = 0, FLAG_SINGULAR = 1, FLAG_NOT_SPD = 2, FLAG_NOISE = 3, FLAG_PEER = 4, N_FLAGS = 5 };
 
   ~Ctx() override {
+    if (comm) comm->peer_release(true, d_status.as<int>(), stream);
+    for (auto& ev : prof_comm)
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
     delete shadow;
     for (auto& pr : prof_events) {
       cudaEventDestroy(pr.first);
@@ -297,11 +304,14 @@ struct Ctx final : rbl_ctx {
 
   // waits for the stream and turns device flags into status codes
   int sync() override {
-    int flags[N_FLAGS] = {0, 0, 0, 0};
+    int flags[N_FLAGS] = {0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (flags[0] || flags[1] || flags[2]) {
+    if (flags[0] || flags[1] || flags[2] || flags[FLAG_PEER]) {
       CK(cudaMemsetAsync(d_flags.p, 0, sizeof(flags), stream));
+      if (flags[FLAG_PEER])
+        return fail(RBL_ERR_CUDA, "peer-memory exchange: a rank of the partitioned suspension did not arrive within the time limit "
+                                  "(RBL_PEER_TIMEOUT_S); results of this call are invalid");
       if (flags[FLAG_BELOW])
         return fail(RBL_ERR_BELOW_WALL,
                     "A blob has its center below the wall (z<0). Cannot compute mobility- check "
@@ -600,6 +610,7 @@ struct Ctx final : rbl_ctx {
     long long tot = 0;
     for (int r = 0; r < world; ++r) tot += blobs_per_rank[r];
     if (tot > 0x7fffffffLL) return fail(RBL_ERR_INVALID, "rbl_comm_init: more than 2^31-1 blobs");
+    if (comm) comm->peer_release(true, d_status.as<int>(), stream);
     delete comm;
     comm = nullptr;
     CK(cudaStreamSynchronize(stream));
@@ -612,6 +623,54 @@ struct Ctx final : rbl_ctx {
     comm = c;
     r_all_valid = false;
     CK(d_status.ensure(4 * sizeof(int)));
+    // the exchanges around every product go over peer memory when every rank can map every other rank's
+    // buffer (rbl_peer.cuh); otherwise NCCL collectives (rbl_comm_exchange tells which, and why)
+    comm->peer_setup(sizeof(real), d_status.as<int>(), stream);
+    return RBL_OK;
+  }
+  int comm_exchange(const char** why) const override {
+    if (why) *why = comm ? comm->peer_why.c_str() : "no communicator";
+    return comm && comm->peer_active() ? 1 : 0;
+  }
+  int comm_set_exchange(int mode) override {
+    if (!comm) return fail(RBL_ERR_STATE, "rbl_comm_set_exchange: no communicator");
+    if (mode != 0 && mode != 1) return fail(RBL_ERR_INVALID, "rbl_comm_set_exchange: mode must be 0 (NCCL) or 1 (peer memory)");
+    if (mode == 1 && !comm->peer.on) return fail(RBL_ERR_STATE, "rbl_comm_set_exchange: the peer-memory exchange is not available: " + comm->peer_why);
+    RET(csync());  // a quiescent point on every rank: the two protocols never interleave
+    comm->peer.use = mode == 1;
+    return RBL_OK;
+  }
+  // events around the two exchanges of every product while profiling is on: [before gather, after gather,
+  // before reduce, after reduce]
+  std::vector<std::array<cudaEvent_t, 4>> prof_comm;
+  int comm_mark(int k) {
+    if (!profile || !comm) return RBL_OK;
+    if (k == 0) {
+      std::array<cudaEvent_t, 4> ev{};
+      for (auto& e : ev) CK(cudaEventCreate(&e));
+      prof_comm.push_back(ev);
+    }
+    CK(cudaEventRecord(prof_comm.back()[k], stream));
+    return RBL_OK;
+  }
+  int comm_profile(double* ms3, int* n, int reset) override {
+    CK(cudaStreamSynchronize(stream));
+    double acc[3] = {0, 0, 0};
+    for (auto& ev : prof_comm)
+      for (int k = 0; k < 3; ++k) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+        acc[k] += t;
+      }
+    const int m = (int)prof_comm.size();
+    if (ms3)
+      for (int k = 0; k < 3; ++k) ms3[k] = m ? acc[k] / m : 0;
+    if (n) *n = m;
+    if (reset) {
+      for (auto& ev : prof_comm)
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+      prof_comm.clear();
+    }
     return RBL_OK;
   }
 #define NK(call)                                                        \
@@ -646,8 +705,10 @@ struct Ctx final : rbl_ctx {
     const void* before = d_r_all.p;
     CK(d_r_all.ensure(2 * n3 * sizeof(real)));
     if (d_r_all.p != before) r_all_valid = false;
-    CK(d_lam_all.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
-    CK(d_mbuf.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
+    if (!comm->peer_active()) {  // (the peer exchange keeps both inside its symmetric buffer)
+      CK(d_lam_all.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
+      CK(d_mbuf.ensure((two_rhs ? 2 : 1) * n3 * sizeof(real)));
+    }
     CK(d_rec.ensure(n_pad * rbl::kRecReals * sizeof(real)));
     CK(d_raw.ensure(3 * n_pad * sizeof(real)));
     size_t tgt_tiles = (size_t)plan.n_tgt_tiles;
@@ -676,11 +737,16 @@ struct Ctx final : rbl_ctx {
       return dev_apply_M(F_local, r_local, nl, 0, nl, out_local);
     }
     const size_t n3_all = 3 * (size_t)comm->n_all;
+    const bool peer = comm->peer_active();
     const void* before = d_r_all.p;
     CK(d_r_all.ensure(2 * n3_all * sizeof(real)));  // [configuration ; scratch positions (RFD)]
     if (d_r_all.p != before) r_all_valid = false;
-    CK(d_lam_all.ensure(n3_all * sizeof(real)));
-    CK(d_mbuf.ensure(n3_all * sizeof(real)));
+    if (!peer) {
+      CK(d_lam_all.ensure(n3_all * sizeof(real)));
+      CK(d_mbuf.ensure(n3_all * sizeof(real)));
+    }
+    real* lam = peer ? comm->peer_lam<real>() : d_lam_all.as<real>();
+    real* mb = peer ? comm->peer_mbuf<real>() : d_mbuf.as<real>();
     real* r_all = d_r_all.as<real>();
     if (r_is_config) {
       if (!r_all_valid) {
@@ -692,10 +758,24 @@ struct Ctx final : rbl_ctx {
       r_all += n3_all;
       NK(comm->allgatherv<real>(r_local, r_all, 3, stream));
     }
-    NK(comm->allgatherv<real>(F_local, d_lam_all.as<real>(), 3, stream));
-    RET(apply_M_part_gen(d_lam_all.p, r_all, (int)comm->n_all, comm->rank, comm->world, d_mbuf.p,
-                         r_is_config ? r_all_gen : 0));
-    NK(comm->reduce_scatterv<real>(d_mbuf.as<real>(), out_local, 3, stream));
+    int* pf = d_flags.as<int>() + FLAG_PEER;
+    RET(comm_mark(0));
+    if (peer) {
+      NK(comm->peer_allgather<real>(&F_local, 1, pf, stream));
+      launches += 2;
+    } else {
+      NK(comm->allgatherv<real>(F_local, lam, 3, stream));
+    }
+    RET(comm_mark(1));
+    RET(apply_M_part_gen(lam, r_all, (int)comm->n_all, comm->rank, comm->world, mb, r_is_config ? r_all_gen : 0));
+    RET(comm_mark(2));
+    if (peer) {
+      NK(comm->peer_reduce_scatter<real>(&out_local, 1, pf, stream));
+      launches += 2;
+    } else {
+      NK(comm->reduce_scatterv<real>(mb, out_local, 3, stream));
+    }
+    RET(comm_mark(3));
     return RBL_OK;
   }
   // d_dots[slot .. slot+m) = <V_i, w> summed over the ranks (results stay on the device; the Krylov
@@ -756,24 +836,45 @@ struct Ctx final : rbl_ctx {
     const int nl = (int)N();
     if (!comm) return dev_apply_M2_part(F1_local, F2_local, d_r.p, nl, 0, 1, out1_local, out2_local, cfg_gen);
     const size_t n3_all = 3 * (size_t)comm->n_all;
+    const bool peer = comm->peer_active();
     const void* before = d_r_all.p;
     CK(d_r_all.ensure(2 * n3_all * sizeof(real)));
     if (d_r_all.p != before) r_all_valid = false;
-    CK(d_lam_all.ensure(2 * n3_all * sizeof(real)));
-    CK(d_mbuf.ensure(2 * n3_all * sizeof(real)));
+    if (!peer) {
+      CK(d_lam_all.ensure(2 * n3_all * sizeof(real)));
+      CK(d_mbuf.ensure(2 * n3_all * sizeof(real)));
+    }
     if (!r_all_valid) {
       NK(comm->allgatherv<real>(d_r.as<real>(), d_r_all.as<real>(), 3, stream));
       r_all_valid = true;
       r_all_gen = ++gen_counter;
     }
-    real* lam = d_lam_all.as<real>();
-    real* mb = d_mbuf.as<real>();
-    NK(comm->allgatherv<real>(F1_local, lam, 3, stream));
-    NK(comm->allgatherv<real>(F2_local, lam + n3_all, 3, stream));
-    RET(dev_apply_M2_part(lam, lam + n3_all, d_r_all.p, (int)comm->n_all, comm->rank, comm->world, mb, mb + n3_all,
-                          r_all_gen));
-    NK(comm->reduce_scatterv<real>(mb, out1_local, 3, stream));
-    NK(comm->reduce_scatterv<real>(mb + n3_all, out2_local, 3, stream));
+    real* lam1 = peer ? comm->peer_lam<real>(0) : d_lam_all.as<real>();
+    real* lam2 = peer ? comm->peer_lam<real>(1) : lam1 + n3_all;
+    real* mb1 = peer ? comm->peer_mbuf<real>(0) : d_mbuf.as<real>();
+    real* mb2 = peer ? comm->peer_mbuf<real>(1) : mb1 + n3_all;
+    int* pf = d_flags.as<int>() + FLAG_PEER;
+    RET(comm_mark(0));
+    if (peer) {
+      const real* send[2] = {F1_local, F2_local};
+      NK(comm->peer_allgather<real>(send, 2, pf, stream));
+      launches += 3;
+    } else {
+      NK(comm->allgatherv<real>(F1_local, lam1, 3, stream));
+      NK(comm->allgatherv<real>(F2_local, lam2, 3, stream));
+    }
+    RET(comm_mark(1));
+    RET(dev_apply_M2_part(lam1, lam2, d_r_all.p, (int)comm->n_all, comm->rank, comm->world, mb1, mb2, r_all_gen));
+    RET(comm_mark(2));
+    if (peer) {
+      real* recv[2] = {out1_local, out2_local};
+      NK(comm->peer_reduce_scatter<real>(recv, 2, pf, stream));
+      launches += 3;
+    } else {
+      NK(comm->reduce_scatterv<real>(mb1, out1_local, 3, stream));
+      NK(comm->reduce_scatterv<real>(mb2, out2_local, 3, stream));
+    }
+    RET(comm_mark(3));
     return RBL_OK;
   }
   int dev_apply_M2(const void* F1, const void* F2, const void* r, int n, void* out1, void* out2) override {
@@ -2335,6 +2436,17 @@ int rbl_comm_unique_id(void* out128) {
 int rbl_comm_init(rbl_ctx* ctx, const void* uid128, int rank, int world, const int* blobs_per_rank) {
   CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
   return ctx->comm_init(uid128, rank, world, blobs_per_rank);
+}
+int rbl_comm_exchange(const rbl_ctx* ctx) { return ctx ? ctx->comm_exchange(nullptr) : 0; }
+const char* rbl_comm_exchange_why(const rbl_ctx* ctx) {
+  const char* why = "";
+  if (ctx) ctx->comm_exchange(&why);
+  return why;
+}
+int rbl_comm_set_exchange(rbl_ctx* ctx, int mode) { CTX_OR_FAIL(ctx); BIND_DEVICE(ctx); return ctx->comm_set_exchange(mode); }
+int rbl_comm_profile(rbl_ctx* ctx, double* ms3, int* n, int reset) {
+  CTX_OR_FAIL(ctx); BIND_DEVICE(ctx);
+  return ctx->comm_profile(ms3, n, reset);
 }
 int rbl_comm_world(const rbl_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->world : 1; }
 int rbl_comm_rank(const rbl_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }

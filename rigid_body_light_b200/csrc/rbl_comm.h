@@ -14,11 +14,30 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "rbl_peer.cuh"
+
 namespace rbl {
+
+// One rank's view of the peer-memory exchange (rbl_peer.cuh): its own symmetric buffer, the other
+// ranks' buffers as mapped through CUDA IPC, and the epochs of the two hand-shakes.
+struct PeerExchange {
+  PeerTable tab{};
+  void* own = nullptr;
+  size_t bytes = 0;
+  size_t region = 0;    // bytes of ONE right-hand side: 3 n_all reals, rounded up to 256
+  size_t lam_off = 0;   // lambda of all blobs, two right-hand sides
+  size_t mbuf_off = 0;  // partial products, two right-hand sides
+  unsigned long long epoch[2] = {0, 0};
+  unsigned long long timeout_ns = 30ull * 1000000000ull;
+  bool mapped[kMaxPeers] = {};
+  bool on = false;      // set up on every rank
+  bool use = false;     // selected (rbl_comm_set_exchange)
+};
 
 struct Comm {
   void* lib = nullptr;
@@ -29,6 +48,8 @@ struct Comm {
   long long n_all = 0;
   bool even = true;
   std::string err;
+  PeerExchange peer;
+  std::string peer_why;  // why the peer exchange is off (empty when it is on)
 
   // entry points
   ncclResult_t (*pCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
@@ -45,6 +66,162 @@ struct Comm {
   ~Comm() {
     if (comm && pCommDestroy) pCommDestroy(comm);
     // the library handle is left open on purpose: torch may share it
+  }
+
+  // ---- peer-memory exchange ------------------------------------------------------------------
+  // max over the ranks of v (a host integer), through the device word d_int; < 0 on an NCCL / CUDA error
+  int agree_max(int v, int* d_int, cudaStream_t s) {
+    if (cudaMemcpyAsync(d_int, &v, sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    if (!allreduce_max_int(d_int, 1, s)) return -1;
+    int h = 0;
+    if (cudaMemcpyAsync(&h, d_int, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    return h;
+  }
+
+  // Collective.  Allocates this rank's symmetric buffer, hands its CUDA IPC handle to every other rank
+  // (one ncclAllGather of 64 bytes per rank) and maps theirs.  Every rank ends with the same answer:
+  // the exchange is on everywhere or nowhere (then peer_why says what failed HERE, or that another rank
+  // failed), and the NCCL collectives stay in charge.  `d_int`: a device word for the agreements.
+  bool peer_setup(size_t real_size, int* d_int, cudaStream_t s) {
+    peer = PeerExchange();
+    peer_why.clear();
+    const char* env = getenv("RBL_PEER_EXCHANGE");
+    bool ok_local = !(env && env[0] == '0');
+    if (!ok_local) peer_why = "disabled by RBL_PEER_EXCHANGE=0";
+    if (ok_local && world > kMaxPeers) {
+      ok_local = false;
+      peer_why = "more ranks than the peer table holds";
+    }
+    if (const char* t = getenv("RBL_PEER_TIMEOUT_S")) {
+      const double sec = atof(t);
+      if (sec > 0) peer.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
+    peer.region = ((3 * (size_t)n_all * real_size + 255) / 256) * 256;
+    peer.lam_off = kPeerFlagBytes;
+    peer.mbuf_off = peer.lam_off + 2 * peer.region;
+    peer.bytes = peer.mbuf_off + 2 * peer.region;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok_local) {
+      cudaError_t e = cudaMalloc(&peer.own, peer.bytes);
+      if (e == cudaSuccess) e = cudaMemsetAsync(peer.own, 0, kPeerFlagBytes, s);
+      if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine, peer.own);
+      if (e != cudaSuccess) {
+        ok_local = false;
+        peer_why = std::string("symmetric buffer: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+      }
+    }
+    // handles of all ranks (always executed, so the collective sequence never depends on a local failure)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    char* d_h = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(world);
+    bool xch = cudaMalloc(&d_h, 64 * (size_t)world) == cudaSuccess;
+    if (xch) xch = cudaMemcpyAsync(d_h + 64 * (size_t)rank, &mine, 64, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    if (xch) xch = ok(pAllGather(d_h + 64 * (size_t)rank, d_h, 64, ncclChar, comm, s), "ncclAllGather(ipc handles)");
+    if (xch) xch = cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)world, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+    if (xch) xch = cudaStreamSynchronize(s) == cudaSuccess;
+    if (d_h) cudaFree(d_h);
+    if (!xch && ok_local) {
+      ok_local = false;
+      peer_why = "exchange of the IPC handles failed";
+      cudaGetLastError();
+    }
+    int bad = agree_max(ok_local ? 0 : 1, d_int, s);
+    if (bad == 0) {
+      for (int r = 0; r < world && ok_local; ++r) {
+        if (r == rank) {
+          peer.tab.base[r] = peer.own;
+          continue;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          ok_local = false;
+          peer_why = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+          cudaGetLastError();
+          break;
+        }
+        peer.tab.base[r] = p;
+        peer.mapped[r] = true;
+      }
+      bad = agree_max(ok_local ? 0 : 1, d_int, s);  // also the barrier that orders every rank's zeroed epochs before the first push
+    }
+    if (bad != 0) {
+      if (peer_why.empty()) peer_why = bad < 0 ? "agreement between the ranks failed" : "another rank could not set it up";
+      // (the imports are closed, then an NCCL barrier, before any rank frees what another may still map)
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (peer.mapped[r]) {
+          cudaIpcCloseMemHandle(peer.tab.base[r]);
+          peer.mapped[r] = false;
+        }
+      if (bad > 0) agree_max(0, d_int, s);
+      peer_release(false, d_int, s);
+      return false;
+    }
+    peer.on = peer.use = true;
+    return true;
+  }
+
+  // `collective`: the context is being closed in step with the other ranks.  Nobody may free a buffer that
+  // another rank still reads or maps: (1) this rank's stream is drained, (2) a bounded hand-shake over
+  // the epochs themselves tells that every rank's is, (3) the imports are closed, (4) an NCCL barrier
+  // (only if the hand-shake succeeded: the peers are alive and on their way to it), then the buffer is
+  // freed.  A peer that never arrives costs the timeout and leaves the buffer to process exit.
+  void peer_release(bool collective, int* d_int, cudaStream_t s) {
+    bool free_own = true;
+    if (collective && comm && peer.on) {
+      int flag = 0;
+      const unsigned long long budget = peer.timeout_ns < 10000000000ull ? peer.timeout_ns : 10000000000ull;
+      free_own = cudaStreamSynchronize(s) == cudaSuccess &&
+                 cudaMemcpyAsync(d_int, &flag, sizeof(int), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+                 peer_signal_wait(peer.tab, world, rank, kPeerClosing, 1, budget, d_int, s) == cudaSuccess &&
+                 cudaMemcpyAsync(&flag, d_int, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                 cudaStreamSynchronize(s) == cudaSuccess && flag == 0;
+    }
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (peer.mapped[r]) {
+        cudaIpcCloseMemHandle(peer.tab.base[r]);
+        peer.mapped[r] = false;
+      }
+    if (collective && comm && peer.on && free_own) free_own = agree_max(0, d_int, s) == 0;
+    if (peer.own && free_own) cudaFree(peer.own);
+    cudaGetLastError();
+    peer.own = nullptr;
+    peer.on = peer.use = false;
+  }
+  bool peer_active() const { return peer.on && peer.use; }
+  template <typename real>
+  real* peer_lam(int k = 0) const { return reinterpret_cast<real*>(static_cast<char*>(peer.own) + peer.lam_off + k * peer.region); }
+  template <typename real>
+  real* peer_mbuf(int k = 0) const { return reinterpret_cast<real*>(static_cast<char*>(peer.own) + peer.mbuf_off + k * peer.region); }
+
+  // every rank's lam_all[k] <- concatenation of the ranks' slices (n_rhs slices pushed, ONE hand-shake)
+  template <typename real>
+  bool peer_allgather(const real* const* send_local, int n_rhs, int* err_flag, cudaStream_t s) {
+    for (int k = 0; k < n_rhs; ++k) {
+      const size_t off = peer.lam_off + k * peer.region + 3 * (size_t)first[rank] * sizeof(real);
+      if (peer_push<real>(peer.tab, world, off, send_local[k], 3 * (size_t)count[rank], s) != cudaSuccess) return cuda_err("peer_push");
+    }
+    if (peer_signal_wait(peer.tab, world, rank, kPeerLambdaReady, ++peer.epoch[kPeerLambdaReady], peer.timeout_ns, err_flag, s) != cudaSuccess)
+      return cuda_err("peer_signal_wait");
+    return true;
+  }
+  // recv_local[k] <- this rank's rows of the sum over the ranks of their partial products k
+  template <typename real>
+  bool peer_reduce_scatter(real* const* recv_local, int n_rhs, int* err_flag, cudaStream_t s) {
+    if (peer_signal_wait(peer.tab, world, rank, kPeerPartialReady, ++peer.epoch[kPeerPartialReady], peer.timeout_ns, err_flag, s) != cudaSuccess)
+      return cuda_err("peer_signal_wait");
+    for (int k = 0; k < n_rhs; ++k) {
+      const size_t off = peer.mbuf_off + k * peer.region + 3 * (size_t)first[rank] * sizeof(real);
+      if (peer_reduce<real>(peer.tab, world, off, 3 * (size_t)count[rank], recv_local[k], s) != cudaSuccess) return cuda_err("peer_reduce");
+    }
+    return true;
+  }
+  bool cuda_err(const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+    return false;
   }
 
   static void* open_lib(std::string* why) {

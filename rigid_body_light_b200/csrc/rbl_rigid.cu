@@ -108,15 +108,25 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
 
 // r_{b,k} = R(q_b) ref_k + X_b   (get_r_vecs / single_body_pos / multi_body_pos, c_rigid_obj.cpp:257-300).
 //
-// Every thread produces FOUR CONSECUTIVE reals of the flat output (one 128-bit store in fp32, two in fp64):
-// they belong to two consecutive blobs (k0, c0..2) and (k1, ...), whose positions are computed in full
-// (18 FMA) and the four wanted components selected.  History, all measured at 6.42 M blobs
-// (profiles/r02_on_kernels.md): the thread-per-blob form spent ~95 instructions per blob (per-thread
-// quaternion->rotation, integer division) and wrote 12 partial sectors per store instruction -- 72 %
-// issue-busy, 9 % of DRAM throughput, 27 us; a thread per output element with the rotation in shared
-// memory coalesced the stores but needed 7 memory instructions per element (3 LDS + 3 LDG + 1 STG) and sat
-// exactly on the LSU issue floor (1.82 cycles per memory instruction and SM: 26.4 us predicted, 26.2
-// measured).  This form needs ~11 memory instructions per 4 elements.
+// Two forms, chosen by the launcher (RBL_PLACE_VARIANT=0/1 overrides, for A/B measurements).
+//
+// (1, default) place_blobs_rows_kernel: a CTA owns G consecutive bodies and a 256-wide window of the
+// 3 n_blb reals of a body.  The first G threads turn the G quaternions into rotation rows [R_c0 R_c1 R_c2 X_c]
+// in shared memory (one 16/32-byte row per output component); every thread then owns ONE element (k, c) of
+// the window -- its reference point ref_k sits in three registers -- and walks over the G bodies: one
+// broadcast LDS.128 (three distinct rows per warp), three FMA, one coalesced STG per element.  Two memory
+// instructions per element against seven for a thread per element that re-reads ref and R per body.
+//
+// (0) place_blobs_kernel: every thread produces FOUR CONSECUTIVE reals of the flat output (one 128-bit
+// store in fp32, two in fp64): they belong to two consecutive blobs (k0, c0..2) and (k1, ...), whose
+// positions are computed in full (18 FMA) and the four wanted components selected.
+//
+// History, measured at 6.42 M blobs (profiles/r02_on_kernels.md): the thread-per-blob form spent ~95
+// instructions per blob (per-thread quaternion->rotation, integer division) and wrote 12 partial sectors
+// per store instruction -- 72 % issue-busy, 9 % of DRAM throughput, 27 us; a CTA per body with a thread per
+// output element and the rotation in shared memory coalesced the stores but needed 7 memory instructions
+// per element (3 LDS + 3 LDG + 1 STG) and sat on the LSU issue floor (1.82 cycles per memory instruction
+// and SM: 26.4 us predicted, 26.2 measured).
 template <typename real>
 __device__ __forceinline__ void place_one(const real* __restrict__ X, const real* __restrict__ Q,
                                           const real* __restrict__ ref, unsigned b, unsigned k, real (&p)[3]) {
@@ -174,12 +184,58 @@ __global__ void place_blobs_kernel(const real* __restrict__ X, const real* __res
   }
 }
 template <typename real>
+struct alignas(16) Row4 {
+  real x, y, z, w;
+};
+template <typename real, int G>
+__global__ void place_blobs_rows_kernel(const real* __restrict__ X, const real* __restrict__ Q,
+                                        const real* __restrict__ ref, unsigned n_bod, unsigned n3,
+                                        real* __restrict__ r) {
+  __shared__ Row4<real> RX[G][3];
+  const unsigned b0 = blockIdx.x * G;
+  const unsigned nb = n_bod - b0 < (unsigned)G ? n_bod - b0 : (unsigned)G;
+  if (threadIdx.x < nb) {
+    const size_t b = (size_t)b0 + threadIdx.x;
+    real R[9];
+    quat_to_rot(Q + 4 * b, R);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) RX[threadIdx.x][c] = Row4<real>{R[3 * c], R[3 * c + 1], R[3 * c + 2], X[3 * b + c]};
+  }
+  __syncthreads();
+  const unsigned e = blockIdx.y * blockDim.x + threadIdx.x;  // element of the body: blob k, component c
+  if (e >= n3) return;
+  const unsigned k = e / 3u, c = e - 3u * k;
+  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
+  real* __restrict__ out = r + (size_t)b0 * n3 + e;
+#pragma unroll 4
+  for (unsigned g = 0; g < nb; ++g) {
+    const Row4<real> row = RX[g][c];
+    out[(size_t)g * n3] = fma(row.x, cx, fma(row.y, cy, fma(row.z, cz, row.w)));  // same order as place_one
+  }
+}
+
+template <typename real>
 cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod, int n_blb,
                         real* r, cudaStream_t s) {
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
   const unsigned n_out = (unsigned)(3 * n);
+  static const int variant = [] {
+    const char* e = getenv("RBL_PLACE_VARIANT");
+    return e ? atoi(e) : 1;
+  }();
+  if (variant == 1) {
+    const unsigned n3 = 3u * (unsigned)n_blb;
+    const unsigned threads = n3 >= 256u ? 256u : ((n3 + 31u) / 32u) * 32u;
+    const unsigned wins = (n3 + threads - 1) / threads;
+    // 32 bodies per CTA amortise the reference point and the rotation set-up; 8 when that would leave SMs idle
+    if ((unsigned long long)((n_bod + 31) / 32) * wins >= 592ull)
+      place_blobs_rows_kernel<real, 32><<<dim3((unsigned)(n_bod + 31) / 32, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
+    else
+      place_blobs_rows_kernel<real, 8><<<dim3((unsigned)(n_bod + 7) / 8, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
+    return cudaGetLastError();
+  }
   const unsigned threads = 256, groups = (n_out + 3u) / 4u;
   if (reinterpret_cast<uintptr_t>(r) % 16 == 0)
     place_blobs_kernel<real, true><<<(groups + threads - 1) / threads, threads, 0, s>>>(X, Q, ref, (unsigned)n_blb, n_out, r);

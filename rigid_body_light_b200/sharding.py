@@ -235,6 +235,26 @@ class PartitionedRigidBody:
         counts = (ctypes.c_int * world)(*[(hi - lo) * self.n_blb for lo, hi in self.ranges])
         self.ctx.call("rbl_comm_init", ctypes.c_char_p(uid), rank, world, counts)
 
+    # -- the exchanges around every product (include/rbl.h: peer memory, or NCCL collectives) ------
+    @property
+    def exchange(self):
+        """'peer' (this library's kernels over NVLink peer memory), 'nccl', or 'none' (no communicator)."""
+        if self.ctx.L.rbl_comm_exchange(self.ctx.h):
+            return "peer"
+        return "none" if self.ctx.L.rbl_comm_exchange_why(self.ctx.h) == b"no communicator" else "nccl"
+
+    @property
+    def exchange_why(self):
+        return (self.ctx.L.rbl_comm_exchange_why(self.ctx.h) or b"").decode()
+
+    def set_exchange(self, mode):
+        """Collective: 'peer' or 'nccl' on every rank."""
+        self.ctx.call("rbl_comm_set_exchange", {"nccl": 0, "peer": 1}[mode])
+
+    def apply_saddle_dev(self, x_ptr, out_ptr):
+        """Device pointers, asynchronous on the context's stream (``rbl_dev_apply_saddle``); collective."""
+        self.ctx.call("rbl_dev_apply_saddle", x_ptr, out_ptr)
+
     # -- helpers ---------------------------------------------------------------------------
     def _in(self, v, n, what):
         v = np.ascontiguousarray(np.asarray(v, dtype=self.real).reshape(-1))

@@ -50,6 +50,14 @@ def main():
             one = RigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=block, precision=precision)
             part = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=True, block_PC=block,
                                         precision=precision, rank=rank, world=world, dist=dist, force_comm=True)
+            # the exchanges around every product: this library's peer-memory kernels where every rank could map
+            # every other rank's buffer, NCCL collectives otherwise (include/rbl.h).  The whole battery below runs
+            # with the default; the NCCL protocol is then checked against it on the saddle operator and a BD step.
+            exch = part.exchange
+            if rank == 0:
+                print(f"OBS world={world} exchange {precision} {block}: {exch} {part.exchange_why!r}", flush=True)
+            if os.environ.get("RBL_REQUIRE_PEER") == "1":
+                assert exch == "peer", part.exchange_why
             # saddle operator: against the single context AND against the CPU oracle (on the positions the
             # ranks placed and the inputs rounded to the run's precision, so that <= 1e-5 / 1e-12 applies)
             got = part.gather_system(part.apply_saddle(part.slice_system(vec)))
@@ -100,6 +108,22 @@ def main():
             X1, Q1 = one.get_config()
             chk(rel(Xp, X1[part.b0:part.b1]), 1e-14 if precision == "double" else 2e-7, "X after the step", precision, block)
             chk(rel(Qp, Q1[part.b0:part.b1]), 1e-14 if precision == "double" else 5e-7, "Q after the step", precision, block)
+            if exch == "peer":
+                # the same operators with the other protocol, switched at run time, at the configuration the step left
+                one_now = one.apply_saddle(vec)
+                for mode in ("nccl", "peer"):
+                    part.set_exchange(mode)
+                    assert part.exchange == mode
+                    got = part.gather_system(part.apply_saddle(part.slice_system(vec)))
+                    chk(rel(got, one_now), tol, f"saddle vs one context [{mode} after switch]", precision, block)
+                part.set_exchange("nccl")
+                U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, seed=99, step=3, tol=gt, restart=40,
+                                         max_iter=120, lanczos_tol=lt, lanczos_max_iter=80)
+                U1, it1, rr1 = one.bd_step(F_ext, kBT=0.0041, seed=99, step=3, tol=gt, restart=40, max_iter=120,
+                                           lanczos_tol=lt, lanczos_max_iter=80)
+                parts = [None] * world
+                dist.all_gather_object(parts, U)
+                chk(rel(np.concatenate(parts), U1), 1e-12 if precision == "double" else 2e-5, "seeded bd_step U [nccl]", precision, block)
             part.close()
     # a blob below the wall on ONE rank must surface as the same error on EVERY rank
     Xb = s["X"].copy()
