@@ -343,6 +343,21 @@ def run_ours(args):
         ctx.call("rbl_profile_matvec", 0)
         kern_ms = max_over_ranks(kern_ms)
         ms_step = ms_total / args.steps
+        if world > 1 and exchange["mode"] == "peer":
+            # the same timed loop with the NCCL collectives in place of the peer-memory exchange (same box, same
+            # process: the A/B the line reports next to `value`, which is the peer-memory number)
+            pb.set_exchange("nccl")
+            for _ in range(args.warmup):
+                step()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                step()
+            f1.record()
+            barrier()
+            exchange["ms_per_step_with_nccl_collectives"] = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+            pb.set_exchange("peer")
 
         # end to end: host buffers, copies inside the timed region
         nbytes = x_local.numel() * x_local.element_size()

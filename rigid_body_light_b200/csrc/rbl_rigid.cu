@@ -108,81 +108,18 @@ cudaError_t normalize_quats(real* Q, int n_bod, cudaStream_t s) {
 
 // r_{b,k} = R(q_b) ref_k + X_b   (get_r_vecs / single_body_pos / multi_body_pos, c_rigid_obj.cpp:257-300).
 //
-// Two forms, chosen by the launcher (RBL_PLACE_VARIANT=0/1 overrides, for A/B measurements).
+// A CTA owns G consecutive bodies and a 256-wide window of the 3 n_blb reals of a body.  The first G threads
+// turn the G quaternions into rotation rows [R_c0 R_c1 R_c2 X_c] in shared memory (one 16/32-byte row per
+// output component); every thread then owns ONE element (k, c) of the window -- its reference point ref_k sits
+// in three registers -- and walks over the G bodies: one broadcast LDS.128 (three distinct rows per warp), three
+// FMA, one coalesced STG per element, i.e. two memory instructions per element.
 //
-// (1, default) place_blobs_rows_kernel: a CTA owns G consecutive bodies and a 256-wide window of the
-// 3 n_blb reals of a body.  The first G threads turn the G quaternions into rotation rows [R_c0 R_c1 R_c2 X_c]
-// in shared memory (one 16/32-byte row per output component); every thread then owns ONE element (k, c) of
-// the window -- its reference point ref_k sits in three registers -- and walks over the G bodies: one
-// broadcast LDS.128 (three distinct rows per warp), three FMA, one coalesced STG per element.  Two memory
-// instructions per element against seven for a thread per element that re-reads ref and R per body.
-//
-// (0) place_blobs_kernel: every thread produces FOUR CONSECUTIVE reals of the flat output (one 128-bit
-// store in fp32, two in fp64): they belong to two consecutive blobs (k0, c0..2) and (k1, ...), whose
-// positions are computed in full (18 FMA) and the four wanted components selected.
-//
-// History, measured at 6.42 M blobs (profiles/r02_on_kernels.md): the thread-per-blob form spent ~95
-// instructions per blob (per-thread quaternion->rotation, integer division) and wrote 12 partial sectors
-// per store instruction -- 72 % issue-busy, 9 % of DRAM throughput, 27 us; a CTA per body with a thread per
-// output element and the rotation in shared memory coalesced the stores but needed 7 memory instructions
-// per element (3 LDS + 3 LDG + 1 STG) and sat on the LSU issue floor (1.82 cycles per memory instruction
-// and SM: 26.4 us predicted, 26.2 measured).
-template <typename real>
-__device__ __forceinline__ void place_one(const real* __restrict__ X, const real* __restrict__ Q,
-                                          const real* __restrict__ ref, unsigned b, unsigned k, real (&p)[3]) {
-  real R[9];
-  quat_to_rot(Q + 4 * (size_t)b, R);
-  const real cx = ref[3 * k], cy = ref[3 * k + 1], cz = ref[3 * k + 2];
-  p[0] = fma(R[0], cx, fma(R[1], cy, fma(R[2], cz, X[3 * (size_t)b + 0])));
-  p[1] = fma(R[3], cx, fma(R[4], cy, fma(R[5], cz, X[3 * (size_t)b + 1])));
-  p[2] = fma(R[6], cx, fma(R[7], cy, fma(R[8], cz, X[3 * (size_t)b + 2])));
-}
-__device__ __forceinline__ void store4(float* o, float a, float b, float c, float d) {
-  *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d);
-}
-__device__ __forceinline__ void store4(double* o, double a, double b, double c, double d) {
-  reinterpret_cast<double2*>(o)[0] = make_double2(a, b);
-  reinterpret_cast<double2*>(o)[1] = make_double2(c, d);
-}
-template <typename real, bool ALIGNED>
-__global__ void place_blobs_kernel(const real* __restrict__ X, const real* __restrict__ Q,
-                                   const real* __restrict__ ref, unsigned n_blb, unsigned n_out,
-                                   real* __restrict__ r) {
-  // 32-bit index arithmetic on purpose (a 64-bit division is a ~100-instruction routine); 3N < 2^31 is
-  // checked by the launcher
-  const unsigned e0 = 4u * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (e0 >= n_out) return;
-  const unsigned g0 = e0 / 3u, c0 = e0 - 3u * g0;      // global blob of the first element, its component
-  const unsigned b0 = g0 / n_blb, k0 = g0 - b0 * n_blb;
-  const unsigned last = n_out / 3u - 1u;
-  const unsigned g1 = g0 < last ? g0 + 1u : last;        // the next blob (clamped at the end of the array)
-  unsigned b1 = b0, k1 = k0 + 1u;
-  if (k1 == n_blb) { b1 = b0 + 1u; k1 = 0u; }
-  if (g1 == g0) { b1 = b0; k1 = k0; }
-  real p0[3], p1[3];
-  place_one(X, Q, ref, b0, k0, p0);
-  if (b1 == b0) {  // same body (the common case): one rotation matrix for both blobs
-    real R[9];
-    quat_to_rot(Q + 4 * (size_t)b0, R);
-    const real cx = ref[3 * k1], cy = ref[3 * k1 + 1], cz = ref[3 * k1 + 2];
-    p1[0] = fma(R[0], cx, fma(R[1], cy, fma(R[2], cz, X[3 * (size_t)b0 + 0])));
-    p1[1] = fma(R[3], cx, fma(R[4], cy, fma(R[5], cz, X[3 * (size_t)b0 + 1])));
-    p1[2] = fma(R[6], cx, fma(R[7], cy, fma(R[8], cz, X[3 * (size_t)b0 + 2])));
-  } else {
-    place_one(X, Q, ref, b1, k1, p1);
-  }
-  // the four consecutive components starting at (g0, c0)
-  const real o0 = c0 == 0 ? p0[0] : (c0 == 1 ? p0[1] : p0[2]);
-  const real o1 = c0 == 0 ? p0[1] : (c0 == 1 ? p0[2] : p1[0]);
-  const real o2 = c0 == 0 ? p0[2] : (c0 == 1 ? p1[0] : p1[1]);
-  const real o3 = c0 == 0 ? p1[0] : (c0 == 1 ? p1[1] : p1[2]);
-  if (ALIGNED && e0 + 4u <= n_out) {
-    store4(r + e0, o0, o1, o2, o3);
-  } else {  // tail of the array (3N is not a multiple of 4), or an output pointer that is not 16-byte aligned
-    const real o[4] = {o0, o1, o2, o3};
-    for (unsigned j = 0; e0 + j < n_out; ++j) r[e0 + j] = o[j];
-  }
-}
+// History, all measured at 6.42 M blobs (profiles/r02_on_kernels.md; a fill of the same buffer takes 13.8 /
+// 24.9 us in fp32 / fp64): thread per blob (~95 instructions per blob for a per-thread quaternion->rotation
+// and an integer division, 12 partial sectors per store instruction, 72 % issue-busy) 27 / 47 us; CTA per body,
+// thread per element re-reading ref and R per element (7 memory instructions per element: the LSU issue
+// floor) 26 / 45 us; four consecutive outputs per thread with 128-bit stores 32 / 52 us; this form 18.3 /
+// 31.2 us.
 template <typename real>
 struct alignas(16) Row4 {
   real x, y, z, w;
@@ -210,7 +147,7 @@ __global__ void place_blobs_rows_kernel(const real* __restrict__ X, const real* 
 #pragma unroll 4
   for (unsigned g = 0; g < nb; ++g) {
     const Row4<real> row = RX[g][c];
-    out[(size_t)g * n3] = fma(row.x, cx, fma(row.y, cy, fma(row.z, cz, row.w)));  // same order as place_one
+    out[(size_t)g * n3] = fma(row.x, cx, fma(row.y, cy, fma(row.z, cz, row.w)));
   }
 }
 
@@ -220,27 +157,15 @@ cudaError_t place_blobs(const real* X, const real* Q, const real* ref, int n_bod
   const long long n = (long long)n_bod * n_blb;
   if (n <= 0) return cudaSuccess;
   if (n > 0x7fffffffLL / 3) return cudaErrorInvalidValue;
-  const unsigned n_out = (unsigned)(3 * n);
-  static const int variant = [] {
-    const char* e = getenv("RBL_PLACE_VARIANT");
-    return e ? atoi(e) : 1;
-  }();
-  if (variant == 1) {
-    const unsigned n3 = 3u * (unsigned)n_blb;
-    const unsigned threads = n3 >= 256u ? 256u : ((n3 + 31u) / 32u) * 32u;
-    const unsigned wins = (n3 + threads - 1) / threads;
-    // 32 bodies per CTA amortise the reference point and the rotation set-up; 8 when that would leave SMs idle
-    if ((unsigned long long)((n_bod + 31) / 32) * wins >= 592ull)
-      place_blobs_rows_kernel<real, 32><<<dim3((unsigned)(n_bod + 31) / 32, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
-    else
-      place_blobs_rows_kernel<real, 8><<<dim3((unsigned)(n_bod + 7) / 8, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
-    return cudaGetLastError();
-  }
-  const unsigned threads = 256, groups = (n_out + 3u) / 4u;
-  if (reinterpret_cast<uintptr_t>(r) % 16 == 0)
-    place_blobs_kernel<real, true><<<(groups + threads - 1) / threads, threads, 0, s>>>(X, Q, ref, (unsigned)n_blb, n_out, r);
+  const unsigned n3 = 3u * (unsigned)n_blb;
+  const unsigned threads = n3 >= 256u ? 256u : ((n3 + 31u) / 32u) * 32u;
+  const unsigned wins = (n3 + threads - 1) / threads;
+  if (wins > 65535u) return cudaErrorInvalidValue;  // (5.5 M blobs in ONE body)
+  // 32 bodies per CTA amortise the reference point and the rotation set-up; 8 when that would leave SMs idle
+  if ((unsigned long long)((n_bod + 31) / 32) * wins >= 592ull)
+    place_blobs_rows_kernel<real, 32><<<dim3((unsigned)(n_bod + 31) / 32, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
   else
-    place_blobs_kernel<real, false><<<(groups + threads - 1) / threads, threads, 0, s>>>(X, Q, ref, (unsigned)n_blb, n_out, r);
+    place_blobs_rows_kernel<real, 8><<<dim3((unsigned)(n_bod + 7) / 8, wins), threads, 0, s>>>(X, Q, ref, (unsigned)n_bod, n3, r);
   return cudaGetLastError();
 }
 
@@ -248,7 +173,7 @@ template <typename real>
 __global__ void k_dot_kernel(const real* __restrict__ U, const real* __restrict__ r,
                              const real* __restrict__ X, int n_bod, int n_blb, real sign,
                              const real* add, real* out) {  // add may alias out
-  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: see place_blobs_kernel
+  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: a 64-bit division is a ~100-instruction routine; 3N < 2^31 is checked by the launcher
   if (iu >= (unsigned)n_bod * (unsigned)n_blb) return;
   const unsigned b = iu / (unsigned)n_blb;
   const size_t i = iu;
@@ -419,7 +344,7 @@ cudaError_t pc_diag_mul(const real* dinv, const real* in, int n_bod, int n_blb, 
 template <typename real>
 __global__ void pc_fill_kcols_kernel(const real* __restrict__ r, const real* __restrict__ X,
                                      int n_bod, int n_blb, real* __restrict__ Kc) {
-  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: see place_blobs_kernel
+  const unsigned iu = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit: a 64-bit division is a ~100-instruction routine; 3N < 2^31 is checked by the launcher
   if (iu >= (unsigned)n_bod * (unsigned)n_blb) return;
   const unsigned b = iu / (unsigned)n_blb, k = iu - b * (unsigned)n_blb;
   const size_t i = iu;

@@ -32,8 +32,12 @@ def main():
             par = d.get("parity") or {}
             par64 = f64.get("parity") or {}
             ps = "-" if not par else f"{par['rel_err']:.1e} / " + (f"{par64['rel_err']:.1e}" if par64 else "-") + f" ({par['rows']} rows)"
+            ex = d.get("exchange") or {}
+            xs = "-" if d["n_gpus"] == 1 else (ex.get("mode") or "nccl (torch.distributed)")
+            if ex.get("ms_per_step_with_nccl_collectives"):
+                xs += f" (same run with NCCL: {ex['ms_per_step_with_nccl_collectives']:.2f} ms/step)"
             rows.append((name, d["n_gpus"], wl, d["value"] / 1e9, d["ms_per_step"], d["e2e"]["value"] / 1e9, d["roofline"]["frac"],
-                         f64.get("value", 0) / 1e9, f64.get("ms_per_step"), (f64.get("roofline") or {}).get("frac"), cs, ps))
+                         f64.get("value", 0) / 1e9, f64.get("ms_per_step"), (f64.get("roofline") or {}).get("frac"), cs, ps, xs))
         bd = d.get("bd_step")
         if bd:
             for p in ("single", "double", "double_mixed1", "double_mixed2"):
@@ -44,11 +48,11 @@ def main():
     out = [f"# Round {int(rnd[1:])} -- bench lines (B200)\n",
            "Full JSON lines: `" + rnd + "_bench_*.json`.  Gpairs/s = ordered blob pairs per second, whole job; frac = N^2 x 127 flop "
            "(35 free space) / kernel time / FMA peak measured live.\n",
-           "| run | GPUs | workload | fp32 Gpairs/s | ms/step | fp32 e2e Gpairs/s | fp32 frac | fp64 Gpairs/s | ms/step | fp64 frac | all-gather / reduce us per step (fp32) | oracle parity fp32 / fp64 (sampled rows) |",
-           "|---|---:|---|---:|---:|---:|---:|---:|---:|---:|---|---|"]
+           "| run | GPUs | workload | fp32 Gpairs/s | ms/step | fp32 e2e Gpairs/s | fp32 frac | fp64 Gpairs/s | ms/step | fp64 frac | gather / reduce us per step (fp32, max over ranks, incl. waiting for the slowest rank) | oracle parity fp32 / fp64 (sampled rows) | exchange around the product |",
+           "|---|---:|---|---:|---:|---:|---:|---:|---:|---:|---|---|---|"]
     for r in rows:
         f = lambda v, fmt: "-" if v in (None, 0) else format(v, fmt)  # noqa: E731
-        out.append(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.1f} | {r[4]:.2f} | {r[5]:.1f} | {r[6]:.3f} | {f(r[7], '.1f')} | {f(r[8], '.2f')} | {f(r[9], '.3f')} | {r[10]} | {r[11]} |")
+        out.append(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.1f} | {r[4]:.2f} | {r[5]:.1f} | {r[6]:.3f} | {f(r[7], '.1f')} | {f(r[8], '.2f')} | {f(r[9], '.3f')} | {r[10]} | {r[11]} | {r[12]} |")
     base = {(r[2]): r for r in rows if r[1] == 1}
     eff = []
     for r in rows:
