@@ -27,7 +27,7 @@ partitioned over the ranks, seconds per step.
             oracle on the inputs the GPU saw; raises above 1e-5 (float) / 1e-12 (double).  The oracle is the
             checker here, outside every timed region.
 `bd_step` : one warm-up + three timed full BD steps (min / mean / max), then one untimed profiled step
-            (wall clock per phase, summed product-kernel time); at N = 1 the double step also with mixed
+            (wall clock per phase, summed product-kernel time); the double step also with mixed
             precision modes 1 and 2 (include/rbl.h rbl_set_mixed_precision).
 `cpu_baseline` / --impl reference: the reference's own dense 3N x 3N assembly + GEMV
             (rotne_prager_tensor / make_damp_mat / apply_M, c_rigid_obj.cpp:413-459,618-659, compiled
@@ -350,12 +350,16 @@ def run_ours(args):
             for _ in range(args.warmup):
                 step()
             barrier()
+            ctx.call("rbl_profile_matvec", 1)  # the same event records between the kernels as in the loop above
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record()
             for _ in range(args.steps):
                 step()
             f1.record()
             barrier()
+            ctx.matvec_profile(reset=True)
+            ctx.call("rbl_comm_profile", None, None, 1)
+            ctx.call("rbl_profile_matvec", 0)
             exchange["ms_per_step_with_nccl_collectives"] = max_over_ranks(f0.elapsed_time(f1)) / args.steps
             pb.set_exchange("peer")
 
@@ -515,8 +519,8 @@ def bd_step_leg(args, rank, world, dist, local_rank, precisions):
            "unit": "s/step", "higher_is_better": False, "n_gpus": world, "steps": args.bd_steps,
            "warmup_steps": 1 if args.bd_warmup else 0, "exchange": None}
     legs = [(p, 0) for p in precisions]
-    if "double" in precisions and world == 1 and args.bd_mixed:
-        legs += [("double", 1), ("double", 2)]  # mixed precision: single-GPU double contexts
+    if "double" in precisions and args.bd_mixed:
+        legs += [("double", 1), ("double", 2)]  # mixed precision (the float mirror shares the communicator at N > 1)
     for precision, mixed in legs:
         tol, ltol = (1e-4, 1e-4) if precision == "single" else (1e-8, 1e-6)
         pb = PartitionedRigidBody(s["cfg"], s["X"], s["Q"], s["a"], 1.0, 0.01, wall_PC=wall, block_PC=True,

@@ -167,8 +167,9 @@ int rbl_evolve_RFD(rbl_ctx* ctx, const void* U);
  * float is most accurate near eps^(1/3) x (length over which M varies ~ the body radius): rounding
  * 3e-7 |M W| / delta against truncation ~ (delta/a)^2 / 6. */
 int rbl_set_rfd_delta(rbl_ctx* ctx, double delta);
-/* Mixed precision for DOUBLE contexts on one GPU (ignored on a partitioned suspension).  The context keeps a
- * float mirror of itself (same parameters, flags, configuration; same stream):
+/* Mixed precision for DOUBLE contexts.  The context keeps a float mirror of itself (same parameters, flags,
+ * configuration; same stream; on a partitioned suspension the mirror shares the context's communicator and
+ * sets up its own float-sized peer buffers -- collective: every rank the same mode at the same point):
  *   0 (default) everything in double;
  *   1 rbl_gmres / the solve of rbl_bd_step: float GMRES corrections inside an iterative refinement whose
  *     residual b - apply_saddle(x) is evaluated in DOUBLE; stops on the same ||b - A x|| / ||b|| <= tol;

@@ -1158,7 +1158,7 @@ struct Ctx final : rbl_ctx {
     mixed = mode;
     return RBL_OK;
   }
-  bool use_mixed(int level) const { return sizeof(real) == 8 && mixed >= level && !comm; }
+  bool use_mixed(int level) const { return sizeof(real) == 8 && mixed >= level; }
   // bring the float mirror to this context's parameters, flags and CURRENT configuration
   int sync_shadow() {
     if constexpr (std::is_same<real, double>::value) {
@@ -1175,9 +1175,19 @@ struct Ctx final : rbl_ctx {
         std::vector<float> rf(ref_host.begin(), ref_host.end());
         st = sh->set_parameters(a, dt, kBT, eta, rf.data(), n_blb);
         if (st != RBL_OK) { err = sh->err; delete sh; return st; }
+        if (comm) {
+          // partitioned suspension: the mirror shares this context's communicator (same ranks, same stream
+          // order -- every rank builds its mirror at the same point of the same driver) and sets up its own,
+          // float-sized, peer buffers; it follows this context's choice of exchange
+          if (cudaSuccess != sh->d_status.ensure(4 * sizeof(int))) { cudaGetLastError(); delete sh; return fail(RBL_ERR_NOMEM, "mixed precision: out of device memory"); }
+          sh->comm = comm->share();
+          sh->comm->peer_setup(sizeof(float), sh->d_status.template as<int>(), stream);
+        }
         shadow = sh;
         shadow_gen = 0;
       }
+      if (comm && shadow->comm) shadow->comm->peer.use = shadow->comm->peer.on && comm->peer_active();
+      shadow->stream = stream;  // (rbl_set_stream may have moved this context since the mirror was built)
       shadow->set_flags(block_pc ? 1 : 0, wall ? 1 : 0);
       shadow->noise_mode = 0;
       if (shadow_gen != cfg_gen || shadow->n_bod != n_bod) {

@@ -42,6 +42,7 @@ struct PeerExchange {
 struct Comm {
   void* lib = nullptr;
   ncclComm_t comm = nullptr;
+  bool owns_comm = true;  // false: a view on another context's communicator (share())
   int rank = 0, world = 1;
   std::vector<long long> count;  // blobs held by each rank
   std::vector<long long> first;  // first global blob of each rank
@@ -64,8 +65,33 @@ struct Comm {
   const char* (*pGetErrorString)(ncclResult_t) = nullptr;
 
   ~Comm() {
-    if (comm && pCommDestroy) pCommDestroy(comm);
+    if (comm && pCommDestroy && owns_comm) pCommDestroy(comm);
     // the library handle is left open on purpose: torch may share it
+  }
+  // A second view on the same NCCL communicator for the float mirror of a double context (mixed
+  // precision): same ranks and blob ranges, same stream order, its own (float-sized) peer buffers.
+  Comm* share() const {
+    Comm* c = new Comm();
+    c->lib = lib;
+    c->comm = comm;
+    c->owns_comm = false;
+    c->rank = rank;
+    c->world = world;
+    c->count = count;
+    c->first = first;
+    c->n_all = n_all;
+    c->even = even;
+    c->pCommInitRank = pCommInitRank;
+    c->pCommDestroy = pCommDestroy;
+    c->pAllGather = pAllGather;
+    c->pAllReduce = pAllReduce;
+    c->pReduceScatter = pReduceScatter;
+    c->pBroadcast = pBroadcast;
+    c->pReduce = pReduce;
+    c->pGroupStart = pGroupStart;
+    c->pGroupEnd = pGroupEnd;
+    c->pGetErrorString = pGetErrorString;
+    return c;
   }
 
   // ---- peer-memory exchange ------------------------------------------------------------------

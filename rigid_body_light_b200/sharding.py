@@ -286,7 +286,8 @@ class PartitionedRigidBody:
         return join_system(parts, self.ranges)
 
     def set_mixed_precision(self, mode):
-        """see Rigid.RigidBody.set_mixed_precision (single-GPU double contexts; ignored when partitioned)"""
+        """see Rigid.RigidBody.set_mixed_precision (double contexts; on a partitioned suspension the float mirror
+        shares the communicator -- collective, every rank the same mode)"""
         self.ctx.call("rbl_set_mixed_precision", int(mode))
 
     def get_blob_positions(self):

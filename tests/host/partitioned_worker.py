@@ -124,6 +124,22 @@ def main():
                 parts = [None] * world
                 dist.all_gather_object(parts, U)
                 chk(rel(np.concatenate(parts), U1), 1e-12 if precision == "double" else 2e-5, "seeded bd_step U [nccl]", precision, block)
+                part.set_exchange("peer")
+            if precision == "double":
+                # mixed precision on the partitioned suspension (the float mirror shares the communicator and has
+                # its own peer buffers): against the all-double single context, same (seed, step)
+                for mode in (1, 2):
+                    part.set_mixed_precision(mode)
+                    U, it, rr = part.bd_step(part.slice_bodies(F_ext), kBT=0.0041, seed=77, step=mode, tol=gt, restart=40,
+                                             max_iter=120, lanczos_tol=lt, lanczos_max_iter=80)
+                    U1, it1, rr1 = one.bd_step(F_ext, kBT=0.0041, seed=77, step=mode, tol=gt, restart=40, max_iter=120,
+                                               lanczos_tol=lt, lanczos_max_iter=80)
+                    assert rr <= gt, ("mixed bd_step relres", mode, rr)
+                    parts = [None] * world
+                    dist.all_gather_object(parts, U)
+                    # mode 1: same stopping rule on the double residual; mode 2: float-rounded operator under the root
+                    chk(rel(np.concatenate(parts), U1), 2e-9 if mode == 1 else 3e-6, f"bd_step U [mixed {mode}]", precision, block)
+                part.set_mixed_precision(0)
             part.close()
     # a blob below the wall on ONE rank must surface as the same error on EVERY rank
     Xb = s["X"].copy()
