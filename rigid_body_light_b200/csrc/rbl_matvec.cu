@@ -916,7 +916,7 @@ int matvec_sym_num_variants<double>() {
   return n;
 }
 
-// defaults measured on B200 at 162 000 blobs (profiles/r02_probe_variants.md): fp32 (6,256,16) with and
+// defaults measured on B200 at 162 000 blobs (profiles/r02_probe_variants_cfg2.jsonl, profiles/r02_ncu_variants.md): fp32 (6,256,16) with and
 // without the wall; fp64 (4,256,16) with the wall, (3,256,16) in free space; small problems take the
 // smallest target tile (the last variant) so that the unit triangle still covers the SMs
 template <>

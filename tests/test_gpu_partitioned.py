@@ -40,3 +40,16 @@ def test_partitioned_multi_gpu_matches_single_context(world, n_bodies):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     _run(world, n_bodies)
+
+
+def test_exchange_entry_points_without_a_communicator():
+    """A context that never called rbl_comm_init reports no exchange and refuses to switch."""
+    from rigid_body_light_b200._lib import Context, RblError
+
+    ctx = Context("single")
+    assert ctx.L.rbl_comm_exchange(ctx.h) == 0
+    assert ctx.L.rbl_comm_exchange_why(ctx.h) == b"no communicator"
+    assert ctx.L.rbl_comm_world(ctx.h) == 1
+    with pytest.raises(RblError, match="no communicator"):
+        ctx.call("rbl_comm_set_exchange", 1)
+    ctx.close()
