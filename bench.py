@@ -344,24 +344,29 @@ def run_ours(args):
         kern_ms = max_over_ranks(kern_ms)
         ms_step = ms_total / args.steps
         if world > 1 and exchange["mode"] == "peer":
-            # the same timed loop with the NCCL collectives in place of the peer-memory exchange (same box, same
-            # process: the A/B the line reports next to `value`, which is the peer-memory number)
-            pb.set_exchange("nccl")
-            for _ in range(args.warmup):
-                step()
-            barrier()
-            ctx.call("rbl_profile_matvec", 1)  # the same event records between the kernels as in the loop above
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(args.steps):
-                step()
-            f1.record()
-            barrier()
-            ctx.matvec_profile(reset=True)
-            ctx.call("rbl_comm_profile", None, None, 1)
-            ctx.call("rbl_profile_matvec", 0)
-            exchange["ms_per_step_with_nccl_collectives"] = max_over_ranks(f0.elapsed_time(f1)) / args.steps
-            pb.set_exchange("peer")
+            # A/B in the same process, AFTER the loop that `value` reports: the same timed loop with the NCCL
+            # collectives in place of the peer-memory exchange, then with the peer-memory exchange once more (the
+            # repeat shows how much of any difference to `value` is the order of the loops, not the protocol;
+            # tools/exchange_ab.py alternates the two on the same contexts)
+            def timed_loop(mode):
+                pb.set_exchange(mode)
+                for _ in range(args.warmup):
+                    step()
+                barrier()
+                ctx.call("rbl_profile_matvec", 1)  # the same event records between the kernels as in the loop above
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(args.steps):
+                    step()
+                f1.record()
+                barrier()
+                ctx.matvec_profile(reset=True)
+                ctx.call("rbl_comm_profile", None, None, 1)
+                ctx.call("rbl_profile_matvec", 0)
+                return max_over_ranks(f0.elapsed_time(f1)) / args.steps
+
+            exchange["ms_per_step_with_nccl_collectives"] = timed_loop("nccl")
+            exchange["ms_per_step_peer_repeated_after_nccl"] = timed_loop("peer")
 
         # end to end: host buffers, copies inside the timed region
         nbytes = x_local.numel() * x_local.element_size()

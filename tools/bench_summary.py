@@ -35,7 +35,8 @@ def main():
             ex = d.get("exchange") or {}
             xs = "-" if d["n_gpus"] == 1 else (ex.get("mode") or "nccl (torch.distributed)")
             if ex.get("ms_per_step_with_nccl_collectives"):
-                xs += f" (same run with NCCL: {ex['ms_per_step_with_nccl_collectives']:.2f} ms/step)"
+                xs += f" (same run with NCCL: {ex['ms_per_step_with_nccl_collectives']:.2f} ms/step" + (
+                    f", peer again after it: {ex['ms_per_step_peer_repeated_after_nccl']:.2f}" if ex.get("ms_per_step_peer_repeated_after_nccl") else "") + ")"
             rows.append((name, d["n_gpus"], wl, d["value"] / 1e9, d["ms_per_step"], d["e2e"]["value"] / 1e9, d["roofline"]["frac"],
                          f64.get("value", 0) / 1e9, f64.get("ms_per_step"), (f64.get("roofline") or {}).get("frac"), cs, ps, xs))
         bd = d.get("bd_step")
