@@ -507,5 +507,6 @@ def test_block_pc_on_indefinite_body_blocks(orc, precision):
     out = cb.apply_PC(vec.astype(ndt))
     err = rel_err(out, want)
     print(f"[{precision}] block PC on indefinite blocks: error {err:.3e}, cond(per-body saddle matrix) up to {max(conds):.1e}")
-    check(err, 1e-12 if precision == "double" else 1e-4,
+    # float: observed 7.0e-5 on B200 = 0.16 x (eps_f32 x cond); the bound below is 4 x observed
+    check(err, 1e-12 if precision == "double" else 3e-4,
           f"pivoted block PC vs exact per-body saddle inverse, cond {max(conds):.1e}")
